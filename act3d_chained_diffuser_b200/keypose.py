@@ -1,0 +1,291 @@
+"""Act3D keypose detector on the B200 kernels -- drop-in for the reference's
+model/keypose_optimization/act3d.py (same ctor kwargs, forward signature, output dict and
+state_dict keys).
+
+Host code is PyTorch (backbone/FPN through cuDNN, tiny token encoders, the action head); the
+coarse-to-fine loop itself -- point pyramid, local top-k, gather, K/V cache with 3-D rotary, the
+fused ghost-point / query cross-attention stacks, mask logits, top-ghost pick and the ghost
+sampler -- runs in libact3d_b200.so with no host synchronisation between levels.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torchvision.ops import FeaturePyramidNetwork
+
+from . import lib
+from .packing import PackCache, pack_kv_set, pack_xattn_layer
+from .params import XAttnStackParams, mlp
+from .rotations import normalise_quat, ortho6d_to_matrix
+from .trunk import build_backbone
+
+
+def _shared_or_separate(n, tie, factory):
+    if tie:
+        one = factory()
+        return nn.ModuleList(one for _ in range(n))
+    return nn.ModuleList(factory() for _ in range(n))
+
+
+class Act3D(nn.Module):
+
+    def __init__(self, backbone="clip", image_size=(256, 256), embedding_dim=60, num_attn_heads=4,
+                 num_ghost_point_cross_attn_layers=2, num_query_cross_attn_layers=2, num_vis_ins_attn_layers=2,
+                 rotation_parametrization="quat_from_query", gripper_loc_bounds=None, num_ghost_points=1000,
+                 num_ghost_points_val=10000, weight_tying=True, gp_emb_tying=True, ins_pos_emb=False,
+                 num_sampling_level=3, fine_sampling_ball_diameter=0.16, regress_position_offset=False,
+                 use_instruction=False):
+        super().__init__()
+        if backbone not in ("resnet", "clip"):
+            raise AssertionError(backbone)
+        image_size = tuple(image_size)
+        if image_size != (256, 256):
+            # the reference asserts {(128,128),(256,256)} but its 128x128 branch is broken
+            raise AssertionError("image_size must be (256, 256)")
+        if rotation_parametrization not in ("quat_from_top_ghost", "quat_from_query", "6D_from_top_ghost", "6D_from_query"):
+            raise AssertionError(rotation_parametrization)
+        if num_sampling_level not in (1, 2, 3, 4):
+            raise AssertionError(num_sampling_level)
+        if embedding_dim % 6 or embedding_dim // num_attn_heads != 15 or embedding_dim % num_attn_heads:
+            raise NotImplementedError("the sm_100a kernels are built for head_dim 15 (embedding_dim=60, 4 heads)")
+        if ins_pos_emb:
+            raise NotImplementedError("ins_pos_emb is off in every shipped configuration and is not built")
+
+        self.image_size = image_size
+        self.rotation_parametrization = rotation_parametrization
+        self.num_ghost_points = num_ghost_points // num_sampling_level
+        self.num_ghost_points_val = num_ghost_points_val // num_sampling_level
+        self.num_sampling_level = num_sampling_level
+        d = fine_sampling_ball_diameter
+        self.sampling_ball_diameter_pyramid = [None, d, d / 4.0, d / 16.0]
+        self.gripper_loc_bounds = np.array(gripper_loc_bounds)
+        self.regress_position_offset = regress_position_offset
+        self.weight_tying, self.gp_emb_tying, self.ins_pos_emb = weight_tying, gp_emb_tying, ins_pos_emb
+        self.use_instruction = use_instruction
+        self.embedding_dim, self.num_attn_heads = embedding_dim, num_attn_heads
+
+        self.backbone, self.normalize = build_backbone(backbone)
+        for p in self.backbone.parameters():
+            p.requires_grad = False
+        self.feature_pyramid = FeaturePyramidNetwork([64, 256, 512, 1024, 2048], embedding_dim)
+        self.feature_map_pyramid = ["res3", "res1", "res1", "res1"]
+        self.downscaling_factor_pyramid = [8, 2, 2, 2]
+
+        e, h, n = embedding_dim, num_attn_heads, num_sampling_level
+        self.ghost_points_embed_pyramid = _shared_or_separate(n, gp_emb_tying, lambda: nn.Embedding(1, e))
+        self.curr_gripper_embed = nn.Embedding(1, e)
+        self.query_embed = nn.Embedding(1, e)
+        self.ghost_point_cross_attn_pyramid = _shared_or_separate(
+            n, weight_tying, lambda: XAttnStackParams(e, h, num_ghost_point_cross_attn_layers))
+        if use_instruction:
+            self.vis_ins_attn_pyramid = _shared_or_separate(
+                n, weight_tying, lambda: XAttnStackParams(e, h, num_vis_ins_attn_layers))
+        self.query_cross_attn_pyramid = _shared_or_separate(
+            n, weight_tying, lambda: XAttnStackParams(e, h, num_query_cross_attn_layers))
+        if regress_position_offset:
+            self.ghost_point_offset_predictor = mlp(e, e, 3)
+        self.rotation_dim = 4 if "quat" in rotation_parametrization else 6
+        self.gripper_state_predictor = mlp(e, e, self.rotation_dim + 1)
+        if use_instruction:
+            self.instruction_encoder = nn.Linear(512, e)
+
+        # not part of the state_dict
+        self._packs = PackCache()
+        self._sampler_seed = 0x5EED
+        self._sampler_calls = 0
+        self._teacher_positions = None      # test hook: list of (B,1,3) fed to the next level
+        self._last_topk = None              # debug/test hook: top-k indices per level of the last call
+
+    # ------------------------------------------------------------------ packed weights
+    def _stack_pack(self, tag, stack):
+        params = list(stack.parameters())
+        e, h = self.embedding_dim, self.num_attn_heads
+
+        def build():
+            layers = [pack_xattn_layer(stack.attn_layers[l].multihead_attn, stack.attn_layers[l].norm,
+                                       stack.ffw_layers[l], e, h) for l in range(stack.num_layers)]
+            kv = [pack_kv_set(stack.attn_layers[l].multihead_attn, e, h) for l in range(stack.num_layers)]
+            return dict(w=torch.cat(layers).contiguous(), wkv=torch.stack([k[0] for k in kv]),
+                        bkv=torch.stack([k[1] for k in kv]))
+        return self._packs.get(tag, params, build)
+
+    # ------------------------------------------------------------------ sampling
+    def seed_ghost_sampler(self, seed):
+        """Seed of the device-side Philox ghost sampler (the reference draws from numpy's global RNG)."""
+        self._sampler_seed, self._sampler_calls = int(seed), 0
+
+    def _sample_ghost_points(self, total_timesteps, device, level, anchor=None):
+        """(B, Ng, 3) uniform ghost points; same contract as act3d.py:394-440 but sampled on the
+        device (no anchor.cpu() round trip).  Ng switches on self.training like the reference."""
+        n = self.num_ghost_points if self.training else self.num_ghost_points_val
+        self._sampler_calls += 1
+        if level == 0:
+            return lib.sample_ghost(None, 0.0, self.gripper_loc_bounds, total_timesteps, n,
+                                    self._sampler_seed, self._sampler_calls, device)
+        anc = anchor[:, 0].detach().contiguous().float()
+        return lib.sample_ghost(anc, self.sampling_ball_diameter_pyramid[level] / 2, self.gripper_loc_bounds,
+                                total_timesteps, n, self._sampler_seed, self._sampler_calls, device)
+
+    # ------------------------------------------------------------------ visual trunk
+    def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras):
+        """backbone + FPN (PyTorch) and the point pyramid (kernel).  Unlike act3d.py:359-392 no
+        rotary table is built here: angles are evaluated inside the K/V kernel for the tokens that
+        are actually attended to."""
+        b = visible_rgb.shape[0]
+        rgb = visible_rgb.reshape(b * num_cameras, *visible_rgb.shape[2:])
+        feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        pcd = visible_pcd.reshape(b * num_cameras, *visible_pcd.shape[2:]).contiguous().float()
+        feats_pyr, pcd_pyr, cache = [], [], {}
+        for i in range(self.num_sampling_level):
+            f = self.downscaling_factor_pyramid[i]
+            if f not in cache:
+                cache[f] = lib.pcd_pyramid(pcd, f).view(b, -1, 3)
+            fm = feats[self.feature_map_pyramid[i]].contiguous().float()
+            feats_pyr.append(fm.view(b, num_cameras, *fm.shape[1:]))
+            pcd_pyr.append(cache[f])
+        return feats_pyr, pcd_pyr
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action=None):
+        """
+        visible_rgb (B, ncam, 3, H, W) in [0,1]; visible_pcd (B, ncam, 3, H, W) world xyz;
+        instruction (B, 53, 512); curr_gripper (B, 8); gt_action (B, 8) or None.
+        Returns the reference's output dict (act3d.py:340-357).
+        """
+        if not visible_rgb.is_cuda:
+            raise RuntimeError("Act3D (B200) runs on CUDA tensors only: there is no CPU fallback path")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "the fused kernels are forward-only in this round (backward kernels: DESIGN.md 'next'); "
+                "call under torch.no_grad()")
+        lib.load()
+        e, h = self.embedding_dim, self.num_attn_heads
+        b, ncam, _, height, width = visible_rgb.shape
+        dev = visible_rgb.device
+        gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None
+        grip_xyz = curr_gripper[:, :3].float()
+
+        feats_pyr, pcd_pyr = self._compute_visual_features(visible_rgb, visible_pcd, ncam)
+
+        if self.use_instruction:
+            instr = F.linear(instruction.float(), self.instruction_encoder.weight, self.instruction_encoder.bias)
+            instr = instr.contiguous()                                       # (B, 53, E)
+            n_instr = instr.shape[1]
+            instr_zero_pos = torch.zeros(b, n_instr, 3, device=dev)
+        else:
+            instr, n_instr = None, 0
+
+        n_vis = 32 * 32 * ncam
+        rows = n_vis + 1 + n_instr
+        position_pyramid, masks_pyramid, ghost_pyramid, carried = [], [], [], []
+        topk_log = []
+        query_feat = None
+        ghost_feats = None
+        lg = self.ghost_point_cross_attn_pyramid[0].num_layers
+        lq = self.query_cross_attn_pyramid[0].num_layers
+
+        for i in range(self.num_sampling_level):
+            anchor = None if i == 0 else (gt_position if gt_position is not None else carried[-1])
+            ghost = self._sample_ghost_points(b, dev, level=i, anchor=anchor).contiguous().float()
+            ng = ghost.shape[1]
+
+            # ---- context tokens: coarse grid (level 0) or the 1024*ncam nearest fine points
+            tok = torch.empty(b, rows, e, device=dev)
+            pos = torch.empty(b, rows, 3, device=dev)
+            fm = feats_pyr[i].reshape(b * ncam, e, -1, feats_pyr[i].shape[-1])
+            if i == 0:
+                idx = None
+            else:
+                idx = lib.local_topk(carried[-1][:, 0].contiguous(), pcd_pyr[i], n_vis)
+            topk_log.append(idx)
+            lib.gather_tokens(fm, pcd_pyr[i], idx, b, ncam, tok, pos)
+            tok[:, n_vis] = self.curr_gripper_embed.weight[0]
+            pos[:, n_vis] = grip_xyz
+
+            if self.use_instruction:
+                # context tokens (incl. gripper) cross-attend to the instruction, no rotary (act3d.py:261-270)
+                vi = self.vis_ins_attn_pyramid[i]
+                pk = self._stack_pack(("vis", id(vi)), vi)
+                kv_i = lib.ctx_kv(instr, instr_zero_pos, n_instr, h, pk["wkv"], pk["bkv"], [0] * vi.num_layers)
+                lib.xattn_stack(tok, rows * e, e, None, b, n_vis + 1, n_instr, e, h, e, vi.num_layers, kv_i, 0,
+                                lib.kv_bytes(1, b, n_instr, h), pk["w"], feat_out=tok, feat_rows=rows)
+                tok[:, n_vis + 1:] = instr
+                pos[:, n_vis + 1:] = 0.0
+
+            # ---- K/V cache of this context for the ghost layers (rotary) and the query layers
+            gs, qs = self.ghost_point_cross_attn_pyramid[i], self.query_cross_attn_pyramid[i]
+            pg, pq = self._stack_pack(("ghost", id(gs)), gs), self._stack_pack(("query", id(qs)), qs)
+            wkv = torch.cat([pg["wkv"], pq["wkv"]])
+            bkv = torch.cat([pg["bkv"], pq["bkv"]])
+            q_rot = 0 if i == 0 else 1            # the query is not localised at level 0 (act3d.py:287-294)
+            kv = lib.ctx_kv(tok, pos, rows, h, wkv, bkv, [1] * lg + [q_rot] * lq)
+            set_bytes = lib.kv_bytes(1, b, rows, h)
+
+            # ---- query token (1 per sample), both layer outputs are needed for the mask logits
+            q_all = torch.empty(lq, b, 1, e, device=dev)
+            if i == 0:
+                q_x0, q_sb = self.query_embed.weight.detach().float().contiguous(), 0
+                q_pos = None
+            else:
+                q_x0, q_sb = query_feat.contiguous(), e
+                q_pos = carried[-1].contiguous()
+            lib.xattn_stack(q_x0, q_sb, 0, q_pos, b, 1, rows, e, h, e, lq, kv, lg * set_bytes, set_bytes, pq["w"],
+                            feat_out=q_all, feat_rows=1, feat_all_layers=True)
+            query_feat = q_all[-1, :, 0]                                     # (B, E)
+
+            # ---- ghost points: fused attention stack + mask logits against both query layers
+            last_level = i == self.num_sampling_level - 1
+            want_feats = last_level and (self.regress_position_offset or "top_ghost" in self.rotation_parametrization)
+            ghost_feats = torch.empty(1, b, ng, e, device=dev) if want_feats else None
+            logits = torch.empty(lq, b, ng, device=dev)
+            g_x0 = self.ghost_points_embed_pyramid[i].weight.detach().float().contiguous()
+            lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"],
+                            feat_out=ghost_feats, feat_rows=ng, qvec=q_all.view(lq, b, e), logits=logits)
+
+            top_idx, top_pos = lib.argmax_pick(logits[-1], ghost)
+            position_i = top_pos.unsqueeze(1)
+            ghost_pyramid.append(ghost.transpose(1, 2))
+            position_pyramid.append(position_i)
+            masks_pyramid.append([logits[j] for j in range(lq)])
+            carried.append(self._teacher_positions[i].to(dev) if self._teacher_positions is not None else position_i)
+
+        self._last_topk = topk_log
+
+        # ---- offsets + action head (act3d.py:323-337, 507-535): tiny, stays PyTorch
+        top_idx_l = top_idx.long()
+        ar = torch.arange(b, device=dev)
+        offsets = None
+        position = top_pos
+        if self.regress_position_offset:
+            offsets = self.ghost_point_offset_predictor(ghost_feats[0]).permute(0, 2, 1)    # (B, 3, Ng)
+            position = position + offsets[ar, :, top_idx_l]
+        if "top_ghost" in self.rotation_parametrization:
+            feats = ghost_feats[0][ar, top_idx_l]
+        else:
+            feats = query_feat
+        pred = self.gripper_state_predictor(feats)
+        if "quat" in self.rotation_parametrization:
+            rotation = normalise_quat(pred[:, :self.rotation_dim])
+        else:
+            rotation = ortho6d_to_matrix(pred[:, :self.rotation_dim])
+        gripper = torch.sigmoid(pred[:, self.rotation_dim:])
+
+        return {
+            "position": position, "rotation": rotation, "gripper": gripper,
+            "position_pyramid": position_pyramid,
+            "visible_rgb_mask_pyramid": [None] * self.num_sampling_level,
+            "ghost_pcd_masks_pyramid": masks_pyramid,
+            "ghost_pcd_pyramid": ghost_pyramid,
+            "fine_ghost_pcd_offsets": offsets if self.regress_position_offset else None,
+            "visible_rgb_features_pyramid": feats_pyr,
+            "visible_pcd_pyramid": pcd_pyr,
+            "query_features": query_feat.unsqueeze(0),
+            "instruction_features": instr.transpose(0, 1) if instr is not None else None,
+            "instruction_dummy_pos": self._identity_rope(b, n_instr, dev) if instr is not None else None,
+        }
+
+    def _identity_rope(self, b, n, dev):
+        """Rotary table of zero positions = (cos 1, sin 0) (act3d.py:212-213); kept for output parity."""
+        t = torch.zeros(b, n, self.embedding_dim, 2, device=dev)
+        t[..., 0] = 1.0
+        return t

@@ -1,0 +1,170 @@
+"""ctypes binding of libact3d_b200.so (the C ABI declared in include/act3d_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+Device pointers are taken from torch tensors (PyTorch owns all memory); the current torch
+CUDA stream is passed to every call.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_long, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libact3d_b200.so")
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "a3d_last_error": (c_char_p, []),
+    "a3d_abi_version": (c_int, []),
+    "a3d_pcd_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "a3d_local_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "a3d_traj_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "a3d_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "a3d_kv_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "a3d_ctx_kv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                           ctypes.POINTER(c_int), c_int, c_void_p, c_void_p]),
+    "a3d_xattn_layer_floats": (c_size_t, [c_int, c_int]),
+    "a3d_xattn_stack": (c_int, [c_void_p, c_long, c_long, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                c_void_p, c_void_p]),
+    "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
+                                 c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class A3DError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building nothing: run __graft_entry__.build() or build.py first)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise A3DError(
+            f"{LIB_PATH} is missing. The CUDA extension is the product: build it with "
+            "`python -m act3d_chained_diffuser_b200.build` (or __graft_entry__.build()). There is no CPU/eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)     # AttributeError => the .so does not match include/act3d_b200.h
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(code, what):
+    if code != 0:
+        msg = load().a3d_last_error()
+        raise A3DError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "libact3d_b200 works on CUDA tensors only (no CPU fallback)"
+    assert t.is_contiguous(), "expected a contiguous tensor"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    assert t.dtype == torch.float32, f"expected float32, got {t.dtype}"
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+def pcd_pyramid(pcd_flat, factor):
+    """(BN, 3, H, W) -> (BN * h * w, 3) flattened; caller reshapes to (B, ncam*h*w, 3)."""
+    bn, c, h, w = pcd_flat.shape
+    assert c == 3
+    out = torch.empty(bn * (h // factor) * (w // factor), 3, device=pcd_flat.device, dtype=torch.float32)
+    _check(load().a3d_pcd_pyramid(_ptr(_f32(pcd_flat)), bn, h, w, factor, _ptr(out), _stream()), "a3d_pcd_pyramid")
+    return out
+
+
+def local_topk(center, pts, k, want_dist=False):
+    """center (B,3), pts (B,N,3) -> idx (B,k) int32 ascending by (distance, index)."""
+    b, n, _ = pts.shape
+    idx = torch.empty(b, k, device=pts.device, dtype=torch.int32)
+    dist = torch.empty(b, k, device=pts.device, dtype=torch.float32) if want_dist else None
+    _check(load().a3d_local_topk(_ptr(_f32(center)), _ptr(_f32(pts)), b, n, k, _ptr(idx), _ptr(dist), _stream()),
+           "a3d_local_topk")
+    return (idx, dist) if want_dist else idx
+
+
+def traj_topk(traj, pts, k, want_dist=False):
+    b, n, _ = pts.shape
+    idx = torch.empty(b, k, device=pts.device, dtype=torch.int32)
+    dist = torch.empty(b, k, device=pts.device, dtype=torch.float32) if want_dist else None
+    _check(load().a3d_traj_topk(_ptr(_f32(traj)), traj.shape[1], _ptr(_f32(pts)), b, n, k, _ptr(idx), _ptr(dist),
+                                _stream()), "a3d_traj_topk")
+    return (idx, dist) if want_dist else idx
+
+
+def gather_tokens(feat, pcd, idx, batch, ncam, tok, pos):
+    """feat (B*ncam, E, h, w), pcd (B, ncam*h*w, 3), idx (B,K) int32 or None -> rows [0,K) of tok/pos."""
+    e, hw = feat.shape[1], feat.shape[2] * feat.shape[3]
+    k = idx.shape[1] if idx is not None else ncam * hw
+    _check(load().a3d_gather_tokens(_ptr(_f32(feat)), _ptr(_f32(pcd)), _ptr(idx), batch, ncam, e, hw, k,
+                                    _ptr(tok), _ptr(pos), tok.shape[1], _stream()), "a3d_gather_tokens")
+    return k
+
+
+def kv_bytes(nsets, batch, nk, heads):
+    return load().a3d_kv_bytes(nsets, batch, nk, heads)
+
+
+def ctx_kv(tok, pos, nk, heads, wkv, bkv, rope_flags, out=None):
+    """tok (B,rows,E), pos (B,rows,3) -> uint8 buffer holding [nsets][B][ntiles][2][H][64][16] fp16."""
+    b, rows, e = tok.shape
+    nsets = len(rope_flags)
+    nbytes = kv_bytes(nsets, b, nk, heads)
+    if out is None or out.numel() < nbytes:
+        out = torch.empty(nbytes, device=tok.device, dtype=torch.uint8)
+    flags = (c_int * nsets)(*[int(f) for f in rope_flags])
+    _check(load().a3d_ctx_kv(_ptr(_f32(tok)), _ptr(_f32(pos)), b, rows, nk, e, heads, _ptr(_f32(wkv)), _ptr(_f32(bkv)),
+                             flags, nsets, _ptr(out), _stream()), "a3d_ctx_kv")
+    return out
+
+
+def xattn_layer_floats(embed, ffn):
+    n = load().a3d_xattn_layer_floats(embed, ffn)
+    if n == 0:
+        raise A3DError(f"a3d_xattn_stack is not built for embed={embed}, ffn={ffn}")
+    return n
+
+
+def xattn_stack(x0, x0_stride_b, x0_stride_n, qpos, batch, nq, nk, embed, heads, ffn, nlayers, kv, kv_offset_bytes,
+                kv_layer_stride, w, feat_out=None, feat_rows=0, feat_all_layers=False, qvec=None, logits=None):
+    nqv = qvec.shape[0] if qvec is not None else 0
+    _check(load().a3d_xattn_stack(_ptr(_f32(x0)), x0_stride_b, x0_stride_n, _ptr(qpos), batch, nq, nk, embed, heads,
+                                  ffn, nlayers, kv.data_ptr() + kv_offset_bytes, kv_layer_stride, _ptr(_f32(w)),
+                                  _ptr(feat_out), feat_rows, int(feat_all_layers), _ptr(qvec), nqv, _ptr(logits),
+                                  _stream()), "a3d_xattn_stack")
+
+
+def argmax_pick(logits, ghost):
+    b, ng = logits.shape
+    top = torch.empty(b, device=logits.device, dtype=torch.int32)
+    pos = torch.empty(b, 3, device=logits.device, dtype=torch.float32)
+    _check(load().a3d_argmax_pick(_ptr(_f32(logits)), _ptr(_f32(ghost)), b, ng, _ptr(top), _ptr(pos), _stream()),
+           "a3d_argmax_pick")
+    return top, pos
+
+
+def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device):
+    out = torch.empty(batch, ng, 3, device=device, dtype=torch.float32)
+    bd = (c_float * 6)(*[float(x) for x in (list(bounds[0]) + list(bounds[1]))])
+    _check(load().a3d_sample_ghost(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
+                                   int(stream_id), _ptr(out), _stream()), "a3d_sample_ghost")
+    return out

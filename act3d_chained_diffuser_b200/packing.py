@@ -1,0 +1,83 @@
+"""Weight packing: nn.Parameters -> the flat fp32 buffers the kernels read.
+
+All matrices are stored K-MAJOR ([in_features][padded out_features]) so that the register-tiled
+GEMMs read 16 consecutive output columns with four 16-byte loads; vectors are padded to the same
+width.  Packed buffers are cached per (parameter storage, version) so inference repacks nothing.
+"""
+import math
+
+import torch
+
+LOG2E = 1.4426950408889634
+
+
+def _pad_cols(m, width):
+    out = m.new_zeros(m.shape[0], width)
+    out[:, : m.shape[1]] = m
+    return out
+
+
+def _pad_vec(v, width):
+    out = v.new_zeros(width)
+    out[: v.shape[0]] = v
+    return out
+
+
+def _kmajor(weight, width):
+    """nn.Linear weight (out, in) -> (in, width) with W^T in the first `out` columns."""
+    return _pad_cols(weight.detach().float().t().contiguous(), width)
+
+
+def pack_xattn_layer(attn, norm, ffw, embed, heads):
+    """One layer of an Act3D stack -> flat tensor in the XaCfg order (csrc/a3d_xattn.cu):
+    W_Q[E][EP] B_Q[EP] W_O[E][EP] B_O G_1 BE_1 W_1[E][EP] B_1 W_2[FF][EP] B_2 G_2 BE_2.
+    The q projection carries hd^-1/2 (multihead_custom_attention.py:244,325) and log2(e) so the
+    kernel's softmax is a bare exp2."""
+    ep = 16 * heads
+    e = embed
+    scale = (float(e // heads) ** -0.5) * LOG2E
+    w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
+    parts = [
+        _kmajor(w_in[:e] * scale, ep).reshape(-1), _pad_vec(b_in[:e] * scale, ep),
+        _kmajor(attn.out_proj.weight, ep).reshape(-1), _pad_vec(attn.out_proj.bias.detach().float(), ep),
+        _pad_vec(norm.weight.detach().float(), ep), _pad_vec(norm.bias.detach().float(), ep),
+        _kmajor(ffw.linear1.weight, ep).reshape(-1), _pad_vec(ffw.linear1.bias.detach().float(), ep),
+        _kmajor(ffw.linear2.weight, ep).reshape(-1), _pad_vec(ffw.linear2.bias.detach().float(), ep),
+        _pad_vec(ffw.norm.weight.detach().float(), ep), _pad_vec(ffw.norm.bias.detach().float(), ep),
+    ]
+    return torch.cat(parts)
+
+
+def pack_kv_set(attn, embed, heads):
+    """K/V in-projection of one attention layer -> (wkv [E][2*EP], bkv [2*EP]):
+    columns [0,E) = W_k^T, [EP, EP+E) = W_v^T (slices W[E:2E], W[2E:3E],
+    multihead_custom_attention.py:268-303)."""
+    ep = 16 * heads
+    e = embed
+    w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
+    wkv = torch.cat([_kmajor(w_in[e:2 * e], ep), _kmajor(w_in[2 * e:], ep)], dim=1)
+    bkv = torch.cat([_pad_vec(b_in[e:2 * e], ep), _pad_vec(b_in[2 * e:], ep)])
+    return wkv.contiguous(), bkv.contiguous()
+
+
+class PackCache:
+    """Memoise packed buffers on the identity + version of the source parameters."""
+
+    def __init__(self):
+        self._store = {}
+
+    @staticmethod
+    def _sig(params):
+        return tuple((p.data_ptr(), p._version, p.device) for p in params)
+
+    def get(self, key, params, builder):
+        sig = self._sig(params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = builder()
+        self._store[key] = (sig, val)
+        return val
+
+    def clear(self):
+        self._store.clear()

@@ -1,0 +1,140 @@
+/*
+ * act3d_b200.h -- C ABI of libact3d_b200.so (hand-written sm_100a kernels).
+ *
+ * The reference (zhouxian/act3d-chained-diffuser) has no FFI: its hot path is eager
+ * PyTorch.  The drop-in boundary is therefore the nn.Module surface (model.Act3D,
+ * model.DiffusionPlanner); these entry points are what those modules call instead of
+ * the eager ops.  Each function cites the reference code it replaces (paths relative
+ * to /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller allocates all inputs, outputs and workspaces (PyTorch owns memory);
+ *   - `stream` is a cudaStream_t passed as void*; functions only enqueue work and
+ *     never synchronise; one caller thread per device;
+ *   - return 0 on success, a negative A3D_E* code otherwise; a3d_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - floats are fp32, indices int32 unless stated; layouts are row-major, last
+ *     dimension fastest.
+ */
+#ifndef ACT3D_B200_H_
+#define ACT3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_OK 0
+#define A3D_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define A3D_ECUDA (-2)    /* CUDA runtime error at launch                */
+#define A3D_ENOSUPPORT (-3)
+
+#define A3D_TILE_KEYS 64  /* keys per K/V tile image                      */
+#define A3D_HEAD_PAD 16   /* head_dim 15 padded to 16 (slot 15: see below) */
+
+const char* a3d_last_error(void);
+int a3d_abi_version(void);
+
+/* ---------------------------------------------------------------------------------
+ * Point pyramid.  Replaces F.interpolate(pcd, scale_factor=1/f, mode='bilinear') +
+ * rearrange "(bt ncam) c h w -> bt (ncam h w) c"   (act3d.py:379-383, encoder.py:147-158).
+ * pcd [BN][3][H][W] -> out [BN*(H/f)*(W/f)][3].  f in {2,4,8}.  Bit-exact w.r.t. the
+ * reference's separable half-weights (0.25*((a+b)+(c+d))).
+ */
+int a3d_pcd_pyramid(const float* pcd, int bn, int height, int width, int factor, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Local context selection.  Replaces
+ *   ((pos - pcd)**2).sum(-1).sqrt().topk(k, largest=False).indices   (act3d.py:244-245)
+ * center [B][3], pts [B][N][3] -> idx [B][K] (int32, ascending (distance, index):
+ * ties resolved toward the lower index), dist [B][K] (may be NULL).
+ * Distance is ((dx*dx + dy*dy) + dz*dz) in fp32 without contraction, IEEE sqrt.
+ * K <= 8192, N <= 2^24.
+ */
+int a3d_local_topk(const float* center, const float* pts, int batch, int n, int k,
+                   int32_t* idx, float* dist, void* stream);
+
+/* Same selection for ChainedDiffuser's find_traj_nn (model/utils/utils.py:38-48):
+ * key = min over L trajectory points of the SQUARED distance (no sqrt).
+ * traj [B][L][3]. */
+int a3d_traj_topk(const float* traj, int traj_len, const float* pts, int batch, int n, int k,
+                  int32_t* idx, float* dist, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Token gather.  Replaces rearrange "b ncam c h w -> b (ncam h w) c" + per-sample
+ * index gather of features and positions (act3d.py:240-254, diffusion_head.py:290-302).
+ * feat [B*ncam][E][hw], pcd [B][ncam*hw][3], idx [B][K] or NULL (identity, K = ncam*hw).
+ * Writes rows [0,K) of tok [B][tok_rows][E] and pos [B][tok_rows][3].
+ */
+int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, int batch, int ncam,
+                      int embed, int hw, int k, float* tok, float* pos, int tok_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Context K/V cache.  Replaces, for `nsets` attention layers that share one context,
+ *   k, v = F.linear(ctx, W[E:], b[E:]).chunk(2)   (multihead_custom_attention.py:268-275)
+ *   k = embed_rotary(k, cos, sin)                  (:352-353, position_encodings.py:31-34,58-97)
+ * and the head split (:356-359).  The rotary table is never materialised: angles are
+ * evaluated from pos on the fly.
+ * tok [B][tok_rows][E], pos [B][tok_rows][3] (first nk rows used), wkv [nsets][2*EP][E]
+ * (rows 0..E-1 = W_k, rows EP..EP+E-1 = W_v, EP = 16*H), bkv [nsets][2*EP],
+ * rope_host[nsets] (1: rotate K of that set).  Output: K/V "tile images", fp16:
+ *   kv [nsets][B][ntiles][2][H][64][16],  ntiles = ceil(nk/64),
+ * slot 15 of every V row holds 1.0 for valid keys (the PV product then carries the
+ * softmax denominator), padded keys are all-zero; inside a 32-byte row the two 16-byte
+ * halves are swapped when (key>>2)&1 (bank-conflict-free ldmatrix).
+ * (embed, heads) in {(60,4), (120,8)}.
+ */
+size_t a3d_kv_bytes(int nsets, int batch, int nk, int heads);
+int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok_rows, int nk, int embed, int heads,
+               const float* wkv, const float* bkv, const int* rope_host, int nsets, void* kv, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fused cross-attention stack (the north-star kernel).  Replaces, per layer,
+ *   RelativeCrossAttentionLayer.forward + FeedforwardLayer.forward  (layers.py:300-332)
+ *   = q-proj, scale, rotary(q), softmax(QK^T)V over all heads, out-proj, +res, LN,
+ *     FFN(relu), +res, LN                      (multihead_custom_attention.py:260-462)
+ * for `nlayers` layers over one query tile kept on chip, plus the mask-logit einsum
+ * (act3d.py:493-494).  No score matrix, attention weight or rotary table reaches HBM.
+ *
+ * x0: initial query features; x0_stride_b / x0_stride_n in floats (0,0 = one shared row,
+ *     i.e. the ghost-point embedding; (E,0) = one row per sample).
+ * qpos [B][nq][3] or NULL (no rotary on this stack: K sets must then be unrotated).
+ * kv[l] = K/V tile images of layer l for this context (a3d_ctx_kv), passed as kv_base +
+ *     l * kv_layer_stride_bytes.
+ * w: packed layer weights, see act3d_chained_diffuser_b200/packing.py (pack_xattn_layer).
+ * feat_out: NULL or [n_feat_layers][B][feat_rows][E]; rows [0,nq) written; if
+ *     feat_all_layers==0 only the last layer is written (n_feat_layers = 1).
+ * qvec [nqv][B][E] + logits [nqv][B][nq]: logits[j][b][n] = <qvec[j][b], x_last[b][n]>; NULL to skip.
+ * (embed, heads, ffn) in {(60,4,60)}.
+ */
+int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride_n, const float* qpos,
+                    int batch, int nq, int nk, int embed, int heads, int ffn, int nlayers,
+                    const void* kv_base, size_t kv_layer_stride_bytes, const float* w,
+                    float* feat_out, int feat_rows, int feat_all_layers,
+                    const float* qvec, int nqv, float* logits, void* stream);
+size_t a3d_xattn_layer_floats(int embed, int ffn);
+
+/* ---------------------------------------------------------------------------------
+ * Top ghost point.  Replaces torch.max(mask, -1).indices + position gather
+ * (act3d.py:312-314, 512-513).  Lowest index wins ties.  ghost [B][Ng][3].
+ */
+int a3d_argmax_pick(const float* logits, const float* ghost, int batch, int ng,
+                    int32_t* top_idx, float* pos, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Ghost-point sampler.  Replaces Act3D._sample_ghost_points + the numpy samplers
+ * (act3d.py:394-440, model/utils/utils.py:68-84) with a device-side Philox4x32-10
+ * stream (same distributions: uniform box at level 0, uniform ball of `radius` around
+ * the anchor intersected with the workspace box at level >= 1).  The anchor stays on the
+ * device: no host round trip between levels.  bounds_host = {lo[3], hi[3]}.
+ */
+int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
+                     uint64_t seed, uint64_t stream_id, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACT3D_B200_H_ */

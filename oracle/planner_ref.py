@@ -1,0 +1,189 @@
+"""Oracle: ChainedDiffuser trajectory denoiser + sampling loop (test infrastructure only).
+
+Functional CPU restatement of
+  model/trajectory_optimization/diffusion_head.py:200-363   (DiffusionHead.forward / _one_attention_round)
+  model/utils/encoder.py:81-203                              (token encoders)
+  model/trajectory_optimization/diffusion_model.py:64-324    (DiffusionPlanner)
+for the shipped configuration family: rotation_parametrization='6D', feat_scales_to_use=1,
+attn_rounds=1.  ``sd`` holds the keys under ``prediction_head.`` with that
+prefix stripped.
+"""
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .attention import parallel_attention_stack
+from .ddpm import DDPMScheduler
+from .geometry import (matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix,
+                       pcd_level, quat_to_matrix)
+from .rope import rope3d_table, sinusoidal_embedding
+
+
+@dataclass
+class PlannerConfig:
+    embedding_dim: int = 120
+    num_attn_heads: int = 8
+    num_vis_ins_attn_layers: int = 2
+    num_query_cross_attn_layers: int = 6
+    use_instruction: bool = True
+    use_goal: bool = True
+    use_goal_at_test: bool = False
+    gripper_loc_bounds: object = None
+    diffusion_timesteps: int = 100
+
+
+def _mlp2(sd, p, x, i0="0", i1="3"):
+    return F.linear(F.relu(F.linear(x, sd[f"{p}{i0}.weight"], sd[f"{p}{i0}.bias"])),
+                    sd[f"{p}{i1}.weight"], sd[f"{p}{i1}.bias"])
+
+
+def encode_context(sd, cfg: PlannerConfig, trunk: Callable, rgb, pcd, instruction, curr_gripper, goal_gripper):
+    """Everything in DiffusionHead.forward that does not depend on the trajectory or the
+    timestep: trunk features, context rotary table, vision->language
+    attention, gripper / goal tokens, instruction tokens."""
+    e, h = cfg.embedding_dim, cfg.num_attn_heads
+    b, ncam = rgb.shape[:2]
+    fpn = trunk(rgb.reshape(b * ncam, *rgb.shape[2:]))                       # encoder.py:133-139
+    fm = fpn["res3"]
+    ctx = fm.view(b, ncam, *fm.shape[1:]).permute(0, 1, 3, 4, 2).reshape(b, -1, e)   # diffusion_head.py:290-293
+    pts = pcd_level(pcd.reshape(b * ncam, *pcd.shape[2:]), 8, ncam)          # encoder.py:147-158
+    ctx_rope = rope3d_table(pts, e)
+
+    instr, instr_rope = None, None
+    if cfg.use_instruction:                                                  # encoder.py:169-187
+        instr = F.linear(instruction, sd["instruction_encoder.weight"], sd["instruction_encoder.bias"])
+        instr_rope = rope3d_table(torch.zeros(b, instr.shape[1], 3), e)
+        ctx = parallel_attention_stack(sd, "vl_attention.0.", h, cfg.num_vis_ins_attn_layers,   # diffusion_head.py:305-314
+                                       ctx, None, instr)
+
+    cur = F.linear(curr_gripper, sd["curr_gripper_encoder.weight"], sd["curr_gripper_encoder.bias"])[:, None]
+    cur = cur + sd["curr_gripper_embed.weight"].repeat(b, 1).unsqueeze(1)    # diffusion_head.py:231-237
+    ctx = torch.cat([ctx, cur], dim=1)
+    ctx_rope = torch.cat([ctx_rope, rope3d_table(curr_gripper[:, :3][:, None], e)], dim=1)
+    if cfg.use_goal:                                                         # diffusion_head.py:239-247, 320-323
+        goal = F.linear(goal_gripper, sd["goal_gripper_encoder.weight"], sd["goal_gripper_encoder.bias"])[:, None]
+        goal = goal + sd["goal_gripper_embed.weight"].repeat(b, 1).unsqueeze(1)
+        ctx = torch.cat([ctx, goal], dim=1)
+        ctx_rope = torch.cat([ctx_rope, rope3d_table(goal_gripper[:, :3][:, None], e)], dim=1)
+    return {"ctx": ctx, "ctx_rope": ctx_rope, "instr": instr, "instr_rope": instr_rope, "pcd": pts}
+
+
+def denoise_once(sd, cfg: PlannerConfig, context, trajectory, trajectory_mask, timestep):
+    """One DiffusionHead.forward given the step-invariant context.  Returns (B, L, 9).
+    diffusion_head.py:215-277 (token prep) and :325-363 (attention + regressors)."""
+    e, h = cfg.embedding_dim, cfg.num_attn_heads
+    b, length, _ = trajectory.shape
+    x = _mlp2(sd, "traj_encoder.", trajectory)
+    traj_rope = rope3d_table(trajectory[..., :3], e)
+    t_emb = sinusoidal_embedding(timestep, e)                                # encoder.py:199
+    wp_pe = sinusoidal_embedding(torch.arange(0, length), e)[None].repeat(b, 1, 1)   # diffusion_head.py:326-328
+
+    if cfg.use_instruction:                                                  # diffusion_head.py:330-336
+        x = parallel_attention_stack(sd, "traj_lang_attention.0.", h, 1, x, trajectory_mask, context["instr"],
+                                     seq1_sem_pos=wp_pe, apply_ffn=False)
+    common = dict(seq1_mask=trajectory_mask, seq2=context["ctx"], seq1_rope=traj_rope,
+                  seq2_rope=context["ctx_rope"], seq1_sem_pos=wp_pe, ada_signal=t_emb,
+                  self_attention=True, rotary=True, use_adaln=True)
+    x = parallel_attention_stack(sd, "traj_attention.0.", h, cfg.num_query_cross_attn_layers - 2, x, **common)
+    pos_f = parallel_attention_stack(sd, "pos_attention.0.", h, 2, x, **common)
+    rot_f = parallel_attention_stack(sd, "rot_attention.0.", h, 2, x, **common)
+    upd = torch.cat((_mlp2(sd, "pos_regressor.0.", pos_f), _mlp2(sd, "rot_regressor.0.", rot_f)), -1)
+    return torch.cat((trajectory[..., :3] + upd[..., :3], upd[..., 3:]), -1)   # diffusion_head.py:271-274
+
+
+# ---------------------------------------------------------------- planner wrapper
+
+def normalize_pos(cfg, pos):
+    lo = torch.tensor(cfg.gripper_loc_bounds[0]).float()
+    hi = torch.tensor(cfg.gripper_loc_bounds[1]).float()
+    return (pos - lo) / (hi - lo) * 2.0 - 1.0                               # diffusion_model.py:187-190
+
+
+def unnormalize_pos(cfg, pos):
+    lo = torch.tensor(cfg.gripper_loc_bounds[0]).float()
+    hi = torch.tensor(cfg.gripper_loc_bounds[1]).float()
+    return (pos + 1.0) / 2.0 * (hi - lo) + lo                               # diffusion_model.py:192-195
+
+
+def quat_signal_to_6d(signal):
+    """(..., 7+) [xyz, quat(taken as real-first), rest] -> (..., 9+).  diffusion_model.py:197-213."""
+    signal = signal.clone()
+    signal[..., 3:7] = normalise_quat(signal[..., 3:7])
+    rot = quat_to_matrix(signal[..., 3:7])
+    lead = rot.shape[:-2]
+    r6 = matrix_to_ortho6d(rot.reshape(-1, 3, 3)).reshape(*lead, 6)
+    return torch.cat([signal[..., :3], r6, signal[..., 7:]], dim=-1)
+
+
+def sixd_signal_to_quat(signal):
+    """(B, L, 9+) -> (B, L, 7+).  diffusion_model.py:215-230."""
+    b, length, _ = signal.shape
+    quat = matrix_to_quat(ortho6d_to_matrix(signal[..., 3:9].reshape(b * length, 6))).reshape(b, length, 4)
+    return torch.cat([signal[..., :3], quat, signal[..., 9:]], dim=-1)
+
+
+def compute_trajectory(sd, cfg: PlannerConfig, trunk, trajectory_mask, rgb, pcd, instruction,
+                       curr_gripper, goal_gripper, noise_fn: Optional[Callable] = None,
+                       hoist_context: bool = True, n_steps: Optional[int] = None):
+    """DiffusionPlanner.compute_trajectory (diffusion_model.py:121-185) + conditional_sample (:86-119).
+
+    ``noise_fn(shape)`` supplies the Gaussian draws in the reference's call order
+    ((B,L,9) once, then per step (B,L,3) and (B,L,6)); default torch.randn.
+    ``hoist_context=False`` re-encodes the context every step like the reference does
+    (bit-identical results) -- used when timing the CPU baseline.
+    """
+    if noise_fn is None:
+        noise_fn = lambda shape: torch.randn(shape)
+    steps = n_steps or cfg.diffusion_timesteps
+    pos_s = DDPMScheduler(cfg.diffusion_timesteps, "scaled_linear", "sample")
+    rot_s = DDPMScheduler(cfg.diffusion_timesteps, "squaredcos_cap_v2", "sample")
+
+    pcd_n = normalize_pos(cfg, pcd.permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
+    cur = curr_gripper.clone()
+    goal = goal_gripper.clone()
+    cur[:, :3] = normalize_pos(cfg, cur[:, :3])
+    goal[:, :3] = normalize_pos(cfg, goal[:, :3])
+    cur = quat_signal_to_6d(cur)
+    goal = quat_signal_to_6d(goal)
+
+    b, d = cur.shape
+    length = trajectory_mask.size(1)
+    cond = torch.zeros(b, length, d)
+    cmask = torch.zeros_like(cond)
+    cond[:, 0] = cur
+    cmask[:, 0] = 1
+    if cfg.use_goal_at_test:                                                 # diffusion_model.py:162-167
+        for i in range(b):
+            neg = -int(trajectory_mask[i].sum())
+            cond[i][neg - 1] = goal[i]
+            cmask[i][neg - 1:] = 1
+    cmask = cmask.bool()
+
+    pos_s.set_timesteps(steps)
+    rot_s.set_timesteps(steps)
+    traj = noise_fn(cond.shape) + cond                                       # diffusion_model.py:91-96
+    ctx = encode_context(sd, cfg, trunk, rgb, pcd_n, instruction, cur, goal) if hoist_context else None
+    last = pos_s.timesteps[-1]
+    for t in pos_s.timesteps:
+        if not hoist_context:
+            ctx = encode_context(sd, cfg, trunk, rgb, pcd_n, instruction, cur, goal)
+        out = denoise_once(sd, cfg, ctx, traj, trajectory_mask, t * torch.ones(b).long())
+        out[cmask] = cond[cmask]
+        if t == last:
+            traj = out
+        else:
+            c0, c1, sg = pos_s.step_coefficients(int(t))
+            p = c0 * out[..., :3].clamp(-1, 1) + c1 * traj[..., :3]
+            if int(t) > 0:
+                p = p + sg * noise_fn(p.shape)
+            c0, c1, sg = rot_s.step_coefficients(int(t))
+            r = c0 * out[..., 3:9].clamp(-1, 1) + c1 * traj[..., 3:9]
+            if int(t) > 0:
+                r = r + sg * noise_fn(r.shape)
+            traj = torch.cat((p, r), -1)
+
+    traj = sixd_signal_to_quat(traj)
+    traj[:, :, :3] = unnormalize_pos(cfg, traj[:, :, :3])
+    return traj

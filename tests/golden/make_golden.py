@@ -1,0 +1,147 @@
+"""Generate the golden vectors from the UNMODIFIED reference (build container only).
+
+    python -m tests.golden.make_golden          # from the repo root; needs /root/reference
+
+The reference is imported from /root/reference through oracle/ref_import.py (import stubs for
+the two missing packages ``clip`` and ``diffusers``; the latter is our DDPM restatement, see
+oracle/ddpm.py "parity unpinned").  Inputs and weights come from tests/golden/{synth,cases}.py
+(name-keyed numpy PCG64 streams), so the tests can rebuild them anywhere; the fixture files
+hold only the reference's OUTPUTS plus a checksum of the inputs.  CPU, fp32, eval mode.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle.ref_import import load_reference  # noqa: E402
+from tests.golden import cases, synth  # noqa: E402
+
+
+def save(name, payload):
+    path = os.path.join(HERE, name + ".pt")
+    torch.save(payload, path)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+@torch.no_grad()
+def gen_rope(ref):
+    out = {}
+    for e in (60, 120):
+        xyz = synth.points_in_bounds(f"rope.{e}", (2, 5))
+        out[f"table_{e}"] = ref.position_encodings.RotaryPositionEncoding3D(e)(xyz)
+        out[f"check_{e}"] = synth.checksum(xyz)
+    t = torch.tensor([0, 1, 17, 99])
+    out["sinus_120"] = ref.position_encodings.SinusoidalPosEmb(120)(t)
+    save("rope", out)
+
+
+@torch.no_grad()
+def gen_attention_stack(ref):
+    c = cases.small_attention_case()
+    mod = ref.layers.RelativeCrossAttentionModule(c["e"], c["heads"], 2).eval()
+    synth.fill_state_dict(mod.state_dict())
+    pe = ref.position_encodings.RotaryPositionEncoding3D(c["e"])
+    with_rope = mod(c["query"], c["context"], pe(c["q_xyz"]), pe(c["c_xyz"]))
+    no_rope = mod(c["query"], c["context"], None, None)
+    save("attention_stack", dict(with_rope=with_rope, no_rope=no_rope,
+                                 check=synth.checksum(c["query"], c["context"], c["q_xyz"], c["c_xyz"])))
+
+
+@torch.no_grad()
+def gen_act3d(ref, use_instruction):
+    kw = dict(cases.ACT3D_KW, use_instruction=use_instruction)
+    torch.manual_seed(0)
+    model = ref.Act3D(**kw).eval()
+    cases.install_synth_trunk(model, kw["embedding_dim"])
+    synth.fill_state_dict(model.state_dict())
+    inp = cases.act3d_inputs(batch=2, ncam=1)
+    sampler = synth.make_ghost_sampler(2, model.num_ghost_points_val, diameter=kw["fine_sampling_ball_diameter"])
+    model._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor)
+    out = model(inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"])
+    keep = dict(
+        position=out["position"], rotation=out["rotation"], gripper=out["gripper"],
+        position_pyramid=out["position_pyramid"],
+        ghost_pcd_masks_pyramid=out["ghost_pcd_masks_pyramid"],
+        ghost_pcd_pyramid=out["ghost_pcd_pyramid"],
+        query_features=out["query_features"],
+        visible_pcd_pyramid=[p[:, :64].clone() for p in out["visible_pcd_pyramid"]],
+        check=synth.checksum(inp["visible_rgb"][:, :, :, :8, :8], inp["visible_pcd"][:, :, :, :8, :8],
+                             inp["curr_gripper"]),
+    )
+    save(f"act3d_c0_instr{int(use_instruction)}", keep)
+
+
+@torch.no_grad()
+def gen_parallel_attention(ref):
+    e, h, b, s1, s2 = 120, 8, 2, 12, 30
+    mod = ref.layers.ParallelAttention(num_layers=2, d_model=e, n_heads=h, self_attention1=True,
+                                       self_attention2=False, cross_attention1=True, cross_attention2=False,
+                                       rotary_pe=True, use_adaln=True).eval()
+    synth.fill_state_dict(mod.state_dict())
+    pe = ref.position_encodings.RotaryPositionEncoding3D(e)
+    x = synth.normal("pa.x", (b, s1, e))
+    ctx = synth.normal("pa.ctx", (b, s2, e))
+    xp = synth.uniform("pa.xp", (b, s1, 3), -1, 1)
+    cp = synth.uniform("pa.cp", (b, s2, 3), -1, 1)
+    sem = synth.normal("pa.sem", (b, s1, e), 0.5)
+    t_emb = synth.normal("pa.t", (b, e))
+    mask = torch.zeros(b, s1, dtype=torch.bool)
+    mask[1, -3:] = True
+    y, _ = mod(seq1=x, seq1_key_padding_mask=mask, seq2=ctx, seq2_key_padding_mask=None,
+               seq1_pos=pe(xp), seq2_pos=pe(cp), seq1_sem_pos=sem, seq2_sem_pos=None, ada_sgnl=t_emb)
+    save("parallel_attention", dict(out=y, check=synth.checksum(x, ctx, xp, cp, sem, t_emb)))
+
+
+def build_planner(ref):
+    torch.manual_seed(0)
+    model = ref.DiffusionPlanner(**cases.PLANNER_KW).eval()
+    cases.install_synth_trunk(model.prediction_head, cases.PLANNER_KW["embedding_dim"])
+    synth.fill_state_dict(model.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    return model
+
+
+@torch.no_grad()
+def gen_diffusion_head(ref):
+    model = build_planner(ref)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.7)
+    # normalised-frame inputs straight into the head (diffusion_head.py:200)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    pcd_n = model.normalize_pos(inp["pcd_obs"].permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
+    t = torch.tensor([37, 5])
+    out = model.prediction_head(traj, inp["trajectory_mask"], t, visible_rgb=inp["rgb_obs"], visible_pcd=pcd_n,
+                                curr_gripper=cur, goal_gripper=goal, instruction=inp["instruction"])
+    save("diffusion_head", dict(out=out[-1], check=synth.checksum(traj, cur, goal, t)))
+
+
+@torch.no_grad()
+def gen_planner(ref):
+    model = build_planner(ref)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    with synth.patched_randn(synth.NoiseStream("cd")):
+        traj = model.compute_trajectory(inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"],
+                                        inp["instruction"], inp["curr_gripper"], inp["goal_gripper"])
+    save("planner_100step", dict(trajectory=traj, check=synth.checksum(inp["curr_gripper"], inp["goal_gripper"])))
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = load_reference()
+    gen_rope(ref)
+    gen_attention_stack(ref)
+    gen_act3d(ref, False)
+    gen_act3d(ref, True)
+    gen_parallel_attention(ref)
+    gen_diffusion_head(ref)
+    gen_planner(ref)
+
+
+if __name__ == "__main__":
+    main()
