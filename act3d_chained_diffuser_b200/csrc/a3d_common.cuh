@@ -106,6 +106,11 @@ __device__ __forceinline__ uint32_t exp2_pack_h2(float lo, float hi) {
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(packed));
     return out;
 }
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t packed;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(hi), "f"(lo));
+    return packed;
+}
 __device__ __forceinline__ float exp2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -25,9 +25,11 @@ int check_launch(const char* what) {
 }
 
 // =================================================================== point pyramid
-// out[(n*h + y)*w + x][c] = 0.25 * ((p00 + p01) + (p10 + p11)) at the two centre pixels of the
-// f x f block -- the exact arithmetic of bilinear interpolation with lambda = 0.5 on both axes
-// (act3d.py:379-380).  One thread per output point, three channels.
+// out[(n*h + y)*w + x][c] = 0.25 * (((p00 + p01) + p10) + p11) at the two centre pixels per axis of
+// the f x f block: bilinear interpolation with lambda = 0.5 on both axes (act3d.py:379-380),
+// accumulated in the order of torch's CPU kernel so that the result is bit-identical to the CPU
+// reference (torch's own CUDA kernel pairs the taps differently and is 1 ulp away from it).
+// One thread per output point, three channels.
 __global__ void __launch_bounds__(256) pcd_pyramid_kernel(const float* __restrict__ pcd, int bn, int H, int W, int f,
                                                           float* __restrict__ out) {
     const int h = H / f, w = W / f;
@@ -42,9 +44,9 @@ __global__ void __launch_bounds__(256) pcd_pyramid_kernel(const float* __restric
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float* p = pcd + ((n * 3 + c) * H + sy) * (long)W + sx;
-            const float top = __fadd_rn(__fmul_rn(0.5f, __ldg(p)), __fmul_rn(0.5f, __ldg(p + 1)));
-            const float bot = __fadd_rn(__fmul_rn(0.5f, __ldg(p + W)), __fmul_rn(0.5f, __ldg(p + W + 1)));
-            v[c] = __fadd_rn(__fmul_rn(0.5f, top), __fmul_rn(0.5f, bot));
+            // weights are all 0.25; torch's CPU kernel accumulates the four taps in raster order
+            const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__ldg(p), __ldg(p + 1)), __ldg(p + W)), __ldg(p + W + 1));
+            v[c] = __fmul_rn(0.25f, acc);
         }
         out[i * 3 + 0] = v[0];
         out[i * 3 + 1] = v[1];

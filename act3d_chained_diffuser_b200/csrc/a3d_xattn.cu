@@ -12,6 +12,8 @@
 //       GEMMs on the K-major shared tile
 // and after the last layer the mask logits <qvec, x> (act3d.py:493-494) and/or the features.
 // The score matrix, the attention weights and the rotary tables never exist in HBM.
+#include <string.h>
+
 #include "a3d_linear.cuh"
 
 namespace a3d {
@@ -21,7 +23,7 @@ struct XaCfg {
     static constexpr int EP = 16 * H;                 // 64
     static constexpr int ROWS = 128;
     static constexpr int RP = 130;                    // row pitch (floats) of the K-major tiles
-    static constexpr int QP = 72;                     // row pitch (halfs) of the fp16 Q tile
+    static constexpr int QP = 64;                     // row pitch (halfs) of the fp16 Q tile (hi | lo planes)
     static constexpr int TILE_BYTES = 2 * H * 2048;   // K image + V image of one 64-key tile
     static constexpr int STAGES = 2;
     static constexpr size_t XT_BYTES = (size_t)EP * RP * 4;
@@ -57,7 +59,9 @@ struct XaArgs {
     float* logits;
 };
 
-template <int E, int H, int FF>
+// EXP32: evaluate 2^(s-m) with the fp32 MUFU path per element (default: packed fp16x2, one op per two
+// scores).  QSPLIT: carry Q as an fp16 hi + lo pair (two S MMAs) so that only K is rounded to fp16.
+template <int E, int H, int FF, bool EXP32, bool QSPLIT>
 __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
     using C = XaCfg<E, H, FF>;
     static_assert(FF == E, "this instantiation keeps the FFN hidden tile in the 64-wide layout");
@@ -173,7 +177,9 @@ __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
                         slot = (dim - E) * 16 + 15;
                         val = 0.f;
                     }
-                    qs[row * C::QP + slot] = __float2half_rn(val);
+                    const __half hi = __float2half_rn(val);
+                    qs[row * C::QP + slot] = hi;
+                    if (QSPLIT) qs[C::ROWS * C::QP + row * C::QP + slot] = __float2half_rn(val - __half2float(hi));
                 }
             }
         }
@@ -181,10 +187,12 @@ __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
 
         // ---------------------------------------------------------------- (b) attention core
         uint32_t qf[H][4];
+        uint32_t ql[QSPLIT ? H : 1][4];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             const int row = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
             ldmatrix_x4(qf[h], smem_u32(qs + row * C::QP + h * 16 + 8 * (lane >> 4)));
+            if (QSPLIT) ldmatrix_x4(ql[h], smem_u32(qs + C::ROWS * C::QP + row * C::QP + h * 16 + 8 * (lane >> 4)));
         }
         __syncthreads();   // qs is dead from here on: `at` may be overwritten by the early warps
 
@@ -229,6 +237,10 @@ __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
                     ldmatrix_x4(r, kbase + h * 2048 + key * 32 + ((chunk ^ ((key >> 2) & 1)) << 4));
                     mma_16816(s[2 * kk], qf[h], r[0], r[1]);
                     mma_16816(s[2 * kk + 1], qf[h], r[2], r[3]);
+                    if (QSPLIT) {
+                        mma_16816(s[2 * kk], ql[h], r[0], r[1]);
+                        mma_16816(s[2 * kk + 1], ql[h], r[2], r[3]);
+                    }
                 }
                 if (mask_this) {
 #pragma unroll
@@ -263,10 +275,17 @@ __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     uint32_t pa[4];
-                    pa[0] = exp2_pack_h2(s[2 * kk][0] - mn0, s[2 * kk][1] - mn0);
-                    pa[1] = exp2_pack_h2(s[2 * kk][2] - mn1, s[2 * kk][3] - mn1);
-                    pa[2] = exp2_pack_h2(s[2 * kk + 1][0] - mn0, s[2 * kk + 1][1] - mn0);
-                    pa[3] = exp2_pack_h2(s[2 * kk + 1][2] - mn1, s[2 * kk + 1][3] - mn1);
+                    if (EXP32) {
+                        pa[0] = pack_h2(exp2_fast(s[2 * kk][0] - mn0), exp2_fast(s[2 * kk][1] - mn0));
+                        pa[1] = pack_h2(exp2_fast(s[2 * kk][2] - mn1), exp2_fast(s[2 * kk][3] - mn1));
+                        pa[2] = pack_h2(exp2_fast(s[2 * kk + 1][0] - mn0), exp2_fast(s[2 * kk + 1][1] - mn0));
+                        pa[3] = pack_h2(exp2_fast(s[2 * kk + 1][2] - mn1), exp2_fast(s[2 * kk + 1][3] - mn1));
+                    } else {
+                        pa[0] = exp2_pack_h2(s[2 * kk][0] - mn0, s[2 * kk][1] - mn0);
+                        pa[1] = exp2_pack_h2(s[2 * kk][2] - mn1, s[2 * kk][3] - mn1);
+                        pa[2] = exp2_pack_h2(s[2 * kk + 1][0] - mn0, s[2 * kk + 1][1] - mn0);
+                        pa[3] = exp2_pack_h2(s[2 * kk + 1][2] - mn1, s[2 * kk + 1][3] - mn1);
+                    }
                     const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
                     const int chunk = lane >> 4;
                     uint32_t r[4];
@@ -392,6 +411,17 @@ __global__ void __launch_bounds__(256, 2) xattn_stack_kernel(const XaArgs a) {
 
 using namespace a3d;
 
+// numerics variant of the attention core: bit0 = fp32 exp, bit1 = split-Q (see kernel comment)
+static int g_xattn_variant = 0;
+extern "C" int a3d_set_option(const char* name, int value) {
+    if (name && strcmp(name, "xattn_variant") == 0) {
+        A3D_REQUIRE(value >= 0 && value <= 3, "a3d_set_option: xattn_variant must be 0..3");
+        g_xattn_variant = value;
+        return A3D_OK;
+    }
+    A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");
+}
+
 extern "C" size_t a3d_xattn_layer_floats(int embed, int ffn) {
     if (embed == 60 && ffn == 60) return XaCfg<60, 4, 60>::LAYER_FLOATS;
     return 0;
@@ -428,8 +458,20 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.qvec = qvec;
     a.nqv = nqv;
     a.logits = logits;
-    cudaFuncSetAttribute(xattn_stack_kernel<60, 4, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     dim3 grid((nq + C::ROWS - 1) / C::ROWS, batch);
-    xattn_stack_kernel<60, 4, 60><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(a);
+    const int variant = g_xattn_variant;
+#define A3D_LAUNCH_XA(EXP32, QSPLIT)                                                                                  \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(xattn_stack_kernel<60, 4, 60, EXP32, QSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)C::SMEM);                                                                            \
+        xattn_stack_kernel<60, 4, 60, EXP32, QSPLIT><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(a);                 \
+    } while (0)
+    switch (variant) {
+        case 1: A3D_LAUNCH_XA(true, false); break;
+        case 2: A3D_LAUNCH_XA(false, true); break;
+        case 3: A3D_LAUNCH_XA(true, true); break;
+        default: A3D_LAUNCH_XA(false, false); break;
+    }
+#undef A3D_LAUNCH_XA
     return check_launch("a3d_xattn_stack");
 }

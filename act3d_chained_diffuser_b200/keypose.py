@@ -95,6 +95,7 @@ class Act3D(nn.Module):
         self._sampler_calls = 0
         self._teacher_positions = None      # test hook: list of (B,1,3) fed to the next level
         self._last_topk = None              # debug/test hook: top-k indices per level of the last call
+        self._profile_events = None         # bench hook: list collecting (tag, start, end) CUDA events
 
     # ------------------------------------------------------------------ packed weights
     def _stack_pack(self, tag, stack):
@@ -239,8 +240,15 @@ class Act3D(nn.Module):
             ghost_feats = torch.empty(1, b, ng, e, device=dev) if want_feats else None
             logits = torch.empty(lq, b, ng, device=dev)
             g_x0 = self.ghost_points_embed_pyramid[i].weight.detach().float().contiguous()
+            prof = self._profile_events
+            if prof is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"],
                             feat_out=ghost_feats, feat_rows=ng, qvec=q_all.view(lq, b, e), logits=logits)
+            if prof is not None:
+                ev1.record()
+                prof.append(("ghost_xattn", ev0, ev1))
 
             top_idx, top_pos = lib.argmax_pick(logits[-1], ghost)
             position_i = top_pos.unsqueeze(1)

@@ -17,6 +17,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "a3d_last_error": (c_char_p, []),
     "a3d_abi_version": (c_int, []),
+    "a3d_set_option": (c_int, [c_char_p, c_int]),
     "a3d_pcd_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a3d_local_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_traj_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -59,10 +60,29 @@ def load():
     return lib
 
 
+_launches = 0
+
+
+def launch_count():
+    """Number of kernel-launching C-ABI calls since the last reset (each is exactly one kernel)."""
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
 def _check(code, what):
+    global _launches
+    _launches += 1
     if code != 0:
         msg = load().a3d_last_error()
         raise A3DError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+
+
+def set_option(name, value):
+    _check(load().a3d_set_option(name.encode(), int(value)), "a3d_set_option")
 
 
 def _ptr(t):

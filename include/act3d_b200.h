@@ -37,6 +37,9 @@ extern "C" {
 
 const char* a3d_last_error(void);
 int a3d_abi_version(void);
+/* Process-wide tuning knobs (not part of the numerical contract):
+ *   "xattn_variant": 0 = packed-fp16 exp2 (default), 1 = fp32 exp2, 2 = split-Q, 3 = both. */
+int a3d_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------
  * Point pyramid.  Replaces F.interpolate(pcd, scale_factor=1/f, mode='bilinear') +

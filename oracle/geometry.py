@@ -17,17 +17,14 @@ def pcd_level(pcd_flat: torch.Tensor, factor: int, num_cameras: int) -> torch.Te
 
 
 def pcd_level_closed_form(pcd_flat: torch.Tensor, factor: int, num_cameras: int) -> torch.Tensor:
-    """Same level written as the explicit 2x2 mean the CUDA kernel computes:
-    pixels (f*i + f/2 - 1, f*i + f/2) per axis, weights 1/4 applied as
-    0.5*(0.5*(a+b)) per the separable bilinear evaluation order (W first, then H)."""
+    """Same level written as the explicit 4-tap mean the CUDA kernel computes: the two centre pixels
+    (f*i + f/2 - 1, f*i + f/2) per axis, all weights 0.25, accumulated in raster order
+    (((p00 + p01) + p10) + p11) * 0.25 -- bit-identical to torch's CPU bilinear kernel."""
     f = factor
     lo, hi = f // 2 - 1, f // 2
-    rows_lo = pcd_flat[:, :, lo::f, :]
-    rows_hi = pcd_flat[:, :, hi::f, :]
-
-    def wmix(t):
-        return 0.5 * t[..., lo::f] + 0.5 * t[..., hi::f]
-    lvl = 0.5 * wmix(rows_lo) + 0.5 * wmix(rows_hi)
+    p00, p01 = pcd_flat[:, :, lo::f, lo::f], pcd_flat[:, :, lo::f, hi::f]
+    p10, p11 = pcd_flat[:, :, hi::f, lo::f], pcd_flat[:, :, hi::f, hi::f]
+    lvl = (((p00 + p01) + p10) + p11) * 0.25
     bn, c, h, w = lvl.shape
     b = bn // num_cameras
     return lvl.view(b, num_cameras, c, h, w).permute(0, 1, 3, 4, 2).reshape(b, num_cameras * h * w, c)
