@@ -33,6 +33,16 @@ EXPORTS = {
     "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
                                  c_void_p, c_void_p]),
+    "cd_pack_floats": (c_size_t, [c_int]),
+    "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                            c_void_p]),
+    "cd_step_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cd_cross": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cd_post": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), c_void_p,
+                        c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -188,3 +198,41 @@ def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device):
     _check(load().a3d_sample_ghost(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
                                    int(stream_id), _ptr(out), _stream()), "a3d_sample_ghost")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ planner
+def cd_pack_floats(which):
+    return load().cd_pack_floats({"lang": 0, "ada": 1, "mlp": 2, "ada_row": 3}[which])
+
+
+def cd_ctx_lang(tok, nctx, kin, vin, w, nlayers):
+    b, rows, e = tok.shape
+    _check(load().cd_ctx_lang(_ptr(_f32(tok)), b, rows, nctx, e, 8, _ptr(_f32(kin)), _ptr(_f32(vin)), kin.shape[2],
+                              _ptr(_f32(w)), nlayers, _stream()), "cd_ctx_lang")
+
+
+def cd_step_begin(traj, wp_pe, t_idx, ada, ada_layers, traj_enc, lang_w, lang_k, lang_v, x_out, next_wq, next_ada_layer,
+                  q_out):
+    b, length, _ = traj.shape
+    n_instr = lang_k.shape[1] if lang_k is not None else 0
+    _check(load().cd_step_begin(_ptr(_f32(traj)), b, length, _ptr(wp_pe), _ptr(t_idx), _ptr(ada), ada_layers,
+                                _ptr(traj_enc), _ptr(lang_w), _ptr(lang_k), _ptr(lang_v), n_instr, _ptr(x_out),
+                                next_wq, next_ada_layer, _ptr(q_out), _stream()), "cd_step_begin")
+
+
+def cd_cross(q, kv, kv_offset_bytes, batch, nk, att):
+    _check(load().cd_cross(_ptr(q), kv.data_ptr() + kv_offset_bytes, batch, nk, 8, _ptr(att), _stream()), "cd_cross")
+
+
+def cd_post(traj, mask, wp_pe, t_idx, ada, ada_layers, ada_layer, x_in, att, layer_w, x_out, reg_w=None, reg_out=None,
+            reg_dim=0, next_src=None, next_wq=None, next_ada_layer=0, q_out=None, update=None):
+    """update = dict(last_step, traj_out, pos_upd, cond_data, cond_mask, coef (6 floats), noise_pos, noise_rot) or None"""
+    b, length, _ = traj.shape
+    u = update or {}
+    coef = (c_float * 6)(*[float(x) for x in u.get("coef", [0.0] * 6)])
+    _check(load().cd_post(_ptr(_f32(traj)), b, length, _ptr(mask), _ptr(wp_pe), _ptr(t_idx), _ptr(ada), ada_layers,
+                          ada_layer, _ptr(x_in), _ptr(att), layer_w, _ptr(x_out), reg_w, _ptr(reg_out), reg_dim,
+                          _ptr(next_src), next_wq, next_ada_layer, _ptr(q_out), int(update is not None),
+                          int(u.get("last_step", 0)), _ptr(u.get("traj_out")), _ptr(u.get("pos_upd")),
+                          _ptr(u.get("cond_data")), _ptr(u.get("cond_mask")), coef, _ptr(u.get("noise_pos")),
+                          _ptr(u.get("noise_rot")), _stream()), "cd_post")

@@ -81,3 +81,60 @@ class PackCache:
 
     def clear(self):
         self._store.clear()
+
+
+# ------------------------------------------------------------------------------------------------ planner packs
+def _scaled_q(attn, e, heads):
+    scale = (float(e // heads) ** -0.5) * LOG2E
+    w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
+    return w_in[:e] * scale, b_in[:e] * scale
+
+
+def _ffn_parts(layer, ep, ffp):
+    w1, b1 = layer.ffn_12[0].weight.detach().float(), layer.ffn_12[0].bias.detach().float()
+    w2, b2 = layer.ffn_12[3].weight.detach().float(), layer.ffn_12[3].bias.detach().float()
+    w2t = _kmajor(w2, ep)                                        # (480, 128)
+    w2t = torch.cat([w2t, w2t.new_zeros(ffp - w2t.shape[0], ep)])
+    return [_kmajor(w1, ffp).reshape(-1), _pad_vec(b1, ffp), w2t.reshape(-1), _pad_vec(b2, ep),
+            _pad_vec(layer.norm_122.weight.detach().float(), ep), _pad_vec(layer.norm_122.bias.detach().float(), ep)]
+
+
+def pack_lang_layer(layer, e=120, heads=8, ffp=512):
+    """ParallelAttentionLayer without adaLN/self-attention (vl_attention, traj_lang_attention) -> LangPack
+    (csrc/cd_denoiser.cu): WQ BQ WO BO G12 B12 | W1[E][512] B1 W2[512][128] B2 G122 B122."""
+    ep = 16 * heads
+    wq, bq = _scaled_q(layer.cross_12, e, heads)
+    parts = [_kmajor(wq, ep).reshape(-1), _pad_vec(bq, ep),
+             _kmajor(layer.cross_12.out_proj.weight, ep).reshape(-1), _pad_vec(layer.cross_12.out_proj.bias.detach().float(), ep),
+             _pad_vec(layer.norm_12.weight.detach().float(), ep), _pad_vec(layer.norm_12.bias.detach().float(), ep)]
+    parts += _ffn_parts(layer, ep, ffp)
+    return torch.cat(parts)
+
+
+def pack_ada_layer(layer, e=120, heads=8, ffp=512):
+    """adaLN cross + self + FFN layer -> AdaPack: cross {WQ BQ WO BO G12 B12} self {WQ BQ WK BK WV BV WO BO G1 B1}
+    ffn {W1 B1 W2 B2 G122 B122}.  Both q projections carry hd^-1/2 * log2(e)."""
+    ep = 16 * heads
+    cq, cbq = _scaled_q(layer.cross_12, e, heads)
+    sq, sbq = _scaled_q(layer.sa1, e, heads)
+    w_in, b_in = layer.sa1.in_proj_weight.detach().float(), layer.sa1.in_proj_bias.detach().float()
+    v = lambda t: _pad_vec(t.detach().float(), ep)
+    parts = [_kmajor(cq, ep).reshape(-1), _pad_vec(cbq, ep),
+             _kmajor(layer.cross_12.out_proj.weight, ep).reshape(-1), v(layer.cross_12.out_proj.bias),
+             v(layer.norm_12.weight), v(layer.norm_12.bias),
+             _kmajor(sq, ep).reshape(-1), _pad_vec(sbq, ep),
+             _kmajor(w_in[e:2 * e], ep).reshape(-1), _pad_vec(b_in[e:2 * e], ep),
+             _kmajor(w_in[2 * e:], ep).reshape(-1), _pad_vec(b_in[2 * e:], ep),
+             _kmajor(layer.sa1.out_proj.weight, ep).reshape(-1), v(layer.sa1.out_proj.bias),
+             v(layer.norm_1.weight), v(layer.norm_1.bias)]
+    parts += _ffn_parts(layer, ep, ffp)
+    return torch.cat(parts)
+
+
+def pack_mlp(seq, e=120, ep=128):
+    """nn.Sequential(Linear(in<=E, E), ReLU, [Dropout], Linear(E, out<=EP)) -> MlpPack W1[E][EP] B1 W2[E][EP] B2."""
+    first, last = seq[0], seq[-1]
+    w1 = _kmajor(first.weight, ep)                               # (in, 128)
+    w1 = torch.cat([w1, w1.new_zeros(e - w1.shape[0], ep)])
+    return torch.cat([w1.reshape(-1), _pad_vec(first.bias.detach().float(), ep),
+                      _kmajor(last.weight, ep).reshape(-1), _pad_vec(last.bias.detach().float(), ep)])

@@ -1,12 +1,29 @@
 """ChainedDiffuser trajectory planner on the B200 kernels -- drop-in for the reference's
 model/trajectory_optimization/diffusion_model.py (+ diffusion_head.py, model/utils/encoder.py):
-same ctor kwargs, forward / compute_trajectory signatures and state_dict keys.
+same ctor kwargs, forward / compute_trajectory signatures and state_dict keys (SURVEY.md 8b).
+
+What runs where
+  PyTorch (host code): frozen backbone + FPN (cuDNN), 512->E instruction / gripper token encoders
+      and the adaLN modulation tables (tiny library GEMMs, once per call), quaternion <-> 6D, RNG.
+  libact3d_b200.so: point pyramid, token gather, vision->language attention (cd_ctx_lang), the
+      rotary K/V cache of the context for all 8 cross-attention layers (a3d_ctx_kv), and per
+      denoising step cd_step_begin + 8 x (cd_cross, cd_post) including the DDPM posterior update.
+Unlike the reference, which re-runs the backbone, the FPN and the vision-language attention on
+every one of the 100 steps (diffusion_head.py:222-224), everything that does not depend on the
+trajectory or the timestep is computed once (bit-identical hoist).
 """
+import math
+
 import torch
+import torch.nn.functional as F
 from torch import nn
 from torchvision.ops import FeaturePyramidNetwork
 
+from . import lib
+from .ddpm import PosteriorTable
+from .packing import PackCache, pack_ada_layer, pack_kv_set, pack_lang_layer, pack_mlp
 from .params import ParallelStackParams, mlp
+from .rotations import matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix, quat_to_matrix
 from .trunk import build_backbone
 
 
@@ -17,8 +34,17 @@ def _repeat(n, tie, factory):
     return nn.ModuleList(factory() for _ in range(n))
 
 
+def sinusoidal(t, dim):
+    """[sin(t w_k) | cos(t w_k)], w_k = 1e4^(-k/(dim/2-1))   (position_encodings.py:13-20)."""
+    half = dim // 2
+    w = torch.exp(torch.arange(half, device=t.device) * -(math.log(10000) / (half - 1)))
+    arg = t[:, None] * w[None, :]
+    return torch.cat((arg.sin(), arg.cos()), dim=-1)
+
+
 class DiffusionHead(nn.Module):
-    """Parameter owner with the reference's key names (diffusion_head.py:12-198, encoder.py:14-79)."""
+    """Denoiser.  Owns the parameters under the reference's key names (diffusion_head.py:12-198,
+    encoder.py:14-79) and drives the kernels."""
 
     def __init__(self, backbone="clip", image_size=(256, 256), embedding_dim=60, output_dim=7, num_attn_heads=8,
                  num_vis_ins_attn_layers=2, num_query_cross_attn_layers=6, use_instruction=False, use_goal=False,
@@ -34,6 +60,9 @@ class DiffusionHead(nn.Module):
             raise NotImplementedError("feat_scales_to_use > 1 / attn_rounds > 1 are not built yet (DESIGN.md 'next')")
         if use_sigma:
             raise NotImplementedError("use_sigma is never enabled by the reference's entry points")
+        if embedding_dim != 120 or num_attn_heads != 8:
+            raise NotImplementedError("the sm_100a denoiser kernels are built for embedding_dim=120, 8 heads "
+                                      "(the shipped ChainedDiffuser configuration)")
         self.image_size = tuple(image_size)
         self.embedding_dim, self.num_attn_heads = embedding_dim, num_attn_heads
         self.use_instruction, self.use_goal = use_instruction, use_goal
@@ -67,6 +96,168 @@ class DiffusionHead(nn.Module):
         self.rot_attention = _repeat(n, weight_tying, lambda: ParallelStackParams(2, e, h, **adaln))
         self.pos_regressor = nn.ModuleList(mlp(e, e, 3, dropout=0.1) for _ in range(n))
         self.rot_regressor = nn.ModuleList(mlp(e, e, output_dim - 3, dropout=0.1) for _ in range(n))
+        self._packs = PackCache()
+
+    # ------------------------------------------------------------------ packed weights / tables
+    def _ada_layers(self):
+        return (list(self.traj_attention[0].layers) + list(self.pos_attention[0].layers)
+                + list(self.rot_attention[0].layers))
+
+    def _weights(self, num_timesteps, device):
+        params = [p for n_, p in self.named_parameters() if not n_.startswith(("backbone.", "feature_pyramid."))]
+        e, h = self.embedding_dim, self.num_attn_heads
+
+        def build():
+            layers = self._ada_layers()
+            ada_w = [pack_ada_layer(l, e, h) for l in layers]
+            kv = [pack_kv_set(l.cross_12, e, h) for l in layers]
+            # adaLN modulation of every (timestep, layer): Linear(SiLU(time_emb))   (layers.py:282-290, encoder.py:199)
+            t_emb = F.silu(sinusoidal(torch.arange(num_timesteps, device=device), e).float())
+            rows = []
+            for l in layers:
+                per = []
+                for nm in ("adaln_12", "adaln_1", "adaln_ff1"):
+                    lin = getattr(l, nm).modulation[1]
+                    mod = F.linear(t_emb, lin.weight.detach().float(), lin.bias.detach().float())     # (T, 2E)
+                    per.append(F.pad(mod.view(num_timesteps, 2, e), (0, 16 * h - e)))                 # (T, 2, EP)
+                rows.append(torch.stack(per, dim=1))                                                  # (T, 3, 2, EP)
+            out = dict(
+                ada_w=[w.contiguous() for w in ada_w],
+                wkv=torch.stack([k[0] for k in kv]).contiguous(), bkv=torch.stack([k[1] for k in kv]).contiguous(),
+                ada=torch.stack(rows, dim=1).contiguous(),                                            # (T, nl, 3, 2, EP)
+                traj_enc=pack_mlp(self.traj_encoder, e).contiguous(),
+                pos_reg=pack_mlp(self.pos_regressor[0], e).contiguous(),
+                rot_reg=pack_mlp(self.rot_regressor[0], e).contiguous(),
+                lang=pack_lang_layer(self.traj_lang_attention[0].layers[0], e, h).contiguous(),
+            )
+            if self.use_instruction:
+                out["vl"] = torch.cat([pack_lang_layer(l, e, h) for l in self.vl_attention[0].layers]).contiguous()
+            return out
+        return self._packs.get(("planner", num_timesteps, str(device)), params, build)
+
+    # ------------------------------------------------------------------ step-invariant context
+    def encode_context(self, visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, num_timesteps):
+        """Everything of DiffusionHead.forward that does not depend on the trajectory or the timestep
+        (diffusion_head.py:221-247, 289-323)."""
+        lib.load()
+        e, h = self.embedding_dim, self.num_attn_heads
+        b, ncam = visible_rgb.shape[:2]
+        dev = visible_rgb.device
+        w = self._weights(num_timesteps, dev)
+        rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:])
+        fm = self.feature_pyramid(self.backbone(self.normalize(rgb)))["res3"].contiguous().float()
+        pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
+        pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
+        nctx = pts.shape[1]
+        rows = nctx + 1 + int(self.use_goal)
+        tok = torch.empty(b, rows, e, device=dev)
+        pos = torch.empty(b, rows, 3, device=dev)
+        lib.gather_tokens(fm, pts, None, b, ncam, tok, pos)
+
+        ctx = dict(nk=rows, batch=b)
+        if self.use_instruction:
+            instr = F.linear(instruction.float(), self.instruction_encoder.weight, self.instruction_encoder.bias)
+
+            def instr_kv(attn):
+                wi, bi = attn.in_proj_weight, attn.in_proj_bias
+                return (F.linear(instr, wi[e:2 * e], bi[e:2 * e]).contiguous(),
+                        F.linear(instr, wi[2 * e:], bi[2 * e:]).contiguous())
+            vl_layers = self.vl_attention[0].layers
+            kvs = [instr_kv(l.cross_12) for l in vl_layers]
+            lib.cd_ctx_lang(tok, nctx, torch.stack([k for k, _ in kvs]), torch.stack([v for _, v in kvs]),
+                            w["vl"], len(vl_layers))
+            ctx["lang_k"], ctx["lang_v"] = instr_kv(self.traj_lang_attention[0].layers[0].cross_12)
+        else:
+            ctx["lang_k"] = ctx["lang_v"] = None
+
+        tok[:, nctx] = self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight[0]
+        pos[:, nctx] = curr_gripper[:, :3].float()
+        if self.use_goal:
+            tok[:, nctx + 1] = self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight[0]
+            pos[:, nctx + 1] = goal_gripper[:, :3].float()
+        nl = len(w["ada_w"])
+        ctx["kv"] = lib.ctx_kv(tok, pos, rows, h, w["wkv"], w["bkv"], [1] * nl)
+        ctx["set_bytes"] = lib.kv_bytes(1, b, rows, h)
+        ctx["w"] = w
+        return ctx
+
+    # ------------------------------------------------------------------ one denoiser evaluation
+    def denoise(self, ctx, trajectory, trajectory_mask, t_idx, work, update=None):
+        """One forward of the denoiser on (B, L, 9); returns (pos_upd (B,L,3), rot (B,L,6)) or, with
+        ``update`` (DDPM step arguments), writes the next trajectory in place of returning."""
+        w = ctx["w"]
+        b, length, _ = trajectory.shape
+        n_traj = len(self.traj_attention[0].layers)
+        nl = len(w["ada_w"])
+        ada = w["ada"]
+        xb, att, qb = work["x"], work["att"], work["q"]
+        off = lambda pack, name: pack.data_ptr() + 4 * _ADA_OFF[name]
+        lang_w = w["lang"] if self.use_instruction else None
+        lib.cd_step_begin(trajectory, work["wp_pe"], t_idx, ada, nl, w["traj_enc"], lang_w, ctx["lang_k"], ctx["lang_v"],
+                          xb[0], off(w["ada_w"][0], "C_WQ"), 0, qb)
+        mask = work["mask_u8"]
+        for li in range(nl):
+            lib.cd_cross(qb, ctx["kv"], li * ctx["set_bytes"], b, ctx["nk"], att)
+            kw = {}
+            x_in = xb[li]
+            if li == n_traj:                      # first pos layer and first rot layer both start from the traj stack output
+                x_in = xb[n_traj]
+            if li == n_traj + 2:
+                x_in = xb[n_traj]
+            if li == n_traj + 1:                  # last pos layer: position regressor; next Q comes from the traj output
+                kw.update(reg_w=w["pos_reg"].data_ptr(), reg_out=work["pos_upd"], reg_dim=3, next_src=xb[n_traj])
+            if li == nl - 1:                      # last rot layer: rotation regressor (+ DDPM update)
+                kw.update(reg_w=w["rot_reg"].data_ptr(), reg_out=work["rot_out"], reg_dim=6, update=update)
+            if li + 1 < nl:
+                kw.update(next_wq=off(w["ada_w"][li + 1], "C_WQ"), next_ada_layer=li + 1, q_out=qb)
+            lib.cd_post(trajectory, mask, work["wp_pe"], t_idx, ada, nl, li, x_in, att, w["ada_w"][li].data_ptr(),
+                        xb[li + 1], **kw)
+        return work["pos_upd"], work["rot_out"]
+
+    def make_work(self, b, length, trajectory_mask, device):
+        e = self.embedding_dim
+        nl = len(self._ada_layers())
+        mask_u8 = None
+        if trajectory_mask is not None and bool(trajectory_mask.any()):
+            mask_u8 = trajectory_mask.to(device=device, dtype=torch.uint8).contiguous()
+        return dict(
+            x=torch.empty(nl + 1, b, 64, e, device=device), att=torch.empty(b, 64, e, device=device),
+            q=torch.empty(b, 8, 64, 16, device=device, dtype=torch.float16),
+            pos_upd=torch.empty(b, length, 3, device=device), rot_out=torch.empty(b, length, 6, device=device),
+            wp_pe=sinusoidal(torch.arange(length, device=device), e).float().contiguous(), mask_u8=mask_u8)
+
+    # ------------------------------------------------------------------ reference-compatible forward
+    def forward(self, trajectory, trajectory_mask, timestep, visible_rgb, visible_pcd, curr_gripper, goal_gripper,
+                instruction):
+        """Same contract as diffusion_head.py:200-277: returns a list with one (B, L, 9) tensor."""
+        if not trajectory.is_cuda:
+            raise RuntimeError("DiffusionHead (B200) runs on CUDA tensors only: there is no CPU fallback path")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the denoiser kernels are forward-only in this round; call under torch.no_grad()")
+        n_t = int(timestep.max().item()) + 1
+        ctx = self.encode_context(visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, max(n_t, 100))
+        b, length, _ = trajectory.shape
+        work = self.make_work(b, length, trajectory_mask, trajectory.device)
+        traj = trajectory.float().contiguous()
+        pos_upd, rot = self.denoise(ctx, traj, trajectory_mask, timestep.to(torch.int32).contiguous(), work)
+        return [torch.cat((traj[..., :3] + pos_upd, rot), -1)]
+
+
+def _ada_offsets():
+    e, ep, ffp = 120, 128, 512
+    names = ["C_WQ", "C_BQ", "C_WO", "C_BO", "G12", "B12", "S_WQ", "S_BQ", "S_WK", "S_BK", "S_WV", "S_BV", "S_WO", "S_BO",
+             "G1", "B1N", "W1", "B1", "W2", "B2", "G122", "B122"]
+    sizes = [e * ep, ep, e * ep, ep, ep, ep, e * ep, ep, e * ep, ep, e * ep, ep, e * ep, ep, ep, ep,
+             e * ffp, ffp, ffp * ep, ep, ep, ep]
+    out, o = {}, 0
+    for n_, s_ in zip(names, sizes):
+        out[n_] = o
+        o += s_
+    out["SIZE"] = o
+    return out
+
+
+_ADA_OFF = _ada_offsets()
 
 
 class DiffusionPlanner(nn.Module):
@@ -84,14 +275,124 @@ class DiffusionPlanner(nn.Module):
             num_vis_ins_attn_layers=num_vis_ins_attn_layers, num_query_cross_attn_layers=num_query_cross_attn_layers,
             use_instruction=use_instruction, use_goal=use_goal, feat_scales_to_use=feat_scales_to_use,
             attn_rounds=attn_rounds, weight_tying=weight_tying, rotation_parametrization=rotation_parametrization)
+        self.position_noise_scheduler = PosteriorTable("scaled_linear", diffusion_timesteps)
+        self.rotation_noise_scheduler = PosteriorTable("squaredcos_cap_v2", diffusion_timesteps)
         self.n_steps = diffusion_timesteps
         self.gripper_loc_bounds = torch.tensor(gripper_loc_bounds)
+        self._noise_fn = None          # test hook: callable(shape) -> CPU/GPU tensor, called in the reference's order
 
+    # ------------------------------------------------------------------ frame conversions (torch, elementwise)
+    def normalize_pos(self, pos):
+        lo = self.gripper_loc_bounds[0].float().to(pos.device)
+        hi = self.gripper_loc_bounds[1].float().to(pos.device)
+        return (pos - lo) / (hi - lo) * 2.0 - 1.0
+
+    def unnormalize_pos(self, pos):
+        lo = self.gripper_loc_bounds[0].float().to(pos.device)
+        hi = self.gripper_loc_bounds[1].float().to(pos.device)
+        return (pos + 1.0) / 2.0 * (hi - lo) + lo
+
+    def convert_rot(self, signal):
+        """[xyz, quaternion (taken real-first, as the reference does), rest] -> [xyz, 6D, rest]
+        (diffusion_model.py:197-213)."""
+        quat = normalise_quat(signal[..., 3:7])
+        rot = quat_to_matrix(quat)
+        lead = rot.shape[:-2]
+        r6 = matrix_to_ortho6d(rot.reshape(-1, 3, 3)).reshape(*lead, 6)
+        return torch.cat([signal[..., :3], r6, signal[..., 7:]], dim=-1)
+
+    def unconvert_rot(self, signal):
+        """[xyz, 6D, rest] -> [xyz, quaternion, rest]   (diffusion_model.py:215-230)."""
+        lead = signal.shape[:-1]
+        quat = matrix_to_quat(ortho6d_to_matrix(signal[..., 3:9].reshape(-1, 6))).reshape(*lead, 4)
+        return torch.cat([signal[..., :3], quat, signal[..., 9:]], dim=-1)
+
+    def _randn(self, shape, device):
+        if self._noise_fn is not None:
+            return self._noise_fn(tuple(shape)).to(device=device, dtype=torch.float32).contiguous()
+        return torch.randn(shape, device=device)
+
+    # ------------------------------------------------------------------ sampling
+    @torch.no_grad()
+    def conditional_sample(self, condition_data, condition_mask, fixed_inputs):
+        """100-step DDPM ancestral sampling with inpainting of the conditioned waypoints
+        (diffusion_model.py:86-119).  Gaussian draws are made in the reference's order:
+        (B,L,9) once, then per step (B,L,3) and (B,L,6) for every t > 0."""
+        trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper = fixed_inputs
+        head = self.prediction_head
+        dev = condition_data.device
+        b, length, _ = condition_data.shape
+        self.position_noise_scheduler.set_timesteps(self.n_steps)
+        self.rotation_noise_scheduler.set_timesteps(self.n_steps)
+        timesteps = self.position_noise_scheduler.timesteps
+        ctx = head.encode_context(rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper, self.n_steps)
+        work = head.make_work(b, length, trajectory_mask, dev)
+        cond = condition_data.float().contiguous()
+        cmask = condition_mask.to(torch.uint8).contiguous()
+        traj = (self._randn(cond.shape, dev) + cond).contiguous()
+        t_all = torch.tensor(timesteps, device=dev, dtype=torch.int32)[:, None].repeat(1, b).contiguous()
+        pc, rc = self.position_noise_scheduler.coef, self.rotation_noise_scheduler.coef
+        for k, t in enumerate(timesteps):
+            last = k == len(timesteps) - 1
+            upd = dict(last_step=int(last), traj_out=traj, pos_upd=work["pos_upd"], cond_data=cond, cond_mask=cmask,
+                       coef=[pc[t, 0], pc[t, 1], pc[t, 2], rc[t, 0], rc[t, 1], rc[t, 2]])
+            if not last:
+                upd["noise_pos"] = self._randn((b, length, 3), dev)
+                upd["noise_rot"] = self._randn((b, length, 6), dev)
+            head.denoise(ctx, traj, trajectory_mask, t_all[k], work, update=upd)
+        return traj
+
+    @torch.no_grad()
     def compute_trajectory(self, trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper):
-        raise NotImplementedError("trajectory kernels land in the next commit")
+        """(B, L) mask, (B, ncam, 3, H, W) rgb / world-frame pcd, (B, 53, 512), (B, 7) poses -> (B, L, 7)
+        (diffusion_model.py:121-185)."""
+        if not rgb_obs.is_cuda:
+            raise RuntimeError("DiffusionPlanner (B200) runs on CUDA tensors only: there is no CPU fallback path")
+        dev = rgb_obs.device
+        pcd_n = self.normalize_pos(pcd_obs.float().permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+        cur = curr_gripper.float().clone()
+        goal = goal_gripper.float().clone()
+        cur[:, :3] = self.normalize_pos(cur[:, :3])
+        goal[:, :3] = self.normalize_pos(goal[:, :3])
+        cur, goal = self.convert_rot(cur), self.convert_rot(goal)
+
+        b, d = cur.shape
+        length = trajectory_mask.size(1)
+        cond = torch.zeros(b, length, d, device=dev)
+        cmask = torch.zeros_like(cond)
+        cond[:, 0] = cur
+        cmask[:, 0] = 1
+        if self._use_goal_at_test:
+            n_pad = trajectory_mask.sum(1).long()
+            for i in range(b):
+                neg = -int(n_pad[i])
+                cond[i][neg - 1] = goal[i]
+                cmask[i][neg - 1:] = 1
+        traj = self.conditional_sample(cond, cmask.bool(), (trajectory_mask, rgb_obs, pcd_n, instruction, cur, goal))
+        traj = self.unconvert_rot(traj)
+        traj[:, :, :3] = self.unnormalize_pos(traj[:, :, :3])
+        return traj
 
     def forward(self, gt_trajectory, trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper,
                 run_inference=False):
         if run_inference:
             return self.compute_trajectory(trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper)
-        raise NotImplementedError("training forward (one denoiser call + L1 loss) lands with the backward kernels")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the denoiser kernels are forward-only in this round (backward: DESIGN.md 'next'); "
+                                      "the training loss can be evaluated under torch.no_grad()")
+        # ---- training objective, forward only (diffusion_model.py:253-324)
+        dev = rgb_obs.device
+        gt = gt_trajectory.float().clone()
+        gt[:, :, :3] = self.normalize_pos(gt[:, :, :3])
+        pcd_n = self.normalize_pos(pcd_obs.float().permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+        cur, goal = curr_gripper.float().clone(), goal_gripper.float().clone()
+        cur[:, :3] = self.normalize_pos(cur[:, :3])
+        goal[:, :3] = self.normalize_pos(goal[:, :3])
+        gt, cur, goal = self.convert_rot(gt), self.convert_rot(cur), self.convert_rot(goal)
+        noise = self._randn(gt.shape, dev)
+        t = torch.randint(0, self.n_steps, (len(noise),), device=dev).long()
+        noisy = torch.cat((self.position_noise_scheduler.add_noise(gt[..., :3], noise[..., :3], t),
+                           self.rotation_noise_scheduler.add_noise(gt[..., 3:9], noise[..., 3:9], t)), -1)
+        pred = self.prediction_head(noisy, trajectory_mask, t, rgb_obs, pcd_n, cur, goal, instruction)[-1]
+        return (100 * F.l1_loss(pred[..., :3], gt[..., :3], reduction="mean")
+                + 10 * F.l1_loss(pred[..., 3:9], gt[..., 3:9], reduction="mean"))

@@ -112,6 +112,63 @@ def build_act3d():
     return m.eval()
 
 
+def planner_inputs(batch, ncam, length, seed):
+    from tests.golden import synth
+    g = torch.Generator().manual_seed(seed)
+    lo, hi = torch.tensor(synth.WORKSPACE_LO), torch.tensor(synth.WORKSPACE_HI)
+    rgb = torch.rand(batch, ncam, 3, 256, 256, generator=g)
+    pcd = (lo + torch.rand(batch, ncam, 256, 256, 3, generator=g) * (hi - lo)).permute(0, 1, 4, 2, 3).contiguous()
+    instr = torch.randn(batch, 53, 512, generator=g)
+
+    def pose():
+        q = torch.randn(batch, 4, generator=g)
+        return torch.cat([lo + torch.rand(batch, 3, generator=g) * (hi - lo), q / q.norm(dim=-1, keepdim=True)], -1)
+    return torch.zeros(batch, length, dtype=torch.bool), rgb, pcd, instr, pose(), pose()
+
+
+def build_planner():
+    from tests.golden import synth
+    from model import DiffusionPlanner
+    torch.manual_seed(0)
+    w = PLANNER_WORKLOAD
+    m = DiffusionPlanner(backbone="resnet", image_size=(256, 256), embedding_dim=w["embed"], output_dim=7,
+                         num_vis_ins_attn_layers=2, num_query_cross_attn_layers=6, use_instruction=True, use_goal=True,
+                         use_goal_at_test=False, weight_tying=True, gripper_loc_bounds=synth.BOUNDS,
+                         rotation_parametrization="6D", diffusion_timesteps=w["steps"])
+    return m.eval()
+
+
+def planner_step_fn(device):
+    w = PLANNER_WORKLOAD
+    m = build_planner().to(device)
+    ins = [t.to(device) for t in planner_inputs(w["batch"], w["ncam"], w["length"], 5)]
+    return lambda: m.compute_trajectory(*ins)
+
+
+def run_planner(rank, world, device, iters=3):
+    """Secondary figure: denoise-steps/s = B * 100 / time of one compute_trajectory (incl. the one-off context encode)."""
+    w = PLANNER_WORKLOAD
+    fn = planner_step_fn(device)
+    fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    return {"metric": "denoise-steps/s", "value": round(w["batch"] * w["steps"] * world / (ms * 1e-3), 1),
+            "ms_per_trajectory_batch": round(ms, 3),
+            "workload": "ChainedDiffuser compute_trajectory C3: batch 32/GPU, 50 waypoints, 100 DDPM steps, 4 views, E=120 H=8"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank, world, device):
     from act3d_chained_diffuser_b200 import lib
@@ -202,6 +259,8 @@ def run_ours(args, rank, world, device):
         "clocks": clk,
         "roofline": roof,
     }
+    if not args.no_planner:
+        line["secondary"] = run_planner(rank, world, device)
     return line
 
 
@@ -257,6 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-planner", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 

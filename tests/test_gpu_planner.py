@@ -1,0 +1,100 @@
+"""GPU: ChainedDiffuser denoiser + 100-step sampling loop through the drop-in module, against the
+golden vectors (unmodified reference) and the CPU oracle.  Tolerances:
+single denoiser call rel-L2 <= 1e-3; full loop with identical injected noise: position max-abs
+<= 1e-3 (world metres), quaternion max-abs <= 2e-3."""
+import os
+
+import pytest
+import torch
+
+from oracle import act3d_ref, planner_ref
+from tests.golden import cases, synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def build(**over):
+    from model import DiffusionPlanner
+    kw = dict(cases.PLANNER_KW, **over)
+    m = DiffusionPlanner(**kw).eval()
+    cases.install_synth_trunk(m.prediction_head, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    return m, kw
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_diffusion_head_matches_golden():
+    g = torch.load(os.path.join(G, "diffusion_head.pt"), weights_only=False)
+    m, _ = build()
+    m = m.cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.7)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    t = torch.tensor([37, 5])
+    assert synth.checksum(traj, cur, goal, t) == g["check"]
+    pcd_n = m.normalize_pos(inp["pcd_obs"].cuda().permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+    with torch.no_grad():
+        out = m.prediction_head(traj.cuda(), inp["trajectory_mask"].cuda(), t.cuda(), inp["rgb_obs"].cuda(), pcd_n,
+                                cur.cuda(), goal.cuda(), inp["instruction"].cuda())[-1].cpu()
+    # masked (padded) waypoints are don't-care in the reference too, but they are still computed: compare all rows
+    assert torch.isfinite(out).all()
+    assert rel(out, g["out"]) <= 1e-3, rel(out, g["out"])
+    assert (out - g["out"]).abs().max() <= 3e-3 * g["out"].abs().max()
+
+
+def test_planner_100_steps_matches_golden():
+    g = torch.load(os.path.join(G, "planner_100step.pt"), weights_only=False)
+    m, _ = build()
+    m = m.cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    assert synth.checksum(inp["curr_gripper"], inp["goal_gripper"]) == g["check"]
+    m._noise_fn = synth.NoiseStream("cd")
+    traj = m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                         "curr_gripper", "goal_gripper")]).cpu()
+    want = g["trajectory"]
+    assert traj.shape == want.shape == (2, 12, 7)
+    assert (traj[..., :3] - want[..., :3]).abs().max() <= 1e-3, (traj[..., :3] - want[..., :3]).abs().max()
+    qd = torch.minimum((traj[..., 3:] - want[..., 3:]).abs().max(-1).values, (traj[..., 3:] + want[..., 3:]).abs().max(-1).values)
+    assert qd.max() <= 2e-3, qd.max()
+    assert torch.allclose(traj[..., 3:].norm(dim=-1), torch.ones(2, 12), atol=1e-5)
+
+
+def test_denoiser_vs_oracle_full_length_multicam():
+    """L = 50 waypoints, 2 cameras, no padding mask, goal conditioning at test time, untied weights."""
+    m, kw = build(weight_tying=False, use_goal_at_test=True)
+    inp = cases.planner_inputs(batch=3, ncam=2, length=50, seed=4)
+    head_sd = {k[len("prediction_head."):]: v for k, v in m.state_dict().items() if k.startswith("prediction_head.")}
+    cfg = planner_ref.PlannerConfig(gripper_loc_bounds=synth.BOUNDS, use_goal_at_test=True)
+    with torch.no_grad():
+        want = planner_ref.compute_trajectory(head_sd, cfg, act3d_ref.trunk_from_module(m.prediction_head),
+                                              inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"], inp["instruction"],
+                                              inp["curr_gripper"], inp["goal_gripper"], noise_fn=synth.NoiseStream("v"),
+                                              n_steps=100)
+    m = m.cuda()
+    m._noise_fn = synth.NoiseStream("v")
+    got = m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                        "curr_gripper", "goal_gripper")]).cpu()
+    assert (got[..., :3] - want[..., :3]).abs().max() <= 1e-3
+    qd = torch.minimum((got[..., 3:] - want[..., 3:]).abs().max(-1).values, (got[..., 3:] + want[..., 3:]).abs().max(-1).values)
+    assert qd.max() <= 2e-3
+    # inpainting: first waypoint = current pose, last = goal pose (position part)
+    assert (got[:, 0, :3] - inp["curr_gripper"][:, :3]).abs().max() <= 1e-5
+    assert (got[:, -1, :3] - inp["goal_gripper"][:, :3]).abs().max() <= 1e-5
+
+
+def test_training_loss_forward_only():
+    m, _ = build()
+    m = m.cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12)
+    gt = torch.cat([synth.points_in_bounds("gt.p", (2, 12)), torch.nn.functional.normalize(synth.normal("gt.q", (2, 12, 4)), dim=-1)], -1)
+    with pytest.raises(NotImplementedError):
+        m(gt.cuda(), *[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction", "curr_gripper", "goal_gripper")])
+    with torch.no_grad():
+        loss = m(gt.cuda(), *[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction", "curr_gripper", "goal_gripper")])
+    assert loss.dim() == 0 and torch.isfinite(loss)
