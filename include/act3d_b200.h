@@ -44,8 +44,9 @@ int a3d_set_option(const char* name, int value);
 /* ---------------------------------------------------------------------------------
  * Point pyramid.  Replaces F.interpolate(pcd, scale_factor=1/f, mode='bilinear') +
  * rearrange "(bt ncam) c h w -> bt (ncam h w) c"   (act3d.py:379-383, encoder.py:147-158).
- * pcd [BN][3][H][W] -> out [BN*(H/f)*(W/f)][3].  f in {2,4,8}.  Bit-exact w.r.t. the
- * reference's separable half-weights (0.25*((a+b)+(c+d))).
+ * pcd [BN][3][H][W] -> out [BN*(H/f)*(W/f)][3].  f in {2,4,8}.  All four taps weigh 0.25 and
+ * are accumulated in raster order, 0.25*(((p00+p01)+p10)+p11): bit-identical to torch's CPU
+ * bilinear kernel in its single-thread form (its multi-thread form differs from itself by 1 ulp).
  */
 int a3d_pcd_pyramid(const float* pcd, int bn, int height, int width, int factor, float* out, void* stream);
 
@@ -136,6 +137,51 @@ int a3d_argmax_pick(const float* logits, const float* ghost, int batch, int ng,
  */
 int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
                      uint64_t seed, uint64_t stream_id, float* out, void* stream);
+
+/* =================================================================================
+ * ChainedDiffuser trajectory denoiser (embedding_dim 120, 8 heads, FFN 480, <= 64 waypoints).
+ * Packed weight layouts (all fp32, K-major, padded to 128 / 512 columns) are produced by
+ * act3d_chained_diffuser_b200/packing.py: pack_lang_layer / pack_ada_layer / pack_mlp;
+ * cd_pack_floats(0|1|2|3) returns the float count of a LangPack / AdaPack / MlpPack / adaLN row.
+ */
+size_t cd_pack_floats(int which);
+
+/* Vision -> language attention, step-invariant.  Replaces the vl_attention ParallelAttention stack
+ * (diffusion_head.py:305-314; layers.py:115-218 with cross_attention1 only + FFN, no adaLN/rotary).
+ * tok [B][tok_rows][E]: first nctx rows updated in place.  kin / vin [nlayers][B][n_instr][E]:
+ * fp32 K and V projections of the instruction tokens.  w: nlayers LangPacks. */
+int cd_ctx_lang(float* tok, int batch, int tok_rows, int nctx, int embed, int heads, const float* kin,
+                const float* vin, int n_instr, const float* w, int nlayers, void* stream);
+
+/* Start of one denoiser evaluation.  Replaces traj_encoder + waypoint sinusoidal embedding +
+ * traj_lang_attention (diffusion_head.py:215-216, 326-336) and prepares the fp16 rotary Q of the
+ * first adaLN cross-attention layer.  traj [B][L][9] (normalised frame), wp_pe [L][E], t_idx [B]
+ * timestep per sample, ada [T][ada_layers][3][2][128] adaLN (scale, shift) table, traj_enc MlpPack,
+ * lang_w LangPack or NULL (use_instruction=0), lang_k / lang_v [B][n_instr][E], x_out [B][64][E],
+ * next_wq -> {W_q^T [E][128], b_q[128]} of the next cross-attention, q_out [B][H][64][16] fp16. */
+int cd_step_begin(const float* traj, int batch, int length, const float* wp_pe, const int* t_idx,
+                  const float* ada, int ada_layers, const float* traj_enc, const float* lang_w,
+                  const float* lang_k, const float* lang_v, int n_instr, float* x_out,
+                  const float* next_wq, int next_ada_layer, void* q_out, void* stream);
+
+/* Cross-attention of the waypoint tokens over the cached context K/V of one layer (tile images from
+ * a3d_ctx_kv).  Replaces the cross_12 attention core of ParallelAttentionLayer (layers.py:135-145;
+ * multihead_custom_attention.py:355-451).  q [B][H][64][16] fp16, att [B][64][E] (heads concatenated). */
+int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float* att, void* stream);
+
+/* Rest of one adaLN layer.  Replaces out-proj + norm_12, the adaLN self-attention (rotary q/k,
+ * key padding mask) + norm_1, the adaLN FFN + norm_122 (layers.py:146-209, 273-290), optionally a
+ * regressor head (diffusion_head.py:179-198, 357-363), the Q of the next layer, and -- on the last
+ * layer of a step -- the denoiser output assembly (diffusion_head.py:271-274), inpainting of the
+ * conditioned waypoints and the DDPM posterior step of both schedulers (diffusion_model.py:105-117).
+ * coef_host = {c_x0, c_xt, sigma} for positions then rotations (act3d_chained_diffuser_b200/ddpm.py). */
+int cd_post(const float* traj, int batch, int length, const unsigned char* mask, const float* wp_pe,
+            const int* t_idx, const float* ada, int ada_layers, int ada_layer, const float* x_in,
+            const float* att, const float* layer_w, float* x_out, const float* reg_w, float* reg_out,
+            int reg_dim, const float* next_src, const float* next_wq, int next_ada_layer, void* q_out,
+            int do_update, int last_step, float* traj_out, const float* pos_upd, const float* cond_data,
+            const unsigned char* cond_mask, const float* coef_host, const float* noise_pos,
+            const float* noise_rot, void* stream);
 
 #ifdef __cplusplus
 }
