@@ -46,11 +46,13 @@ __device__ __forceinline__ void store_tile(float* __restrict__ dst, const float*
     }
 }
 
+// (FFMA path, used only for the K = 9 trajectory-encoder layer; threads >= 256 idle)
 // out[c][r] = act( sum_k in[k][r] * W^T[k][c] + bias[c] )  for c < 128 (one pass), optional ReLU.
 // wt: [KD][NP] K-major, `col0` selects a 128-column window.
 template <int KD, int NP, bool RELU>
 __device__ __forceinline__ void linear_to_smem(const Map& m, const float* __restrict__ in, const float* __restrict__ wt,
                                                const float* __restrict__ bias, int col0, float* __restrict__ out) {
+    if (threadIdx.x >= 256) return;
     float acc[2][16];
     gemm_2x16<KD, RP, NP>(in, wt + col0, m.rg, m.cg, acc);
 #pragma unroll
@@ -61,7 +63,7 @@ __device__ __forceinline__ void linear_to_smem(const Map& m, const float* __rest
             v0 = fmaxf(v0, 0.f);
             v1 = fmaxf(v1, 0.f);
         }
-        *reinterpret_cast<float2*>(out + (16 * m.cg + c) * RP + 2 * m.rg) = make_float2(v0, v1);
+        if (16 * m.cg + c < E) *reinterpret_cast<float2*>(out + (16 * m.cg + c) * RP + 2 * m.rg) = make_float2(v0, v1);
     }
 }
 
@@ -116,28 +118,41 @@ __device__ __forceinline__ void linear_rope_to_smem(const Map& m, const float* _
 }
 
 // x[c][r] <- LayerNorm_c( x[c][r] + add[c][r] ) * g + b, rows 0..63 (4 threads per row).  add may be null.
+// LPR = lanes cooperating on one row = blockDim.x / 64 (4 for 256 threads, 8 for 512)
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int LPR>
+__device__ __forceinline__ float row_max(float v) {
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int LPR>
 __device__ __forceinline__ void residual_layernorm(float* __restrict__ x, const float* __restrict__ add,
                                                    const float* __restrict__ g, const float* __restrict__ b) {
-    const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int r = threadIdx.x / LPR, part = threadIdx.x % LPR;
     float s = 0.f;
-    for (int c = part; c < E; c += 4) {
+    for (int c = part; c < E; c += LPR) {
         float v = x[c * RP + r];
         if (add) v += add[c * RP + r];
         x[c * RP + r] = v;
         s += v;
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s = row_sum<LPR>(s);
     const float mean = s * (1.0f / E);
     float v2 = 0.f;
-    for (int c = part; c < E; c += 4) {
+    for (int c = part; c < E; c += LPR) {
         const float d = x[c * RP + r] - mean;
         v2 = fmaf(d, d, v2);
     }
-    v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
-    v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
+    v2 = row_sum<LPR>(v2);
     const float rstd = 1.0f / sqrtf(v2 * (1.0f / E) + 1e-5f);
-    for (int c = part; c < E; c += 4) x[c * RP + r] = (x[c * RP + r] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+    for (int c = part; c < E; c += LPR) x[c * RP + r] = (x[c * RP + r] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
 }
 
 // dst[c][r] = (src[c][r] + pe[r][c]) * (1 + scale[c]) + shift[c]; pe / scale / shift may be null
@@ -158,40 +173,49 @@ __device__ __forceinline__ void modulate(float* __restrict__ dst, const float* _
 // hd^-1/2 * log2(e).  key_mask[j] != 0 => key j ignored (key_padding_mask, layers.py:178).
 // scores: [64][65] scratch.  out may alias q (each head's q columns are consumed before its
 // output columns are written).
+template <int LPR>
 __device__ __forceinline__ void small_mha(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                           int nk, const unsigned char* __restrict__ key_mask, float* __restrict__ scores,
                                           float* __restrict__ out) {
-    const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int i = threadIdx.x / LPR, part = threadIdx.x % LPR;
     for (int h = 0; h < H; ++h) {
         const int d0 = h * HD;
         float qv[HD];
 #pragma unroll
         for (int d = 0; d < HD; ++d) qv[d] = q[(d0 + d) * RP + i];
         float mx = -INFINITY;
-        for (int j = part; j < nk; j += 4) {
-            float s = 0.f;
+        for (int j = part; j < nk; j += LPR) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;   // three independent chains hide the FMA latency
 #pragma unroll
-            for (int d = 0; d < HD; ++d) s = fmaf(qv[d], k[(d0 + d) * RP + j], s);
+            for (int d = 0; d < HD; d += 3) {
+                s0 = fmaf(qv[d], k[(d0 + d) * RP + j], s0);
+                s1 = fmaf(qv[d + 1], k[(d0 + d + 1) * RP + j], s1);
+                s2 = fmaf(qv[d + 2], k[(d0 + d + 2) * RP + j], s2);
+            }
+            float s = (s0 + s1) + s2;
             if (key_mask && key_mask[j]) s = -INFINITY;
             scores[i * 65 + j] = s;
             mx = fmaxf(mx, s);
         }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        mx = row_max<LPR>(mx);
         float sum = 0.f;
-        for (int j = part; j < nk; j += 4) {
+        for (int j = part; j < nk; j += LPR) {
             const float p = exp2f(scores[i * 65 + j] - mx);
             scores[i * 65 + j] = p;
             sum += p;
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum = row_sum<LPR>(sum);
         const float inv = 1.0f / sum;
-        __syncwarp();   // the 4 lanes of a row share its score row
-        for (int d = part; d < HD; d += 4) {
-            float o = 0.f;
-            for (int j = 0; j < nk; ++j) o = fmaf(scores[i * 65 + j], v[(d0 + d) * RP + j], o);
-            out[(d0 + d) * RP + i] = o * inv;
+        __syncwarp();   // the LPR lanes of a row share its score row
+        for (int d = part; d < HD; d += LPR) {
+            float o0 = 0.f, o1 = 0.f;
+            int j = 0;
+            for (; j + 1 < nk; j += 2) {
+                o0 = fmaf(scores[i * 65 + j], v[(d0 + d) * RP + j], o0);
+                o1 = fmaf(scores[i * 65 + j + 1], v[(d0 + d) * RP + j + 1], o1);
+            }
+            if (j < nk) o0 = fmaf(scores[i * 65 + j], v[(d0 + d) * RP + j], o0);
+            out[(d0 + d) * RP + i] = (o0 + o1) * inv;
         }
         __syncwarp();
     }

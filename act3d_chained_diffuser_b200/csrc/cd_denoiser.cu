@@ -10,52 +10,80 @@
 //
 // Everything that does not depend on the trajectory or the timestep is hoisted out of the loop
 // (SURVEY.md F6): context K/V for the 8 layers (a3d_ctx_kv), instruction K/V, adaLN tables.
+//
+// All E x E / E x 4E linear layers run on the tensor cores through the error-compensated fp16-split
+// GEMM of a3d_mma_gemm.cuh (fp32-class accuracy); one CTA owns the 64-row token tile of a sample:
+// residual stream fp32 K-major in shared memory, GEMM inputs as fp16 (hi, lo) row-major planes.
+#include "a3d_mma_gemm.cuh"
 #include "cd_blocks.cuh"
 
 namespace a3d {
 namespace cd {
 
-// ------------------------------------------------------------------ packed weight layouts (floats)
-// "lang" layer = ParallelAttentionLayer without adaLN / self-attention (vl_attention, traj_lang_attention)
-struct LangPack {
-    static constexpr int WQ = 0, BQ = WQ + E * EP, WO = BQ + EP, BO = WO + E * EP, G12 = BO + EP, B12 = G12 + EP;
-    static constexpr int W1 = B12 + EP, B1 = W1 + E * FFP, W2 = B1 + FFP, B2 = W2 + FFP * EP, G122 = B2 + EP,
-                         B122 = G122 + EP;
-    static constexpr int SIZE = B122 + EP;
+constexpr int THREADS = 512;               // 16 warps: 4 m tiles x 4 n parts
+constexpr int LPR = THREADS / ROWS;        // lanes per row in the row-wise passes
+constexpr int NTW = 4;                     // n tiles per warp in the CTA GEMM
+constexpr int PITCH = 136;                 // halfs per row of an A plane (272 B: conflict-free ldmatrix)
+constexpr int PLANE = ROWS * PITCH;        // halfs per plane
+constexpr int FRAG = 32;                   // uint4 per (k step, n tile)
+constexpr int U = 8 * 16 * FRAG;           // uint4 of one [K=128][N=128] weight
+
+// ------------------------------------------------------------------ packed weight layouts
+// fragment-ordered fp16 (hi, lo) weights, offsets in uint4 (packing.py mirrors these tables)
+struct LangW { static constexpr int WQ = 0, WO = U, W1 = 2 * U, W2 = W1 + 8 * 64 * FRAG, SIZE = W2 + 32 * 16 * FRAG; };
+struct AdaW {
+    static constexpr int C_WQ = 0, C_WO = U, S_WQ = 2 * U, S_WK = 3 * U, S_WV = 4 * U, S_WO = 5 * U, W1 = 6 * U,
+                         W2 = W1 + 8 * 64 * FRAG, SIZE = W2 + 32 * 16 * FRAG;
 };
-// "ada" layer = adaLN cross + self + FFN layer (traj_attention / pos_attention / rot_attention)
-struct AdaPack {
-    static constexpr int C_WQ = 0, C_BQ = C_WQ + E * EP, C_WO = C_BQ + EP, C_BO = C_WO + E * EP, G12 = C_BO + EP,
-                         B12 = G12 + EP;
-    static constexpr int S_WQ = B12 + EP, S_BQ = S_WQ + E * EP, S_WK = S_BQ + EP, S_BK = S_WK + E * EP,
-                         S_WV = S_BK + EP, S_BV = S_WV + E * EP, S_WO = S_BV + EP, S_BO = S_WO + E * EP,
-                         G1 = S_BO + EP, B1N = G1 + EP;
-    static constexpr int W1 = B1N + EP, B1 = W1 + E * FFP, W2 = B1 + FFP, B2 = W2 + FFP * EP, G122 = B2 + EP,
-                         B122 = G122 + EP;
-    static constexpr int SIZE = B122 + EP;
+struct MlpW { static constexpr int W1 = 0, W2 = U, SIZE = 2 * U; };
+// fp32 vectors (biases, LayerNorm), offsets in floats
+struct LangV { static constexpr int BQ = 0, BO = EP, G12 = 2 * EP, B12 = 3 * EP, B1 = 4 * EP, B2 = B1 + FFP, G122 = B2 + EP, B122 = G122 + EP, SIZE = B122 + EP; };
+struct AdaV {
+    static constexpr int C_BQ = 0, C_BO = EP, G12 = 2 * EP, B12 = 3 * EP, S_BQ = 4 * EP, S_BK = 5 * EP, S_BV = 6 * EP,
+                         S_BO = 7 * EP, G1 = 8 * EP, B1N = 9 * EP, B1 = 10 * EP, B2 = B1 + FFP, G122 = B2 + EP,
+                         B122 = G122 + EP, SIZE = B122 + EP;
 };
-// two-layer MLP head E -> E -> out (traj_encoder uses in = 9)
-struct MlpPack {
-    static constexpr int W1 = 0, B1 = W1 + E * EP, W2 = B1 + EP, B2 = W2 + E * EP;
-    static constexpr int SIZE = B2 + EP;
-};
+struct MlpV { static constexpr int B1 = 0, B2 = EP, SIZE = 2 * EP; };
 constexpr int ADA_ROW = 3 * 2 * EP;   // per (timestep, layer): {adaln_12, adaln_1, adaln_ff1} x {scale, shift}
 
-constexpr size_t SMEM_POST = (size_t)5 * TILE * 4 + 64 * 65 * 4 + 64 * 3 * 4 + 32 * 4 + 64;
+// ------------------------------------------------------------------ shared memory map
+constexpr int TILE_E = E * RP;             // floats of a K-major activation tile (only the E real channels are stored)
+constexpr size_t SMEM_BYTES = (size_t)4 * TILE_E * 4 + (size_t)4 * PLANE * 2 + (size_t)kRingStages * kSlabBytes +
+                              64 * 3 * 4 + 32 * 4 + 64 + 16;
 
 struct Smem {
-    float *xs, *t1, *t2, *t3, *t4, *scores, *xyz, *freq;
+    float *xs, *t1, *t2, *t3, *scores, *xyz, *freq;
+    __half *ah, *al, *hh, *hl;
     unsigned char* mask;
+    WeightRing ring;
     __device__ explicit Smem(unsigned char* base) {
-        xs = reinterpret_cast<float*>(base);
-        t1 = xs + TILE;
-        t2 = t1 + TILE;
-        t3 = t2 + TILE;
-        t4 = t3 + TILE;
-        scores = t4 + TILE;
-        xyz = scores + 64 * 65;
+        ring.buf = base;                                // 16-byte aligned weight ring first
+        ring.head_of = nullptr;
+        xs = reinterpret_cast<float*>(base + kRingStages * kSlabBytes);
+        t1 = xs + TILE_E;
+        t2 = t1 + TILE_E;
+        t3 = t2 + TILE_E;
+        ah = reinterpret_cast<__half*>(t3 + TILE_E);
+        al = ah + PLANE;
+        hh = al + PLANE;
+        hl = hh + PLANE;
+        scores = reinterpret_cast<float*>(hh);          // aliases the hidden planes (never live together)
+        xyz = reinterpret_cast<float*>(hl + PLANE);
         freq = xyz + 64 * 3;
         mask = reinterpret_cast<unsigned char*>(freq + 32);
+    }
+};
+
+struct WarpMap {
+    int tid, lane, warp, m0, nh, g, q4;
+    __device__ WarpMap() {
+        tid = threadIdx.x;
+        lane = tid & 31;
+        warp = tid >> 5;
+        m0 = 16 * (warp & 3);
+        nh = warp >> 2;                         // n part 0..3 (4 n tiles each)
+        g = lane >> 2;
+        q4 = lane & 3;
     }
 };
 
@@ -70,33 +98,194 @@ __device__ __forceinline__ void init_common(const Smem& s, const float* traj_b, 
     if (t < 64) s.mask[t] = (mask_b && t < nrows) ? mask_b[t] : 0;
 }
 
-// FFN with hidden 480 processed in four 128-wide chunks: out = W2 relu(W1 y + b1) + b2  -> dst tile
-__device__ __forceinline__ void ffn_chunked(const Map& m, const float* y, const float* w1, const float* b1,
-                                            const float* w2, const float* b2, float* hidden, float* dst) {
-    float sum[2][16];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int c = 0; c < 16; ++c) sum[r][c] = 0.f;
-    for (int ch = 0; ch < FFP / 128; ++ch) {
-        linear_to_smem<E, FFP, true>(m, y, w1, b1, ch * 128, hidden);
-        __syncthreads();
-        linear_accumulate<128, EP>(m, hidden, w2 + (size_t)ch * 128 * EP, sum);
-        __syncthreads();
+// ---- producers of GEMM input planes ----------------------------------------------------------
+// planes[r][c] = split( (src[c][r] + pe[r][c]) * (1 + scale[c]) + shift[c] ), optional fp32 copy (K-major)
+__device__ __forceinline__ void planes_from_tile(const float* __restrict__ src, const float* __restrict__ pe,
+                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                 int nrows, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                 float* __restrict__ f32_out) {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < ROWS * (EP / 2); i += blockDim.x) {
+        const int r = i >> 6, c = (i & 63) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (c < E) {
+            v0 = src[c * RP + r];
+            v1 = src[(c + 1) * RP + r];
+            if (pe && r < nrows) {
+                v0 += __ldg(pe + r * E + c);
+                v1 += __ldg(pe + r * E + c + 1);
+            }
+            if (scale) {
+                v0 = v0 * (1.0f + __ldg(scale + c)) + __ldg(shift + c);
+                v1 = v1 * (1.0f + __ldg(scale + c + 1)) + __ldg(shift + c + 1);
+            }
+            if (f32_out) {
+                f32_out[c * RP + r] = v0;
+                f32_out[(c + 1) * RP + r] = v1;
+            }
+        }
+        uint32_t h, l;
+        split_h2(v0, v1, h, l);
+        *reinterpret_cast<uint32_t*>(hi + r * PITCH + c) = h;
+        *reinterpret_cast<uint32_t*>(lo + r * PITCH + c) = l;
     }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float b = __ldg(b2 + 16 * m.cg + c);
-        *reinterpret_cast<float2*>(dst + (16 * m.cg + c) * RP + 2 * m.rg) = make_float2(sum[0][c] + b, sum[1][c] + b);
+}
+// planes from a row-major global matrix [nrows][ld] (zero padded to 64 x 128)
+__device__ __forceinline__ void planes_from_global(const float* __restrict__ src, int nrows, int ld, int ncols,
+                                                   __half* __restrict__ hi, __half* __restrict__ lo) {
+    for (int i = threadIdx.x; i < ROWS * (EP / 2); i += blockDim.x) {
+        const int r = i >> 6, c = (i & 63) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (r < nrows && c < ncols) {
+            v0 = __ldg(src + (size_t)r * ld + c);
+            v1 = (c + 1 < ncols) ? __ldg(src + (size_t)r * ld + c + 1) : 0.f;
+        }
+        uint32_t h, l;
+        split_h2(v0, v1, h, l);
+        *reinterpret_cast<uint32_t*>(hi + r * PITCH + c) = h;
+        *reinterpret_cast<uint32_t*>(lo + r * PITCH + c) = l;
     }
 }
 
-// Q (K-major fp32 tile, already rotated / scaled) -> global fp16 [H][64][16], pad slot zero
-__device__ __forceinline__ void write_q_half(const float* q, __half* dst) {
-    for (int i = threadIdx.x; i < H * ROWS * 16; i += blockDim.x) {
-        const int d = i & 15, r = (i >> 4) & 63, h = i >> 10;
-        dst[i] = __float2half_rn(d < HD ? q[(h * HD + d) * RP + r] : 0.f);
+// ---- the 64 x 128 GEMM of one CTA: warp = (m tile, n half), eight n tiles per warp, weights via the smem ring
+// epi(row, col, v0, v1) receives output elements (row, col) and (row, col + 1), col relative to the window
+template <class Epi>
+__device__ __forceinline__ void gemm64(const WarpMap& w, Smem& s, const __half* ah, const __half* al, const uint4* wfrag,
+                                       int ntiles_total, int nt_base, Epi epi) {
+    float acc[NTW][4];
+    mma_gemm_split_cta<8, PITCH, NTW>(ah, al, w.m0, w.nh, s.ring, wfrag, ntiles_total, nt_base, w.lane, acc);
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) {
+        const int col = 8 * (NTW * w.nh + n) + 2 * w.q4;
+        epi(w.m0 + w.g, col, acc[n][0], acc[n][1]);
+        epi(w.m0 + w.g + 8, col, acc[n][2], acc[n][3]);
     }
+}
+// early fetch of the first weight slabs of the next GEMM; legal right after a __syncthreads that follows the last GEMM
+__device__ __forceinline__ void prefetch_w(Smem& s, const uint4* wfrag, int ntiles_total = 16, int nt_base = 0) {
+    ring_prefetch_head<8>(s.ring, wfrag, ntiles_total, nt_base);
+}
+
+// out tile (K-major fp32) = A W^T + bias
+__device__ __forceinline__ void linear_tile(const WarpMap& w, Smem& s, const __half* ah, const __half* al, const uint4* wf,
+                                            const float* __restrict__ bias, float* __restrict__ out) {
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+        if (c < E) {
+            out[c * RP + r] = v0 + __ldg(bias + c);
+            out[(c + 1) * RP + r] = v1 + __ldg(bias + c + 1);
+        }
+    });
+}
+// rotary variant: the accumulator pair (c, c+1) is exactly rotary pair c/2 of row r
+__device__ __forceinline__ void rotate_pair(const Smem& s, int r, int c, float& v0, float& v1) {
+    const int pi = c >> 1;
+    if (pi < NPAIR) {
+        const int axis = pi / (E / 6), j = pi - axis * (E / 6);
+        // |angle| is a few radians at most (normalised coordinates x frequency <= 1): one step of
+        // 2*pi range reduction + the fast SFU sine/cosine (abs error ~5e-7) instead of libm's sincosf
+        float ang = __fmul_rn(s.xyz[r * 3 + axis], s.freq[j]);
+        ang = fmaf(-6.283185307179586f, rintf(ang * 0.15915494309189535f), ang);
+        float sv, cv;
+        __sincosf(ang, &sv, &cv);
+        const float ev = v0, od = v1;
+        v0 = ev * cv - od * sv;
+        v1 = od * cv + ev * sv;
+    }
+}
+__device__ __forceinline__ void linear_rope_tile(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
+                                                 const uint4* wf, const float* __restrict__ bias, float* __restrict__ out) {
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+        if (c < E) {
+            v0 += __ldg(bias + c);
+            v1 += __ldg(bias + c + 1);
+            rotate_pair(s, r, c, v0, v1);
+            out[c * RP + r] = v0;
+            out[(c + 1) * RP + r] = v1;
+        }
+    });
+}
+// rotary projection written straight to the global fp16 Q of the next cross-attention [H][64][16]
+__device__ __forceinline__ void linear_rope_q(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
+                                              const uint4* wf, const float* __restrict__ bias, __half* __restrict__ q) {
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+        if (c < E) {
+            v0 += __ldg(bias + c);
+            v1 += __ldg(bias + c + 1);
+            rotate_pair(s, r, c, v0, v1);
+            const int h0 = c / HD, h1 = (c + 1) / HD;
+            q[(h0 * ROWS + r) * 16 + (c - h0 * HD)] = __float2half_rn(v0);
+            q[(h1 * ROWS + r) * 16 + (c + 1 - h1 * HD)] = __float2half_rn(v1);
+        } else {   // padded embed dims 120..127 own the pad slot of head c-120
+            q[((c - E) * ROWS + r) * 16 + 15] = __float2half_rn(0.f);
+            q[((c + 1 - E) * ROWS + r) * 16 + 15] = __float2half_rn(0.f);
+        }
+    });
+}
+
+// FFN 120 -> 480 -> 120 in four 128-wide hidden chunks; y planes in (ah, al); result (+b2) -> out tile
+__device__ __forceinline__ void ffn_tile(const WarpMap& w, Smem& s, const uint4* w1, const float* __restrict__ b1,
+                                         const uint4* w2, const float* __restrict__ b2, float* __restrict__ out) {
+    float sum[NTW][4];
+#pragma unroll
+    for (int n = 0; n < NTW; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sum[n][e] = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < FFP / 128; ++ch) {
+        gemm64(w, s, s.ah, s.al, w1, 64, 16 * ch, [&](int r, int c, float v0, float v1) {
+            v0 = fmaxf(v0 + __ldg(b1 + 128 * ch + c), 0.f);
+            v1 = fmaxf(v1 + __ldg(b1 + 128 * ch + c + 1), 0.f);
+            uint32_t h, l;
+            split_h2(v0, v1, h, l);
+            *reinterpret_cast<uint32_t*>(s.hh + r * PITCH + c) = h;
+            *reinterpret_cast<uint32_t*>(s.hl + r * PITCH + c) = l;
+        });
+        __syncthreads();
+        prefetch_w(s, w2 + (size_t)ch * 8 * 16 * FRAG);
+        {
+            float acc[NTW][4];
+            mma_gemm_split_cta<8, PITCH, NTW>(s.hh, s.hl, w.m0, w.nh, s.ring, w2 + (size_t)ch * 8 * 16 * FRAG, 16, 0, w.lane, acc);
+#pragma unroll
+            for (int n = 0; n < NTW; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sum[n][e] += acc[n][e];
+        }
+        __syncthreads();
+        if (ch + 1 < FFP / 128) prefetch_w(s, w1, 64, 16 * (ch + 1));
+    }
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) {
+        const int c = 8 * (NTW * w.nh + n) + 2 * w.q4;
+        if (c < E) {
+            const float bb0 = __ldg(b2 + c), bb1 = __ldg(b2 + c + 1);
+            out[c * RP + w.m0 + w.g] = sum[n][0] + bb0;
+            out[(c + 1) * RP + w.m0 + w.g] = sum[n][1] + bb1;
+            out[c * RP + w.m0 + w.g + 8] = sum[n][2] + bb0;
+            out[(c + 1) * RP + w.m0 + w.g + 8] = sum[n][3] + bb1;
+        }
+    }
+}
+
+// attention to the <= 64 instruction tokens: x <- LN(x + Wo attn((x [+pe]) Wq, K, V))   (lang layers)
+__device__ __forceinline__ void lang_attention(const WarpMap& w, Smem& s, const float* pe, int nrows,
+                                               const uint4* wq, const float* bq, const uint4* wo, const float* bo,
+                                               const float* g, const float* b, const float* kin, const float* vin,
+                                               int n_instr) {
+    planes_from_tile(s.xs, pe, nullptr, nullptr, nrows, s.ah, s.al, nullptr);
+    load_tile(s.t2, kin, n_instr, E);
+    load_tile(s.t3, vin, n_instr, E);
+    __syncthreads();
+    linear_tile(w, s, s.ah, s.al, wq, bq, s.t1);
+    __syncthreads();
+    prefetch_w(s, wo);
+    small_mha<LPR>(s.t1, s.t2, s.t3, n_instr, nullptr, s.scores, s.t1);
+    __syncthreads();
+    planes_from_tile(s.t1, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
+    __syncthreads();
+    linear_tile(w, s, s.ah, s.al, wo, bo, s.t2);
+    __syncthreads();
+    residual_layernorm<LPR>(s.xs, s.t2, g, b);
+    __syncthreads();
 }
 
 // =============================================================== vision -> language (step-invariant)
@@ -105,34 +294,30 @@ struct CtxLangArgs {
     int tok_rows, nctx, n_instr, nlayers, batch;
     const float* kin;      // [nlayers][B][n_instr][E]  fp32 K projection of the instruction tokens
     const float* vin;      // same for V
-    const float* w;        // [nlayers] LangPack
+    const uint4* w;        // [nlayers] LangW
+    const float* v;        // [nlayers] LangV
 };
 
-__global__ void __launch_bounds__(256, 1) cd_ctx_lang_kernel(const CtxLangArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) cd_ctx_lang_kernel(const CtxLangArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s(smem_raw);
-    const Map m;
+    const WarpMap w;
     const int b = blockIdx.y, r0 = blockIdx.x * ROWS;
     const int nrows = min(ROWS, a.nctx - r0);
     float* tok_b = a.tok + ((size_t)b * a.tok_rows + r0) * E;
     load_tile(s.xs, tok_b, nrows, E);
     __syncthreads();
     for (int l = 0; l < a.nlayers; ++l) {
-        const float* w = a.w + (size_t)l * LangPack::SIZE;
+        const uint4* wl = a.w + (size_t)l * LangW::SIZE;
+        const float* vl = a.v + (size_t)l * LangV::SIZE;
         const size_t kvo = ((size_t)l * a.batch + b) * a.n_instr * E;
-        linear_to_smem<E, EP, false>(m, s.xs, w + LangPack::WQ, w + LangPack::BQ, 0, s.t2);      // q (no pos, no adaLN)
-        load_tile(s.t3, a.kin + kvo, a.n_instr, E);
-        load_tile(s.t4, a.vin + kvo, a.n_instr, E);
+        lang_attention(w, s, nullptr, 0, wl + LangW::WQ, vl + LangV::BQ, wl + LangW::WO, vl + LangV::BO, vl + LangV::G12,
+                       vl + LangV::B12, a.kin + kvo, a.vin + kvo, a.n_instr);
+        planes_from_tile(s.xs, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
         __syncthreads();
-        small_mha(s.t2, s.t3, s.t4, a.n_instr, nullptr, s.scores, s.t2);
+        ffn_tile(w, s, wl + LangW::W1, vl + LangV::B1, wl + LangW::W2, vl + LangV::B2, s.t1);
         __syncthreads();
-        linear_to_smem<E, EP, false>(m, s.t2, w + LangPack::WO, w + LangPack::BO, 0, s.t1);
-        __syncthreads();
-        residual_layernorm(s.xs, s.t1, w + LangPack::G12, w + LangPack::B12);
-        __syncthreads();
-        ffn_chunked(m, s.xs, w + LangPack::W1, w + LangPack::B1, w + LangPack::W2, w + LangPack::B2, s.t2, s.t1);
-        __syncthreads();
-        residual_layernorm(s.xs, s.t1, w + LangPack::G122, w + LangPack::B122);
+        residual_layernorm<LPR>(s.xs, s.t1, vl + LangV::G122, vl + LangV::B122);
         __syncthreads();
     }
     store_tile(tok_b, s.xs, nrows, E);
@@ -148,23 +333,29 @@ struct StepArgs {
     const float* ada;               // [T][nlayers_total][ADA_ROW]
     int ada_layers;                 // layers per timestep in the table
     // ---- begin kernel
-    const float* traj_enc;          // MlpPack with W1 as [9][EP]
-    const float* lang_w;            // LangPack (no FFN part used) or null
+    const float* traj_enc1;         // first trajectory-encoder layer, fp32 K-major [9][EP] + bias [EP]
+    const uint4* traj_enc2;         // second layer, fragment order [8][16]
+    const float* traj_enc2_b;       // [EP]
+    const uint4* lang_w;            // LangW or null
+    const float* lang_v;            // LangV
     const float* lang_k;            // [B][n_instr][E]
-    const float* lang_v;
+    const float* lang_vv;
     int n_instr;
     // ---- post kernel
     const float* x_in;              // [B][64][E]
     const float* att;               // [B][64][E] cross-attention output (heads concatenated)
-    const float* layer_w;           // AdaPack of this layer
+    const uint4* layer_w;           // AdaW of this layer
+    const float* layer_v;           // AdaV
     int ada_layer;                  // index of this layer in the adaLN table
     float* x_out;                   // [B][64][E]
-    const float* reg_w;             // MlpPack or null
+    const uint4* reg_w;             // MlpW or null
+    const float* reg_v;             // MlpV
     float* reg_out;                 // [B][L][reg_dim]
     int reg_dim;
     // ---- next layer's Q
     const float* next_src;          // null: use the tile just computed; else [B][64][E]
-    const float* next_wq;           // [E][EP] + bias [EP] contiguous (C_WQ, C_BQ of the next layer) or null
+    const uint4* next_wq;           // [8][16] fragment-ordered W_q of the next cross-attention or null
+    const float* next_bq;           // [EP]
     int next_ada_layer;
     __half* q_out;                  // [B][H][64][16]
     // ---- DDPM update (last layer of a step)
@@ -178,95 +369,102 @@ struct StepArgs {
     const float* noise_rot;         // [B][L][6]
 };
 
-__device__ __forceinline__ void next_q(const Map& m, const Smem& s, const StepArgs& a, int b, const float* src_tile) {
+__device__ __forceinline__ void next_q(const WarpMap& w, Smem& s, const StepArgs& a, int b, const float* src_tile) {
     const float* ada = a.ada + ((size_t)a.t_idx[b] * a.ada_layers + a.next_ada_layer) * ADA_ROW;
-    modulate(s.t1, src_tile, a.wp_pe, ada + 0, ada + EP, a.nrows);                    // adaln_12(x + wp_pe)
+    planes_from_tile(src_tile, a.wp_pe, ada + 0, ada + EP, a.nrows, s.ah, s.al, nullptr);    // adaln_12(x + wp_pe)
     __syncthreads();
-    linear_rope_to_smem<E, EP>(m, s.t1, a.next_wq, a.next_wq + E * EP, s.xyz, s.freq, true, s.t2);
-    __syncthreads();
-    write_q_half(s.t2, a.q_out + (size_t)b * H * ROWS * 16);
+    linear_rope_q(w, s, s.ah, s.al, a.next_wq, a.next_bq, a.q_out + (size_t)b * H * ROWS * 16);
 }
 
-__global__ void __launch_bounds__(256, 1) cd_step_begin_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) cd_step_begin_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s(smem_raw);
+    const WarpMap w;
     const Map m;
     const int b = blockIdx.x;
     const float* traj_b = a.traj + (size_t)b * a.nrows * 9;
     init_common(s, traj_b, a.nrows, 9, nullptr);
     load_tile(s.t1, traj_b, a.nrows, 9, 9);
     __syncthreads();
-    // trajectory encoder: Linear(9,E) -> ReLU -> Linear(E,E)   (diffusion_head.py:43-48, 215)
-    linear_to_smem<9, EP, true>(m, s.t1, a.traj_enc + MlpPack::W1, a.traj_enc + MlpPack::B1, 0, s.t2);
+    // trajectory encoder: Linear(9,E) -> ReLU (fp32 FMA, K = 9) -> Linear(E,E) (tensor cores)   (diffusion_head.py:43-48, 215)
+    linear_to_smem<9, EP, true>(m, s.t1, a.traj_enc1, a.traj_enc1 + 9 * EP, 0, s.t2);
     __syncthreads();
-    linear_to_smem<E, EP, false>(m, s.t2, a.traj_enc + MlpPack::W2, a.traj_enc + MlpPack::B2, 0, s.xs);
+    planes_from_tile(s.t2, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
     __syncthreads();
-    if (a.lang_w) {   // trajectory tokens attend to the instruction (diffusion_head.py:330-336)
-        const float* w = a.lang_w;
-        modulate(s.t1, s.xs, a.wp_pe, nullptr, nullptr, a.nrows);
-        load_tile(s.t3, a.lang_k + (size_t)b * a.n_instr * E, a.n_instr, E);
-        load_tile(s.t4, a.lang_v + (size_t)b * a.n_instr * E, a.n_instr, E);
-        __syncthreads();
-        linear_to_smem<E, EP, false>(m, s.t1, w + LangPack::WQ, w + LangPack::BQ, 0, s.t2);
-        __syncthreads();
-        small_mha(s.t2, s.t3, s.t4, a.n_instr, nullptr, s.scores, s.t2);
-        __syncthreads();
-        linear_to_smem<E, EP, false>(m, s.t2, w + LangPack::WO, w + LangPack::BO, 0, s.t1);
-        __syncthreads();
-        residual_layernorm(s.xs, s.t1, w + LangPack::G12, w + LangPack::B12);
-        __syncthreads();
-    }
+    linear_tile(w, s, s.ah, s.al, a.traj_enc2, a.traj_enc2_b, s.xs);
+    __syncthreads();
+    if (a.lang_w)   // trajectory tokens attend to the instruction (diffusion_head.py:330-336)
+        lang_attention(w, s, a.wp_pe, a.nrows, a.lang_w + LangW::WQ, a.lang_v + LangV::BQ, a.lang_w + LangW::WO,
+                       a.lang_v + LangV::BO, a.lang_v + LangV::G12, a.lang_v + LangV::B12,
+                       a.lang_k + (size_t)b * a.n_instr * E, a.lang_vv + (size_t)b * a.n_instr * E, a.n_instr);
     store_tile(a.x_out + (size_t)b * ROWS * E, s.xs, ROWS, E);
-    if (a.next_wq) next_q(m, s, a, b, s.xs);
+    if (a.next_wq) next_q(w, s, a, b, s.xs);
 }
 
-__global__ void __launch_bounds__(256, 1) cd_post_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) cd_post_kernel(const StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem s(smem_raw);
-    const Map m;
+    const WarpMap w;
     const int b = blockIdx.x;
-    const float* w = a.layer_w;
+    const uint4* lw = a.layer_w;
+    const float* lv = a.layer_v;
     const float* ada = a.ada + ((size_t)a.t_idx[b] * a.ada_layers + a.ada_layer) * ADA_ROW;
     const float* traj_b = a.traj + (size_t)b * a.nrows * 9;
+    prefetch_w(s, lw + AdaW::C_WO);
     init_common(s, traj_b, a.nrows, 9, a.mask ? a.mask + (size_t)b * a.nrows : nullptr);
     load_tile(s.xs, a.x_in + (size_t)b * ROWS * E, ROWS, E);
-    load_tile(s.t1, a.att + (size_t)b * ROWS * E, ROWS, E);
+    planes_from_global(a.att + (size_t)b * ROWS * E, ROWS, E, E, s.ah, s.al);
     __syncthreads();
     // ---- cross-attention epilogue: x = LN_12(x + att Wo^T + bo)          (layers.py:146-147)
-    linear_to_smem<E, EP, false>(m, s.t1, w + AdaPack::C_WO, w + AdaPack::C_BO, 0, s.t2);
+    linear_tile(w, s, s.ah, s.al, lw + AdaW::C_WO, lv + AdaV::C_BO, s.t1);
     __syncthreads();
-    residual_layernorm(s.xs, s.t2, w + AdaPack::G12, w + AdaPack::B12);
+    prefetch_w(s, lw + AdaW::S_WQ);
+    residual_layernorm<LPR>(s.xs, s.t1, lv + AdaV::G12, lv + AdaV::B12);
     __syncthreads();
     // ---- self-attention: q = k = adaLN_1(x + pe), v = adaLN_1(x), rotary on q and k, padding mask (layers.py:165-182)
-    modulate(s.t1, s.xs, a.wp_pe, ada + 2 * EP, ada + 3 * EP, a.nrows);
-    modulate(s.t2, s.xs, nullptr, ada + 2 * EP, ada + 3 * EP, a.nrows);
+    planes_from_tile(s.xs, a.wp_pe, ada + 2 * EP, ada + 3 * EP, a.nrows, s.ah, s.al, nullptr);
+    planes_from_tile(s.xs, nullptr, ada + 2 * EP, ada + 3 * EP, a.nrows, s.hh, s.hl, nullptr);
     __syncthreads();
-    linear_rope_to_smem<E, EP>(m, s.t1, w + AdaPack::S_WQ, w + AdaPack::S_BQ, s.xyz, s.freq, true, s.t3);
-    linear_rope_to_smem<E, EP>(m, s.t1, w + AdaPack::S_WK, w + AdaPack::S_BK, s.xyz, s.freq, true, s.t4);
+    linear_rope_tile(w, s, s.ah, s.al, lw + AdaW::S_WQ, lv + AdaV::S_BQ, s.t1);
+    linear_rope_tile(w, s, s.ah, s.al, lw + AdaW::S_WK, lv + AdaV::S_BK, s.t2);
+    linear_tile(w, s, s.hh, s.hl, lw + AdaW::S_WV, lv + AdaV::S_BV, s.t3);
     __syncthreads();
-    linear_to_smem<E, EP, false>(m, s.t2, w + AdaPack::S_WV, w + AdaPack::S_BV, 0, s.t1);
+    prefetch_w(s, lw + AdaW::S_WO);
+    small_mha<LPR>(s.t1, s.t2, s.t3, a.nrows, a.mask ? s.mask : nullptr, s.scores, s.t1);
     __syncthreads();
-    small_mha(s.t3, s.t4, s.t1, a.nrows, a.mask ? s.mask : nullptr, s.scores, s.t3);
+    planes_from_tile(s.t1, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
     __syncthreads();
-    linear_to_smem<E, EP, false>(m, s.t3, w + AdaPack::S_WO, w + AdaPack::S_BO, 0, s.t2);
+    linear_tile(w, s, s.ah, s.al, lw + AdaW::S_WO, lv + AdaV::S_BO, s.t2);
     __syncthreads();
-    residual_layernorm(s.xs, s.t2, w + AdaPack::G1, w + AdaPack::B1N);
+    prefetch_w(s, lw + AdaW::W1, 64, 0);
+    residual_layernorm<LPR>(s.xs, s.t2, lv + AdaV::G1, lv + AdaV::B1N);
     __syncthreads();
     // ---- FFN: y = adaLN_ff(x); x = LN_122(y + FFN(y))                      (layers.py:205-209)
-    modulate(s.t1, s.xs, nullptr, ada + 4 * EP, ada + 5 * EP, a.nrows);
+    planes_from_tile(s.xs, nullptr, ada + 4 * EP, ada + 5 * EP, a.nrows, s.ah, s.al, s.t1);   // t1 = y (fp32)
     __syncthreads();
-    ffn_chunked(m, s.t1, w + AdaPack::W1, w + AdaPack::B1, w + AdaPack::W2, w + AdaPack::B2, s.t2, s.t3);
+    ffn_tile(w, s, lw + AdaW::W1, lv + AdaV::B1, lw + AdaW::W2, lv + AdaV::B2, s.t2);
     __syncthreads();
-    residual_layernorm(s.t1, s.t3, w + AdaPack::G122, w + AdaPack::B122);
+    if (a.reg_w) prefetch_w(s, a.reg_w + MlpW::W1);
+    else if (a.next_wq) prefetch_w(s, a.next_wq);
+    residual_layernorm<LPR>(s.t1, s.t2, lv + AdaV::G122, lv + AdaV::B122);
     __syncthreads();
     float* x = s.t1;   // layer output
     store_tile(a.x_out + (size_t)b * ROWS * E, x, ROWS, E);
 
     // ---- regressor head: Linear(E,E) -> ReLU -> Linear(E,d)                (diffusion_head.py:179-198)
     if (a.reg_w) {
-        linear_to_smem<E, EP, true>(m, x, a.reg_w + MlpPack::W1, a.reg_w + MlpPack::B1, 0, s.t2);
+        planes_from_tile(x, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
         __syncthreads();
-        linear_to_smem<E, EP, false>(m, s.t2, a.reg_w + MlpPack::W2, a.reg_w + MlpPack::B2, 0, s.t3);
+        gemm64(w, s, s.ah, s.al, a.reg_w + MlpW::W1, 16, 0, [&](int r, int c, float v0, float v1) {
+            v0 = fmaxf(v0 + __ldg(a.reg_v + MlpV::B1 + c), 0.f);
+            v1 = fmaxf(v1 + __ldg(a.reg_v + MlpV::B1 + c + 1), 0.f);
+            uint32_t h, l;
+            split_h2(v0, v1, h, l);
+            *reinterpret_cast<uint32_t*>(s.hh + r * PITCH + c) = h;
+            *reinterpret_cast<uint32_t*>(s.hl + r * PITCH + c) = l;
+        });
+        __syncthreads();
+        linear_tile(w, s, s.hh, s.hl, a.reg_w + MlpW::W2, a.reg_v + MlpV::B2, s.t3);
         __syncthreads();
         for (int i = threadIdx.x; i < a.nrows * a.reg_dim; i += blockDim.x) {
             const int r = i / a.reg_dim, d = i - r * a.reg_dim;
@@ -282,7 +480,7 @@ __global__ void __launch_bounds__(256, 1) cd_post_kernel(const StepArgs a) {
             __syncthreads();
             src = s.xs;
         }
-        next_q(m, s, a, b, src);
+        next_q(w, s, a, b, src);
     }
     // ---- denoiser output + DDPM posterior step (diffusion_head.py:271-274, diffusion_model.py:105-117)
     if (a.do_update) {
@@ -443,10 +641,13 @@ using namespace a3d::cd;
 
 extern "C" size_t cd_pack_floats(int which) {
     switch (which) {
-        case 0: return LangPack::SIZE;
-        case 1: return AdaPack::SIZE;
-        case 2: return MlpPack::SIZE;
+        case 0: return LangV::SIZE;
+        case 1: return AdaV::SIZE;
+        case 2: return MlpV::SIZE;
         case 3: return ADA_ROW;
+        case 4: return (size_t)LangW::SIZE * 4;   // fragment buffers, in 32-bit words
+        case 5: return (size_t)AdaW::SIZE * 4;
+        case 6: return (size_t)MlpW::SIZE * 4;
         default: return 0;
     }
 }
@@ -461,33 +662,34 @@ static int set_smem(const void* fn, size_t bytes) {
 }
 
 extern "C" int cd_ctx_lang(float* tok, int batch, int tok_rows, int nctx, int embed, int heads, const float* kin,
-                           const float* vin, int n_instr, const float* w, int nlayers, void* stream) {
-    A3D_REQUIRE(tok && kin && vin && w, "cd_ctx_lang: null pointer");
+                           const float* vin, int n_instr, const void* w, const float* v, int nlayers, void* stream) {
+    A3D_REQUIRE(tok && kin && vin && w && v, "cd_ctx_lang: null pointer");
     A3D_REQUIRE(embed == E && heads == H, "cd_ctx_lang: built for embedding_dim 120 / 8 heads (got %d / %d)", embed, heads);
     A3D_REQUIRE(batch > 0 && nctx > 0 && nctx <= tok_rows && n_instr > 0 && n_instr <= 64 && nlayers > 0,
                 "cd_ctx_lang: bad sizes (nctx=%d rows=%d n_instr=%d)", nctx, tok_rows, n_instr);
     static bool once = false;
     if (!once) {
-        if (int rc = set_smem((const void*)cd_ctx_lang_kernel, SMEM_POST)) return rc;
+        if (int rc = set_smem((const void*)cd_ctx_lang_kernel, SMEM_BYTES)) return rc;
         once = true;
     }
-    CtxLangArgs a{tok, tok_rows, nctx, n_instr, nlayers, batch, kin, vin, w};
+    CtxLangArgs a{tok, tok_rows, nctx, n_instr, nlayers, batch, kin, vin, (const uint4*)w, v};
     dim3 grid((nctx + ROWS - 1) / ROWS, batch);
-    cd_ctx_lang_kernel<<<grid, 256, SMEM_POST, (cudaStream_t)stream>>>(a);
+    cd_ctx_lang_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
     return check_launch("cd_ctx_lang");
 }
 
 extern "C" int cd_step_begin(const float* traj, int batch, int length, const float* wp_pe, const int* t_idx,
-                             const float* ada, int ada_layers, const float* traj_enc, const float* lang_w,
-                             const float* lang_k, const float* lang_v, int n_instr, float* x_out,
-                             const float* next_wq, int next_ada_layer, void* q_out, void* stream) {
-    A3D_REQUIRE(traj && wp_pe && t_idx && ada && traj_enc && x_out, "cd_step_begin: null pointer");
+                             const float* ada, int ada_layers, const float* traj_enc1, const void* traj_enc2,
+                             const float* traj_enc2_b, const void* lang_w, const float* lang_v, const float* lang_k,
+                             const float* lang_vv, int n_instr, float* x_out, const void* next_wq,
+                             const float* next_bq, int next_ada_layer, void* q_out, void* stream) {
+    A3D_REQUIRE(traj && wp_pe && t_idx && ada && traj_enc1 && traj_enc2 && traj_enc2_b && x_out, "cd_step_begin: null pointer");
     A3D_REQUIRE(batch > 0 && length > 0 && length <= ROWS, "cd_step_begin: trajectory length %d not in [1,64]", length);
-    A3D_REQUIRE(!lang_w || (lang_k && lang_v && n_instr > 0 && n_instr <= 64), "cd_step_begin: instruction K/V missing");
-    A3D_REQUIRE(!next_wq || q_out, "cd_step_begin: q_out missing");
+    A3D_REQUIRE(!lang_w || (lang_v && lang_k && lang_vv && n_instr > 0 && n_instr <= 64), "cd_step_begin: instruction K/V missing");
+    A3D_REQUIRE(!next_wq || (q_out && next_bq), "cd_step_begin: q_out / next_bq missing");
     static bool once = false;
     if (!once) {
-        if (int rc = set_smem((const void*)cd_step_begin_kernel, SMEM_POST)) return rc;
+        if (int rc = set_smem((const void*)cd_step_begin_kernel, SMEM_BYTES)) return rc;
         once = true;
     }
     StepArgs a{};
@@ -498,16 +700,20 @@ extern "C" int cd_step_begin(const float* traj, int batch, int length, const flo
     a.t_idx = t_idx;
     a.ada = ada;
     a.ada_layers = ada_layers;
-    a.traj_enc = traj_enc;
-    a.lang_w = lang_w;
-    a.lang_k = lang_k;
+    a.traj_enc1 = traj_enc1;
+    a.traj_enc2 = (const uint4*)traj_enc2;
+    a.traj_enc2_b = traj_enc2_b;
+    a.lang_w = (const uint4*)lang_w;
     a.lang_v = lang_v;
+    a.lang_k = lang_k;
+    a.lang_vv = lang_vv;
     a.n_instr = n_instr;
     a.x_out = x_out;
-    a.next_wq = next_wq;
+    a.next_wq = (const uint4*)next_wq;
+    a.next_bq = next_bq;
     a.next_ada_layer = next_ada_layer;
     a.q_out = (__half*)q_out;
-    cd_step_begin_kernel<<<batch, 256, SMEM_POST, (cudaStream_t)stream>>>(a);
+    cd_step_begin_kernel<<<batch, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
     return check_launch("cd_step_begin");
 }
 
@@ -523,21 +729,21 @@ extern "C" int cd_cross(const void* q, const void* kv, int batch, int nk, int he
 
 extern "C" int cd_post(const float* traj, int batch, int length, const unsigned char* mask, const float* wp_pe,
                        const int* t_idx, const float* ada, int ada_layers, int ada_layer, const float* x_in,
-                       const float* att, const float* layer_w, float* x_out, const float* reg_w, float* reg_out,
-                       int reg_dim, const float* next_src, const float* next_wq, int next_ada_layer, void* q_out,
-                       int do_update, int last_step, float* traj_out, const float* pos_upd, const float* cond_data,
-                       const unsigned char* cond_mask, const float* coef_host, const float* noise_pos,
-                       const float* noise_rot, void* stream) {
-    A3D_REQUIRE(traj && wp_pe && t_idx && ada && x_in && att && layer_w && x_out, "cd_post: null pointer");
+                       const float* att, const void* layer_w, const float* layer_v, float* x_out, const void* reg_w,
+                       const float* reg_v, float* reg_out, int reg_dim, const float* next_src, const void* next_wq,
+                       const float* next_bq, int next_ada_layer, void* q_out, int do_update, int last_step,
+                       float* traj_out, const float* pos_upd, const float* cond_data, const unsigned char* cond_mask,
+                       const float* coef_host, const float* noise_pos, const float* noise_rot, void* stream) {
+    A3D_REQUIRE(traj && wp_pe && t_idx && ada && x_in && att && layer_w && layer_v && x_out, "cd_post: null pointer");
     A3D_REQUIRE(batch > 0 && length > 0 && length <= ROWS, "cd_post: trajectory length %d not in [1,64]", length);
-    A3D_REQUIRE(!reg_w || (reg_out && reg_dim > 0 && reg_dim <= 16), "cd_post: regressor output missing");
-    A3D_REQUIRE(!next_wq || q_out, "cd_post: q_out missing");
+    A3D_REQUIRE(!reg_w || (reg_v && reg_out && reg_dim > 0 && reg_dim <= 16), "cd_post: regressor output missing");
+    A3D_REQUIRE(!next_wq || (q_out && next_bq), "cd_post: q_out / next_bq missing");
     A3D_REQUIRE(!do_update || (traj_out && pos_upd && cond_data && cond_mask && coef_host && reg_w && reg_dim == 6 &&
                                (last_step || (noise_pos && noise_rot))),
                 "cd_post: DDPM update needs traj_out, pos_upd, cond_*, coef, the rotation regressor and noise");
     static bool once = false;
     if (!once) {
-        if (int rc = set_smem((const void*)cd_post_kernel, SMEM_POST)) return rc;
+        if (int rc = set_smem((const void*)cd_post_kernel, SMEM_BYTES)) return rc;
         once = true;
     }
     StepArgs a{};
@@ -552,13 +758,16 @@ extern "C" int cd_post(const float* traj, int batch, int length, const unsigned 
     a.ada_layer = ada_layer;
     a.x_in = x_in;
     a.att = att;
-    a.layer_w = layer_w;
+    a.layer_w = (const uint4*)layer_w;
+    a.layer_v = layer_v;
     a.x_out = x_out;
-    a.reg_w = reg_w;
+    a.reg_w = (const uint4*)reg_w;
+    a.reg_v = reg_v;
     a.reg_out = reg_out;
     a.reg_dim = reg_dim;
     a.next_src = next_src;
-    a.next_wq = next_wq;
+    a.next_wq = (const uint4*)next_wq;
+    a.next_bq = next_bq;
     a.next_ada_layer = next_ada_layer;
     a.q_out = (__half*)q_out;
     a.do_update = do_update;
@@ -570,6 +779,6 @@ extern "C" int cd_post(const float* traj, int batch, int length, const unsigned 
     for (int i = 0; i < 6; ++i) a.coef[i] = coef_host ? coef_host[i] : 0.f;
     a.noise_pos = noise_pos;
     a.noise_rot = noise_rot;
-    cd_post_kernel<<<batch, 256, SMEM_POST, (cudaStream_t)stream>>>(a);
+    cd_post_kernel<<<batch, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
     return check_launch("cd_post");
 }

@@ -17,7 +17,7 @@ from . import lib
 from .packing import PackCache, pack_kv_set, pack_xattn_layer
 from .params import XAttnStackParams, mlp
 from .rotations import normalise_quat, ortho6d_to_matrix
-from .trunk import build_backbone
+from .trunk import EvalTrunk, build_backbone
 
 
 def _shared_or_separate(n, tie, factory):
@@ -96,6 +96,8 @@ class Act3D(nn.Module):
         self._teacher_positions = None      # test hook: list of (B,1,3) fed to the next level
         self._last_topk = None              # debug/test hook: top-k indices per level of the last call
         self._profile_events = None         # bench hook: list collecting (tag, start, end) CUDA events
+        self.fold_trunk = True              # eval: BN-folded channels-last copy of the frozen backbone (trunk.EvalTrunk)
+        self._eval_trunk = EvalTrunk()
 
     # ------------------------------------------------------------------ packed weights
     def _stack_pack(self, tag, stack):
@@ -134,7 +136,11 @@ class Act3D(nn.Module):
         are actually attended to."""
         b = visible_rgb.shape[0]
         rgb = visible_rgb.reshape(b * num_cameras, *visible_rgb.shape[2:])
-        feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        if self.training or not self.fold_trunk or not isinstance(self.backbone, torch.nn.Module) \
+                or isinstance(self.backbone, torch.nn.Identity):
+            feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        else:
+            feats = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb)
         pcd = visible_pcd.reshape(b * num_cameras, *visible_pcd.shape[2:]).contiguous().float()
         feats_pyr, pcd_pyr, cache = [], [], {}
         for i in range(self.num_sampling_level):

@@ -34,15 +34,16 @@ EXPORTS = {
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
                                  c_void_p, c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
-    "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                            c_void_p]),
-    "cd_step_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                            c_int, c_void_p]),
+    "cd_step_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_void_p]),
     "cd_cross": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cd_post": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
-                        c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), c_void_p,
-                        c_void_p, c_void_p]),
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                        c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                        ctypes.POINTER(c_float), c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None
@@ -202,37 +203,49 @@ def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device):
 
 # ------------------------------------------------------------------------------------------------ planner
 def cd_pack_floats(which):
-    return load().cd_pack_floats({"lang": 0, "ada": 1, "mlp": 2, "ada_row": 3}[which])
+    return load().cd_pack_floats({"lang_v": 0, "ada_v": 1, "mlp_v": 2, "ada_row": 3, "lang_w": 4, "ada_w": 5,
+                                  "mlp_w": 6}[which])
 
 
-def cd_ctx_lang(tok, nctx, kin, vin, w, nlayers):
+def _raw(t):
+    """device pointer of a tensor or None (weights: any dtype)"""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def cd_ctx_lang(tok, nctx, kin, vin, w, v, nlayers):
     b, rows, e = tok.shape
     _check(load().cd_ctx_lang(_ptr(_f32(tok)), b, rows, nctx, e, 8, _ptr(_f32(kin)), _ptr(_f32(vin)), kin.shape[2],
-                              _ptr(_f32(w)), nlayers, _stream()), "cd_ctx_lang")
+                              _raw(w), _raw(v), nlayers, _stream()), "cd_ctx_lang")
 
 
-def cd_step_begin(traj, wp_pe, t_idx, ada, ada_layers, traj_enc, lang_w, lang_k, lang_v, x_out, next_wq, next_ada_layer,
-                  q_out):
+def cd_step_begin(traj, wp_pe, t_idx, ada, ada_layers, enc1, enc2, enc2_b, lang_w, lang_v, lang_k, lang_vv, x_out,
+                  next_wq, next_bq, next_ada_layer, q_out):
     b, length, _ = traj.shape
     n_instr = lang_k.shape[1] if lang_k is not None else 0
     _check(load().cd_step_begin(_ptr(_f32(traj)), b, length, _ptr(wp_pe), _ptr(t_idx), _ptr(ada), ada_layers,
-                                _ptr(traj_enc), _ptr(lang_w), _ptr(lang_k), _ptr(lang_v), n_instr, _ptr(x_out),
-                                next_wq, next_ada_layer, _ptr(q_out), _stream()), "cd_step_begin")
+                                _raw(enc1), _raw(enc2), _raw(enc2_b), _raw(lang_w), _raw(lang_v), _ptr(lang_k),
+                                _ptr(lang_vv), n_instr, _ptr(x_out), _raw(next_wq), _raw(next_bq), next_ada_layer,
+                                _ptr(q_out), _stream()), "cd_step_begin")
 
 
 def cd_cross(q, kv, kv_offset_bytes, batch, nk, att):
     _check(load().cd_cross(_ptr(q), kv.data_ptr() + kv_offset_bytes, batch, nk, 8, _ptr(att), _stream()), "cd_cross")
 
 
-def cd_post(traj, mask, wp_pe, t_idx, ada, ada_layers, ada_layer, x_in, att, layer_w, x_out, reg_w=None, reg_out=None,
-            reg_dim=0, next_src=None, next_wq=None, next_ada_layer=0, q_out=None, update=None):
+def cd_post(traj, mask, wp_pe, t_idx, ada, ada_layers, ada_layer, x_in, att, layer_w, layer_v, x_out, reg_w=None,
+            reg_v=None, reg_out=None, reg_dim=0, next_src=None, next_wq=None, next_bq=None, next_ada_layer=0, q_out=None,
+            update=None):
     """update = dict(last_step, traj_out, pos_upd, cond_data, cond_mask, coef (6 floats), noise_pos, noise_rot) or None"""
     b, length, _ = traj.shape
     u = update or {}
     coef = (c_float * 6)(*[float(x) for x in u.get("coef", [0.0] * 6)])
     _check(load().cd_post(_ptr(_f32(traj)), b, length, _ptr(mask), _ptr(wp_pe), _ptr(t_idx), _ptr(ada), ada_layers,
-                          ada_layer, _ptr(x_in), _ptr(att), layer_w, _ptr(x_out), reg_w, _ptr(reg_out), reg_dim,
-                          _ptr(next_src), next_wq, next_ada_layer, _ptr(q_out), int(update is not None),
-                          int(u.get("last_step", 0)), _ptr(u.get("traj_out")), _ptr(u.get("pos_upd")),
-                          _ptr(u.get("cond_data")), _ptr(u.get("cond_mask")), coef, _ptr(u.get("noise_pos")),
-                          _ptr(u.get("noise_rot")), _stream()), "cd_post")
+                          ada_layer, _ptr(x_in), _ptr(att), _raw(layer_w), _raw(layer_v), _ptr(x_out), _raw(reg_w),
+                          _raw(reg_v), _ptr(reg_out), reg_dim, _ptr(next_src), _raw(next_wq), _raw(next_bq),
+                          next_ada_layer, _ptr(q_out), int(update is not None), int(u.get("last_step", 0)),
+                          _ptr(u.get("traj_out")), _ptr(u.get("pos_upd")), _ptr(u.get("cond_data")),
+                          _ptr(u.get("cond_mask")), coef, _ptr(u.get("noise_pos")), _ptr(u.get("noise_rot")),
+                          _stream()), "cd_post")

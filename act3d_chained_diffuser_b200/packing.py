@@ -84,57 +84,78 @@ class PackCache:
 
 
 # ------------------------------------------------------------------------------------------------ planner packs
+def pack_mma_weight(weight, kpad, npad):
+    """nn.Linear weight (N_out, K_in) -> int32 buffer in the B-fragment order of csrc/a3d_mma_gemm.cuh:
+    [kstep][ntile][lane] -> {b0_hi, b1_hi, b0_lo, b1_lo} with hi = fp16(w), lo = fp16((w - hi) * 2^11);
+    b0 = (w[n][k0], w[n][k0+1]), b1 = (w[n][k0+8], w[n][k0+9]), n = 8*ntile + lane//4, k0 = 16*kstep + 2*(lane%4)."""
+    w = weight.detach().float()
+    full = w.new_zeros(npad, kpad)
+    full[: w.shape[0], : w.shape[1]] = w
+    hi = full.half()
+    lo = ((full - hi.float()) * 2048.0).half()
+    ks, nt = kpad // 16, npad // 8
+
+    def frag(p):
+        t = p.view(nt, 8, ks, 2, 4, 2).permute(2, 0, 1, 4, 3, 5)          # (ks, nt, g, q, hsel, pair)
+        return t.reshape(ks, nt, 32, 2, 2)
+    both = torch.stack([frag(hi), frag(lo)], dim=3).contiguous()          # (ks, nt, lane, plane, hsel, pair)
+    return both.view(torch.int32).reshape(-1)
+
+
 def _scaled_q(attn, e, heads):
     scale = (float(e // heads) ** -0.5) * LOG2E
     w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
     return w_in[:e] * scale, b_in[:e] * scale
 
 
-def _ffn_parts(layer, ep, ffp):
-    w1, b1 = layer.ffn_12[0].weight.detach().float(), layer.ffn_12[0].bias.detach().float()
-    w2, b2 = layer.ffn_12[3].weight.detach().float(), layer.ffn_12[3].bias.detach().float()
-    w2t = _kmajor(w2, ep)                                        # (480, 128)
-    w2t = torch.cat([w2t, w2t.new_zeros(ffp - w2t.shape[0], ep)])
-    return [_kmajor(w1, ffp).reshape(-1), _pad_vec(b1, ffp), w2t.reshape(-1), _pad_vec(b2, ep),
-            _pad_vec(layer.norm_122.weight.detach().float(), ep), _pad_vec(layer.norm_122.bias.detach().float(), ep)]
+def _vec(t, width):
+    return _pad_vec(t.detach().float(), width)
 
 
 def pack_lang_layer(layer, e=120, heads=8, ffp=512):
-    """ParallelAttentionLayer without adaLN/self-attention (vl_attention, traj_lang_attention) -> LangPack
-    (csrc/cd_denoiser.cu): WQ BQ WO BO G12 B12 | W1[E][512] B1 W2[512][128] B2 G122 B122."""
+    """ParallelAttentionLayer without adaLN / self-attention (vl_attention, traj_lang_attention) ->
+    (LangW int32 fragments {WQ WO W1 W2}, LangV floats {BQ BO G12 B12 B1[512] B2 G122 B122}); csrc/cd_denoiser.cu."""
     ep = 16 * heads
     wq, bq = _scaled_q(layer.cross_12, e, heads)
-    parts = [_kmajor(wq, ep).reshape(-1), _pad_vec(bq, ep),
-             _kmajor(layer.cross_12.out_proj.weight, ep).reshape(-1), _pad_vec(layer.cross_12.out_proj.bias.detach().float(), ep),
-             _pad_vec(layer.norm_12.weight.detach().float(), ep), _pad_vec(layer.norm_12.bias.detach().float(), ep)]
-    parts += _ffn_parts(layer, ep, ffp)
-    return torch.cat(parts)
+    w = torch.cat([pack_mma_weight(wq, ep, ep), pack_mma_weight(layer.cross_12.out_proj.weight, ep, ep),
+                   pack_mma_weight(layer.ffn_12[0].weight, ep, ffp), pack_mma_weight(layer.ffn_12[3].weight, ffp, ep)])
+    v = torch.cat([_pad_vec(bq, ep), _vec(layer.cross_12.out_proj.bias, ep), _vec(layer.norm_12.weight, ep),
+                   _vec(layer.norm_12.bias, ep), _vec(layer.ffn_12[0].bias, ffp), _vec(layer.ffn_12[3].bias, ep),
+                   _vec(layer.norm_122.weight, ep), _vec(layer.norm_122.bias, ep)])
+    return w.contiguous(), v.contiguous()
 
 
 def pack_ada_layer(layer, e=120, heads=8, ffp=512):
-    """adaLN cross + self + FFN layer -> AdaPack: cross {WQ BQ WO BO G12 B12} self {WQ BQ WK BK WV BV WO BO G1 B1}
-    ffn {W1 B1 W2 B2 G122 B122}.  Both q projections carry hd^-1/2 * log2(e)."""
+    """adaLN cross + self + FFN layer -> (AdaW {C_WQ C_WO S_WQ S_WK S_WV S_WO W1 W2},
+    AdaV {C_BQ C_BO G12 B12 S_BQ S_BK S_BV S_BO G1 B1N B1[512] B2 G122 B122}).
+    Both q projections carry hd^-1/2 * log2(e)."""
     ep = 16 * heads
     cq, cbq = _scaled_q(layer.cross_12, e, heads)
     sq, sbq = _scaled_q(layer.sa1, e, heads)
     w_in, b_in = layer.sa1.in_proj_weight.detach().float(), layer.sa1.in_proj_bias.detach().float()
-    v = lambda t: _pad_vec(t.detach().float(), ep)
-    parts = [_kmajor(cq, ep).reshape(-1), _pad_vec(cbq, ep),
-             _kmajor(layer.cross_12.out_proj.weight, ep).reshape(-1), v(layer.cross_12.out_proj.bias),
-             v(layer.norm_12.weight), v(layer.norm_12.bias),
-             _kmajor(sq, ep).reshape(-1), _pad_vec(sbq, ep),
-             _kmajor(w_in[e:2 * e], ep).reshape(-1), _pad_vec(b_in[e:2 * e], ep),
-             _kmajor(w_in[2 * e:], ep).reshape(-1), _pad_vec(b_in[2 * e:], ep),
-             _kmajor(layer.sa1.out_proj.weight, ep).reshape(-1), v(layer.sa1.out_proj.bias),
-             v(layer.norm_1.weight), v(layer.norm_1.bias)]
-    parts += _ffn_parts(layer, ep, ffp)
-    return torch.cat(parts)
+    w = torch.cat([pack_mma_weight(cq, ep, ep), pack_mma_weight(layer.cross_12.out_proj.weight, ep, ep),
+                   pack_mma_weight(sq, ep, ep), pack_mma_weight(w_in[e:2 * e], ep, ep),
+                   pack_mma_weight(w_in[2 * e:], ep, ep), pack_mma_weight(layer.sa1.out_proj.weight, ep, ep),
+                   pack_mma_weight(layer.ffn_12[0].weight, ep, ffp), pack_mma_weight(layer.ffn_12[3].weight, ffp, ep)])
+    v = torch.cat([_pad_vec(cbq, ep), _vec(layer.cross_12.out_proj.bias, ep), _vec(layer.norm_12.weight, ep),
+                   _vec(layer.norm_12.bias, ep), _pad_vec(sbq, ep), _pad_vec(b_in[e:2 * e], ep), _pad_vec(b_in[2 * e:], ep),
+                   _vec(layer.sa1.out_proj.bias, ep), _vec(layer.norm_1.weight, ep), _vec(layer.norm_1.bias, ep),
+                   _vec(layer.ffn_12[0].bias, ffp), _vec(layer.ffn_12[3].bias, ep),
+                   _vec(layer.norm_122.weight, ep), _vec(layer.norm_122.bias, ep)])
+    return w.contiguous(), v.contiguous()
 
 
 def pack_mlp(seq, e=120, ep=128):
-    """nn.Sequential(Linear(in<=E, E), ReLU, [Dropout], Linear(E, out<=EP)) -> MlpPack W1[E][EP] B1 W2[E][EP] B2."""
+    """nn.Sequential(Linear(E, E), ReLU, [Dropout], Linear(E, out<=EP)) -> (MlpW {W1 W2}, MlpV {B1 B2})."""
     first, last = seq[0], seq[-1]
-    w1 = _kmajor(first.weight, ep)                               # (in, 128)
-    w1 = torch.cat([w1, w1.new_zeros(e - w1.shape[0], ep)])
-    return torch.cat([w1.reshape(-1), _pad_vec(first.bias.detach().float(), ep),
-                      _kmajor(last.weight, ep).reshape(-1), _pad_vec(last.bias.detach().float(), ep)])
+    w = torch.cat([pack_mma_weight(first.weight, ep, ep), pack_mma_weight(last.weight, ep, ep)])
+    v = torch.cat([_vec(first.bias, ep), _vec(last.bias, ep)])
+    return w.contiguous(), v.contiguous()
+
+
+def pack_traj_encoder(seq, e=120, ep=128):
+    """traj_encoder = Linear(9, E) -> ReLU -> Dropout -> Linear(E, E): first layer stays an fp32 K-major [9][EP]
+    matrix + bias (K = 9 is not worth a tensor-core pass), second layer in fragment order."""
+    first, last = seq[0], seq[-1]
+    enc1 = torch.cat([_kmajor(first.weight, ep).reshape(-1), _vec(first.bias, ep)])
+    return enc1.contiguous(), pack_mma_weight(last.weight, ep, ep).contiguous(), _vec(last.bias, ep).contiguous()

@@ -21,10 +21,10 @@ from torchvision.ops import FeaturePyramidNetwork
 
 from . import lib
 from .ddpm import PosteriorTable
-from .packing import PackCache, pack_ada_layer, pack_kv_set, pack_lang_layer, pack_mlp
+from .packing import PackCache, pack_ada_layer, pack_kv_set, pack_lang_layer, pack_mlp, pack_traj_encoder
 from .params import ParallelStackParams, mlp
 from .rotations import matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix, quat_to_matrix
-from .trunk import build_backbone
+from .trunk import EvalTrunk, build_backbone
 
 
 def _repeat(n, tie, factory):
@@ -97,6 +97,8 @@ class DiffusionHead(nn.Module):
         self.pos_regressor = nn.ModuleList(mlp(e, e, 3, dropout=0.1) for _ in range(n))
         self.rot_regressor = nn.ModuleList(mlp(e, e, output_dim - 3, dropout=0.1) for _ in range(n))
         self._packs = PackCache()
+        self.fold_trunk = True
+        self._eval_trunk = EvalTrunk()
 
     # ------------------------------------------------------------------ packed weights / tables
     def _ada_layers(self):
@@ -109,7 +111,7 @@ class DiffusionHead(nn.Module):
 
         def build():
             layers = self._ada_layers()
-            ada_w = [pack_ada_layer(l, e, h) for l in layers]
+            ada = [pack_ada_layer(l, e, h) for l in layers]
             kv = [pack_kv_set(l.cross_12, e, h) for l in layers]
             # adaLN modulation of every (timestep, layer): Linear(SiLU(time_emb))   (layers.py:282-290, encoder.py:199)
             t_emb = F.silu(sinusoidal(torch.arange(num_timesteps, device=device), e).float())
@@ -122,30 +124,37 @@ class DiffusionHead(nn.Module):
                     per.append(F.pad(mod.view(num_timesteps, 2, e), (0, 16 * h - e)))                 # (T, 2, EP)
                 rows.append(torch.stack(per, dim=1))                                                  # (T, 3, 2, EP)
             out = dict(
-                ada_w=[w.contiguous() for w in ada_w],
+                ada_w=[a[0] for a in ada], ada_v=[a[1] for a in ada],
                 wkv=torch.stack([k[0] for k in kv]).contiguous(), bkv=torch.stack([k[1] for k in kv]).contiguous(),
                 ada=torch.stack(rows, dim=1).contiguous(),                                            # (T, nl, 3, 2, EP)
-                traj_enc=pack_mlp(self.traj_encoder, e).contiguous(),
-                pos_reg=pack_mlp(self.pos_regressor[0], e).contiguous(),
-                rot_reg=pack_mlp(self.rot_regressor[0], e).contiguous(),
-                lang=pack_lang_layer(self.traj_lang_attention[0].layers[0], e, h).contiguous(),
+                traj_enc=pack_traj_encoder(self.traj_encoder, e),
+                pos_reg=pack_mlp(self.pos_regressor[0], e), rot_reg=pack_mlp(self.rot_regressor[0], e),
+                lang=pack_lang_layer(self.traj_lang_attention[0].layers[0], e, h),
             )
             if self.use_instruction:
-                out["vl"] = torch.cat([pack_lang_layer(l, e, h) for l in self.vl_attention[0].layers]).contiguous()
+                vl = [pack_lang_layer(l, e, h) for l in self.vl_attention[0].layers]
+                out["vl_w"] = torch.cat([x[0] for x in vl]).contiguous()
+                out["vl_v"] = torch.cat([x[1] for x in vl]).contiguous()
             return out
         return self._packs.get(("planner", num_timesteps, str(device)), params, build)
 
     # ------------------------------------------------------------------ step-invariant context
-    def encode_context(self, visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, num_timesteps):
+    def encode_context(self, visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, num_timesteps,
+                       static=None):
         """Everything of DiffusionHead.forward that does not depend on the trajectory or the timestep
-        (diffusion_head.py:221-247, 289-323)."""
+        (diffusion_head.py:221-247, 289-323).  ``static``: dict of persistent buffers (kv, lang_k, lang_v) to
+        write into, so that a captured CUDA graph of the sampling loop can be replayed on new inputs."""
         lib.load()
         e, h = self.embedding_dim, self.num_attn_heads
         b, ncam = visible_rgb.shape[:2]
         dev = visible_rgb.device
         w = self._weights(num_timesteps, dev)
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:])
-        fm = self.feature_pyramid(self.backbone(self.normalize(rgb)))["res3"].contiguous().float()
+        if self.training or not self.fold_trunk or isinstance(self.backbone, torch.nn.Identity):
+            fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        else:
+            fpn = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb)
+        fm = fpn["res3"].contiguous().float()
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
         nctx = pts.shape[1]
@@ -165,8 +174,15 @@ class DiffusionHead(nn.Module):
             vl_layers = self.vl_attention[0].layers
             kvs = [instr_kv(l.cross_12) for l in vl_layers]
             lib.cd_ctx_lang(tok, nctx, torch.stack([k for k, _ in kvs]), torch.stack([v for _, v in kvs]),
-                            w["vl"], len(vl_layers))
-            ctx["lang_k"], ctx["lang_v"] = instr_kv(self.traj_lang_attention[0].layers[0].cross_12)
+                            w["vl_w"], w["vl_v"], len(vl_layers))
+            lk, lv = instr_kv(self.traj_lang_attention[0].layers[0].cross_12)
+            if static is not None and static.get("lang_k") is not None:
+                static["lang_k"].copy_(lk)
+                static["lang_v"].copy_(lv)
+                lk, lv = static["lang_k"], static["lang_v"]
+            elif static is not None:
+                static["lang_k"], static["lang_v"] = lk, lv
+            ctx["lang_k"], ctx["lang_v"] = lk, lv
         else:
             ctx["lang_k"] = ctx["lang_v"] = None
 
@@ -176,7 +192,10 @@ class DiffusionHead(nn.Module):
             tok[:, nctx + 1] = self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight[0]
             pos[:, nctx + 1] = goal_gripper[:, :3].float()
         nl = len(w["ada_w"])
-        ctx["kv"] = lib.ctx_kv(tok, pos, rows, h, w["wkv"], w["bkv"], [1] * nl)
+        ctx["kv"] = lib.ctx_kv(tok, pos, rows, h, w["wkv"], w["bkv"], [1] * nl,
+                               out=static.get("kv") if static is not None else None)
+        if static is not None:
+            static["kv"] = ctx["kv"]
         ctx["set_bytes"] = lib.kv_bytes(1, b, rows, h)
         ctx["w"] = w
         return ctx
@@ -191,26 +210,25 @@ class DiffusionHead(nn.Module):
         nl = len(w["ada_w"])
         ada = w["ada"]
         xb, att, qb = work["x"], work["att"], work["q"]
-        off = lambda pack, name: pack.data_ptr() + 4 * _ADA_OFF[name]
-        lang_w = w["lang"] if self.use_instruction else None
-        lib.cd_step_begin(trajectory, work["wp_pe"], t_idx, ada, nl, w["traj_enc"], lang_w, ctx["lang_k"], ctx["lang_v"],
-                          xb[0], off(w["ada_w"][0], "C_WQ"), 0, qb)
+        enc1, enc2, enc2_b = w["traj_enc"]
+        lang_w, lang_v = w["lang"] if self.use_instruction else (None, None)
+        lib.cd_step_begin(trajectory, work["wp_pe"], t_idx, ada, nl, enc1, enc2, enc2_b, lang_w, lang_v, ctx["lang_k"],
+                          ctx["lang_v"], xb[0], w["ada_w"][0], w["ada_v"][0], 0, qb)
         mask = work["mask_u8"]
         for li in range(nl):
             lib.cd_cross(qb, ctx["kv"], li * ctx["set_bytes"], b, ctx["nk"], att)
             kw = {}
             x_in = xb[li]
-            if li == n_traj:                      # first pos layer and first rot layer both start from the traj stack output
-                x_in = xb[n_traj]
-            if li == n_traj + 2:
+            if li in (n_traj, n_traj + 2):        # first pos layer and first rot layer both start from the traj stack output
                 x_in = xb[n_traj]
             if li == n_traj + 1:                  # last pos layer: position regressor; next Q comes from the traj output
-                kw.update(reg_w=w["pos_reg"].data_ptr(), reg_out=work["pos_upd"], reg_dim=3, next_src=xb[n_traj])
+                kw.update(reg_w=w["pos_reg"][0], reg_v=w["pos_reg"][1], reg_out=work["pos_upd"], reg_dim=3,
+                          next_src=xb[n_traj])
             if li == nl - 1:                      # last rot layer: rotation regressor (+ DDPM update)
-                kw.update(reg_w=w["rot_reg"].data_ptr(), reg_out=work["rot_out"], reg_dim=6, update=update)
+                kw.update(reg_w=w["rot_reg"][0], reg_v=w["rot_reg"][1], reg_out=work["rot_out"], reg_dim=6, update=update)
             if li + 1 < nl:
-                kw.update(next_wq=off(w["ada_w"][li + 1], "C_WQ"), next_ada_layer=li + 1, q_out=qb)
-            lib.cd_post(trajectory, mask, work["wp_pe"], t_idx, ada, nl, li, x_in, att, w["ada_w"][li].data_ptr(),
+                kw.update(next_wq=w["ada_w"][li + 1], next_bq=w["ada_v"][li + 1], next_ada_layer=li + 1, q_out=qb)
+            lib.cd_post(trajectory, mask, work["wp_pe"], t_idx, ada, nl, li, x_in, att, w["ada_w"][li], w["ada_v"][li],
                         xb[li + 1], **kw)
         return work["pos_upd"], work["rot_out"]
 
@@ -243,23 +261,6 @@ class DiffusionHead(nn.Module):
         return [torch.cat((traj[..., :3] + pos_upd, rot), -1)]
 
 
-def _ada_offsets():
-    e, ep, ffp = 120, 128, 512
-    names = ["C_WQ", "C_BQ", "C_WO", "C_BO", "G12", "B12", "S_WQ", "S_BQ", "S_WK", "S_BK", "S_WV", "S_BV", "S_WO", "S_BO",
-             "G1", "B1N", "W1", "B1", "W2", "B2", "G122", "B122"]
-    sizes = [e * ep, ep, e * ep, ep, ep, ep, e * ep, ep, e * ep, ep, e * ep, ep, e * ep, ep, ep, ep,
-             e * ffp, ffp, ffp * ep, ep, ep, ep]
-    out, o = {}, 0
-    for n_, s_ in zip(names, sizes):
-        out[n_] = o
-        o += s_
-    out["SIZE"] = o
-    return out
-
-
-_ADA_OFF = _ada_offsets()
-
-
 class DiffusionPlanner(nn.Module):
 
     def __init__(self, backbone="clip", image_size=(256, 256), embedding_dim=60, output_dim=7,
@@ -280,6 +281,9 @@ class DiffusionPlanner(nn.Module):
         self.n_steps = diffusion_timesteps
         self.gripper_loc_bounds = torch.tensor(gripper_loc_bounds)
         self._noise_fn = None          # test hook: callable(shape) -> CPU/GPU tensor, called in the reference's order
+        self.rng_compat = False        # True: draw Gaussian noise with the reference's torch.randn call sequence
+        self.use_cuda_graph = True     # capture the 100-step loop once per shape and replay it
+        self._samplers = {}
 
     # ------------------------------------------------------------------ frame conversions (torch, elementwise)
     def normalize_pos(self, pos):
@@ -313,11 +317,36 @@ class DiffusionPlanner(nn.Module):
         return torch.randn(shape, device=device)
 
     # ------------------------------------------------------------------ sampling
+    def _sampler_state(self, b, length, rows_key, dev):
+        """Persistent buffers (+ the captured CUDA graph) of the sampling loop for one problem shape."""
+        key = (b, length, rows_key, str(dev))
+        st = self._samplers.get(key)
+        if st is None:
+            n = self.n_steps
+            st = dict(traj=torch.empty(b, length, 9, device=dev), cond=torch.empty(b, length, 9, device=dev),
+                      cmask=torch.empty(b, length, 9, device=dev, dtype=torch.uint8),
+                      noise_pos=torch.empty(n, b, length, 3, device=dev), noise_rot=torch.empty(n, b, length, 6, device=dev),
+                      static={}, graph=None, graph_sig=None)
+            self._samplers[key] = st
+        return st
+
+    def _run_steps(self, ctx, st, work, trajectory_mask, timesteps, t_all):
+        head = self.prediction_head
+        pc, rc = self.position_noise_scheduler.coef, self.rotation_noise_scheduler.coef
+        for k, t in enumerate(timesteps):
+            last = k == len(timesteps) - 1
+            upd = dict(last_step=int(last), traj_out=st["traj"], pos_upd=work["pos_upd"], cond_data=st["cond"],
+                       cond_mask=st["cmask"], coef=[pc[t, 0], pc[t, 1], pc[t, 2], rc[t, 0], rc[t, 1], rc[t, 2]],
+                       noise_pos=st["noise_pos"][k], noise_rot=st["noise_rot"][k])
+            head.denoise(ctx, st["traj"], trajectory_mask, t_all[k], work, update=upd)
+
     @torch.no_grad()
     def conditional_sample(self, condition_data, condition_mask, fixed_inputs):
         """100-step DDPM ancestral sampling with inpainting of the conditioned waypoints
-        (diffusion_model.py:86-119).  Gaussian draws are made in the reference's order:
-        (B,L,9) once, then per step (B,L,3) and (B,L,6) for every t > 0."""
+        (diffusion_model.py:86-119).  The whole loop (17 kernels per step) is captured once per problem shape in
+        a CUDA graph and replayed.  Gaussian noise: with ``rng_compat`` (or the test hook ``_noise_fn``) the draws
+        are made in the reference's call order -- (B,L,9) once, then per step (B,L,3) and (B,L,6) for t > 0;
+        otherwise the per-step tensors are filled with two bulk normal_() calls (same distribution)."""
         trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper = fixed_inputs
         head = self.prediction_head
         dev = condition_data.device
@@ -325,22 +354,43 @@ class DiffusionPlanner(nn.Module):
         self.position_noise_scheduler.set_timesteps(self.n_steps)
         self.rotation_noise_scheduler.set_timesteps(self.n_steps)
         timesteps = self.position_noise_scheduler.timesteps
-        ctx = head.encode_context(rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper, self.n_steps)
-        work = head.make_work(b, length, trajectory_mask, dev)
-        cond = condition_data.float().contiguous()
-        cmask = condition_mask.to(torch.uint8).contiguous()
-        traj = (self._randn(cond.shape, dev) + cond).contiguous()
-        t_all = torch.tensor(timesteps, device=dev, dtype=torch.int32)[:, None].repeat(1, b).contiguous()
-        pc, rc = self.position_noise_scheduler.coef, self.rotation_noise_scheduler.coef
-        for k, t in enumerate(timesteps):
-            last = k == len(timesteps) - 1
-            upd = dict(last_step=int(last), traj_out=traj, pos_upd=work["pos_upd"], cond_data=cond, cond_mask=cmask,
-                       coef=[pc[t, 0], pc[t, 1], pc[t, 2], rc[t, 0], rc[t, 1], rc[t, 2]])
-            if not last:
-                upd["noise_pos"] = self._randn((b, length, 3), dev)
-                upd["noise_rot"] = self._randn((b, length, 6), dev)
-            head.denoise(ctx, traj, trajectory_mask, t_all[k], work, update=upd)
-        return traj
+        has_mask = trajectory_mask is not None and bool(trajectory_mask.any())
+        st = self._sampler_state(b, length, (rgb_obs.shape[1], has_mask), dev)
+        ctx = head.encode_context(rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper, self.n_steps,
+                                  static=st["static"])
+        if "work" not in st:
+            st["work"] = head.make_work(b, length, trajectory_mask, dev)
+            st["t_all"] = torch.tensor(timesteps, device=dev, dtype=torch.int32)[:, None].repeat(1, b).contiguous()
+        work = st["work"]
+        if has_mask:
+            work["mask_u8"].copy_(trajectory_mask.to(torch.uint8))
+        st["cond"].copy_(condition_data.float())
+        st["cmask"].copy_(condition_mask.to(torch.uint8))
+        compat = self.rng_compat or self._noise_fn is not None
+        st["traj"].copy_(self._randn(st["cond"].shape, dev) + st["cond"])
+        if compat:
+            for k in range(len(timesteps) - 1):
+                st["noise_pos"][k].copy_(self._randn((b, length, 3), dev))
+                st["noise_rot"][k].copy_(self._randn((b, length, 6), dev))
+        else:
+            st["noise_pos"].normal_()
+            st["noise_rot"].normal_()
+
+        if not self.use_cuda_graph:
+            self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
+            return st["traj"].clone()
+        sig = (ctx["kv"].data_ptr(), id(ctx["w"]), ctx["nk"])
+        if st["graph"] is None or st["graph_sig"] != sig:
+            # one eager evaluation first: sets kernel attributes / warms caches outside the capture
+            scratch = st["traj"].clone()
+            head.denoise(ctx, scratch, trajectory_mask if has_mask else None, st["t_all"][0], work)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
+            st["graph"], st["graph_sig"], st["ctx_keepalive"] = g, sig, ctx
+        st["graph"].replay()
+        return st["traj"].clone()
 
     @torch.no_grad()
     def compute_trajectory(self, trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper):

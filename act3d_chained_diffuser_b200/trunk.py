@@ -54,3 +54,45 @@ def build_backbone(kind):
         net.load_state_dict(clip_model.visual.state_dict())
         return net, clip_tf.transforms[-1]
     raise ValueError(f"backbone must be 'resnet' or 'clip', got {kind!r}")
+
+
+class EvalTrunk:
+    """Inference-time view of (normalize, frozen backbone, FPN): BatchNorm folded into the preceding
+    convolution and channels-last activations, so that cuDNN runs NHWC tensor-core kernels without
+    the per-layer NCHW<->NHWC conversions and separate BN / ReLU passes of the eager module.
+    Only used in eval mode (the reference keeps the frozen backbone's BN in train mode while
+    training, act3d.py:72-73 -- that behaviour is preserved by falling back to the plain modules).
+    The folded copy is rebuilt when the source parameters / buffers change."""
+
+    def __init__(self):
+        self._sig = None
+        self._fused = None
+
+    @staticmethod
+    def _signature(backbone):
+        return tuple((t.data_ptr(), t._version) for t in list(backbone.parameters()) + list(backbone.buffers()))
+
+    def _fuse(self, backbone):
+        import copy
+        from torch.nn.utils.fusion import fuse_conv_bn_eval
+        net = copy.deepcopy(backbone).eval()
+
+        def fold(module):
+            names = list(module._modules.keys())
+            for a, b in zip(names, names[1:]):
+                ma, mb = module._modules[a], module._modules[b]
+                if isinstance(ma, torch.nn.Conv2d) and isinstance(mb, torch.nn.BatchNorm2d):
+                    module._modules[a] = fuse_conv_bn_eval(ma, mb)
+                    module._modules[b] = torch.nn.Identity()
+            for child in module._modules.values():
+                if child is not None:
+                    fold(child)
+        fold(net)
+        return net.to(memory_format=torch.channels_last)
+
+    def __call__(self, normalize, backbone, fpn, rgb):
+        sig = self._signature(backbone)
+        if self._fused is None or sig != self._sig:
+            self._fused, self._sig = self._fuse(backbone), sig
+        x = normalize(rgb).contiguous(memory_format=torch.channels_last)
+        return fpn(self._fused(x))

@@ -327,6 +327,7 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.backends.cudnn.benchmark = True          # as the reference's entry points do (main_keypose.py:518-520)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:

@@ -140,29 +140,35 @@ int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host
 
 /* =================================================================================
  * ChainedDiffuser trajectory denoiser (embedding_dim 120, 8 heads, FFN 480, <= 64 waypoints).
- * Packed weight layouts (all fp32, K-major, padded to 128 / 512 columns) are produced by
- * act3d_chained_diffuser_b200/packing.py: pack_lang_layer / pack_ada_layer / pack_mlp;
- * cd_pack_floats(0|1|2|3) returns the float count of a LangPack / AdaPack / MlpPack / adaLN row.
+ * Linear layers run as error-compensated fp16-split tensor-core GEMMs (csrc/a3d_mma_gemm.cuh):
+ * every weight matrix is passed as a fragment-ordered (hi, lo) fp16 buffer ("W" packs, void*) plus
+ * an fp32 vector buffer with biases / LayerNorm parameters ("V" packs).  Layouts are produced by
+ * act3d_chained_diffuser_b200/packing.py (pack_lang_layer / pack_ada_layer / pack_mlp);
+ * cd_pack_floats(0..3) = float count of LangV / AdaV / MlpV / one adaLN table row,
+ * cd_pack_floats(4..6) = 32-bit word count of LangW / AdaW / MlpW.
  */
 size_t cd_pack_floats(int which);
 
 /* Vision -> language attention, step-invariant.  Replaces the vl_attention ParallelAttention stack
  * (diffusion_head.py:305-314; layers.py:115-218 with cross_attention1 only + FFN, no adaLN/rotary).
  * tok [B][tok_rows][E]: first nctx rows updated in place.  kin / vin [nlayers][B][n_instr][E]:
- * fp32 K and V projections of the instruction tokens.  w: nlayers LangPacks. */
+ * fp32 K and V projections of the instruction tokens.  w / v: nlayers LangW / LangV packs. */
 int cd_ctx_lang(float* tok, int batch, int tok_rows, int nctx, int embed, int heads, const float* kin,
-                const float* vin, int n_instr, const float* w, int nlayers, void* stream);
+                const float* vin, int n_instr, const void* w, const float* v, int nlayers, void* stream);
 
 /* Start of one denoiser evaluation.  Replaces traj_encoder + waypoint sinusoidal embedding +
  * traj_lang_attention (diffusion_head.py:215-216, 326-336) and prepares the fp16 rotary Q of the
  * first adaLN cross-attention layer.  traj [B][L][9] (normalised frame), wp_pe [L][E], t_idx [B]
- * timestep per sample, ada [T][ada_layers][3][2][128] adaLN (scale, shift) table, traj_enc MlpPack,
- * lang_w LangPack or NULL (use_instruction=0), lang_k / lang_v [B][n_instr][E], x_out [B][64][E],
- * next_wq -> {W_q^T [E][128], b_q[128]} of the next cross-attention, q_out [B][H][64][16] fp16. */
+ * timestep per sample, ada [T][ada_layers][3][2][128] adaLN (scale, shift) table; traj_enc1 = fp32
+ * K-major [9][128] weight + [128] bias of the first encoder layer, traj_enc2 / traj_enc2_b = second
+ * layer (fragment order / bias); lang_w / lang_v LangW / LangV or NULL (use_instruction=0);
+ * lang_k / lang_vv [B][n_instr][E]; x_out [B][64][E]; next_wq / next_bq = W_q (fragment order) and
+ * bias of the first cross-attention; q_out [B][H][64][16] fp16. */
 int cd_step_begin(const float* traj, int batch, int length, const float* wp_pe, const int* t_idx,
-                  const float* ada, int ada_layers, const float* traj_enc, const float* lang_w,
-                  const float* lang_k, const float* lang_v, int n_instr, float* x_out,
-                  const float* next_wq, int next_ada_layer, void* q_out, void* stream);
+                  const float* ada, int ada_layers, const float* traj_enc1, const void* traj_enc2,
+                  const float* traj_enc2_b, const void* lang_w, const float* lang_v, const float* lang_k,
+                  const float* lang_vv, int n_instr, float* x_out, const void* next_wq,
+                  const float* next_bq, int next_ada_layer, void* q_out, void* stream);
 
 /* Cross-attention of the waypoint tokens over the cached context K/V of one layer (tile images from
  * a3d_ctx_kv).  Replaces the cross_12 attention core of ParallelAttentionLayer (layers.py:135-145;
@@ -174,14 +180,15 @@ int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float*
  * regressor head (diffusion_head.py:179-198, 357-363), the Q of the next layer, and -- on the last
  * layer of a step -- the denoiser output assembly (diffusion_head.py:271-274), inpainting of the
  * conditioned waypoints and the DDPM posterior step of both schedulers (diffusion_model.py:105-117).
+ * layer_w / layer_v = AdaW / AdaV of this layer, reg_w / reg_v = MlpW / MlpV or NULL.
  * coef_host = {c_x0, c_xt, sigma} for positions then rotations (act3d_chained_diffuser_b200/ddpm.py). */
 int cd_post(const float* traj, int batch, int length, const unsigned char* mask, const float* wp_pe,
             const int* t_idx, const float* ada, int ada_layers, int ada_layer, const float* x_in,
-            const float* att, const float* layer_w, float* x_out, const float* reg_w, float* reg_out,
-            int reg_dim, const float* next_src, const float* next_wq, int next_ada_layer, void* q_out,
-            int do_update, int last_step, float* traj_out, const float* pos_upd, const float* cond_data,
-            const unsigned char* cond_mask, const float* coef_host, const float* noise_pos,
-            const float* noise_rot, void* stream);
+            const float* att, const void* layer_w, const float* layer_v, float* x_out, const void* reg_w,
+            const float* reg_v, float* reg_out, int reg_dim, const float* next_src, const void* next_wq,
+            const float* next_bq, int next_ada_layer, void* q_out, int do_update, int last_step,
+            float* traj_out, const float* pos_upd, const float* cond_data, const unsigned char* cond_mask,
+            const float* coef_host, const float* noise_pos, const float* noise_rot, void* stream);
 
 #ifdef __cplusplus
 }
