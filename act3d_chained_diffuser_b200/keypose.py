@@ -140,7 +140,8 @@ class Act3D(nn.Module):
                 or isinstance(self.backbone, torch.nn.Identity):
             feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
         else:
-            feats = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb)
+            feats = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
+                                     needed=self.feature_map_pyramid[:self.num_sampling_level])
         pcd = visible_pcd.reshape(b * num_cameras, *visible_pcd.shape[2:]).contiguous().float()
         feats_pyr, pcd_pyr, cache = [], [], {}
         for i in range(self.num_sampling_level):

@@ -153,7 +153,7 @@ class DiffusionHead(nn.Module):
         if self.training or not self.fold_trunk or isinstance(self.backbone, torch.nn.Identity):
             fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
         else:
-            fpn = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb)
+            fpn = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=("res3",))
         fm = fpn["res3"].contiguous().float()
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)

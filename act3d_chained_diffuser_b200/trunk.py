@@ -57,22 +57,32 @@ def build_backbone(kind):
 
 
 class EvalTrunk:
-    """Inference-time view of (normalize, frozen backbone, FPN): BatchNorm folded into the preceding
-    convolution and channels-last activations, so that cuDNN runs NHWC tensor-core kernels without
-    the per-layer NCHW<->NHWC conversions and separate BN / ReLU passes of the eager module.
-    Only used in eval mode (the reference keeps the frozen backbone's BN in train mode while
-    training, act3d.py:72-73 -- that behaviour is preserved by falling back to the plain modules).
-    The folded copy is rebuilt when the source parameters / buffers change."""
+    """Inference-time evaluation of (normalize, frozen backbone, FPN) -- still PyTorch / cuDNN library
+    calls (the trunk is dense convolution work that stays on cuDNN), but organised the
+    way an inference engine would:
+      * BatchNorm folded into the preceding convolution (frozen backbone, eval statistics);
+      * channels-last activations (NHWC tensor-core kernels, no per-layer layout conversions);
+      * for torchvision ResNets, cuDNN's fused conv+bias+ReLU and conv+bias+residual+ReLU entry points
+        (`torch.cudnn_convolution_relu`, `torch.cudnn_convolution_add_relu`) instead of separate bias / add /
+        clamp kernels;
+      * only the FPN levels the model reads are computed (the reference evaluates all five output
+        convolutions and discards three of them).
+    Only used in eval mode: while training, the reference keeps the frozen backbone's BN in train mode
+    (act3d.py:72-73) and that behaviour is preserved by running the plain modules.  The folded weights are
+    rebuilt whenever the backbone's parameters / buffers change."""
 
     def __init__(self):
         self._sig = None
         self._fused = None
+        self._plan = None
+        self._fused_ok = True
 
     @staticmethod
     def _signature(backbone):
         return tuple((t.data_ptr(), t._version) for t in list(backbone.parameters()) + list(backbone.buffers()))
 
-    def _fuse(self, backbone):
+    @staticmethod
+    def _fold_modules(backbone):
         import copy
         from torch.nn.utils.fusion import fuse_conv_bn_eval
         net = copy.deepcopy(backbone).eval()
@@ -90,9 +100,73 @@ class EvalTrunk:
         fold(net)
         return net.to(memory_format=torch.channels_last)
 
-    def __call__(self, normalize, backbone, fpn, rgb):
+    @staticmethod
+    def _conv_args(conv):
+        w = conv.weight.detach().contiguous(memory_format=torch.channels_last)
+        b = conv.bias.detach() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+        return w, b, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups
+
+    def _resnet_plan(self, folded):
+        """Flatten a folded torchvision ResNet into (stem, [blocks]) of cuDNN fused-call arguments."""
+        plan = dict(stem=self._conv_args(folded.conv1), pool=folded.maxpool, stages=[])
+        for stage in (folded.layer1, folded.layer2, folded.layer3, folded.layer4):
+            blocks = []
+            for blk in stage:
+                down = self._conv_args(blk.downsample[0]) if blk.downsample is not None else None
+                blocks.append((self._conv_args(blk.conv1), self._conv_args(blk.conv2), self._conv_args(blk.conv3), down))
+            plan["stages"].append(blocks)
+        return plan
+
+    @staticmethod
+    def _run_resnet(plan, x):
+        cr, car = torch.cudnn_convolution_relu, torch.cudnn_convolution_add_relu
+        stem = cr(x, *plan["stem"])
+        feats = {"res1": stem}
+        y = plan["pool"](stem)
+        for i, blocks in enumerate(plan["stages"]):
+            for c1, c2, c3, down in blocks:
+                ident = y if down is None else torch.nn.functional.conv2d(y, down[0], down[1], down[2], down[3], down[4], down[5])
+                o = cr(y, *c1)
+                o = cr(o, *c2)
+                y = car(o, c3[0], ident, 1.0, c3[1], c3[2], c3[3], c3[4], c3[5])
+            feats[f"res{i + 2}"] = y
+        return feats
+
+    @staticmethod
+    def _run_fpn(fpn, feats, needed):
+        """torchvision FeaturePyramidNetwork.forward restricted to the requested output levels
+        (identical arithmetic for those levels)."""
+        names = list(feats.keys())
+        lowest = min(names.index(n) for n in needed)
+        conv = torch.nn.functional.conv2d
+
+        def inner(i):
+            m = fpn.inner_blocks[i][0]
+            return conv(feats[names[i]], m.weight, m.bias)
+
+        def layer(i, t):
+            m = fpn.layer_blocks[i][0]
+            return conv(t, m.weight, m.bias, padding=1)
+        out = {}
+        last = inner(len(names) - 1)
+        if names[-1] in needed:
+            out[names[-1]] = layer(len(names) - 1, last)
+        for i in range(len(names) - 2, lowest - 1, -1):
+            lat = inner(i)
+            last = lat + torch.nn.functional.interpolate(last, size=lat.shape[-2:], mode="nearest")
+            if names[i] in needed:
+                out[names[i]] = layer(i, last)
+        return out
+
+    def __call__(self, normalize, backbone, fpn, rgb, needed=("res1", "res3")):
         sig = self._signature(backbone)
         if self._fused is None or sig != self._sig:
-            self._fused, self._sig = self._fuse(backbone), sig
+            self._fused, self._sig = self._fold_modules(backbone), sig
+            self._plan = self._resnet_plan(self._fused) if isinstance(backbone, ResNet) else None
         x = normalize(rgb).contiguous(memory_format=torch.channels_last)
+        if self._plan is not None and self._fused_ok and x.is_cuda:
+            try:
+                return self._run_fpn(fpn, self._run_resnet(self._plan, x), set(needed))
+            except RuntimeError:          # cuDNN fused entry points unavailable for this build / shape
+                self._fused_ok = False
         return fpn(self._fused(x))
