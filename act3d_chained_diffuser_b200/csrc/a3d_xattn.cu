@@ -1,3 +1,5 @@
+// FIRST-GENERATION fused cross-attention stack (FFMA epilogue through shared memory).  Superseded by
+// a3d_xattn2.cu; kept exported as a3d_xattn_stack_v1 for A/B profiling only (not in the public header).
 // Fused cross-attention stack (Act3D ghost-point / query / vision-language stacks).
 //
 // One CTA owns 128 query rows of one sample for ALL layers of the stack; the residual stream
@@ -422,22 +424,22 @@ extern "C" int a3d_set_option(const char* name, int value) {
     A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");
 }
 
-extern "C" size_t a3d_xattn_layer_floats(int embed, int ffn) {
+extern "C" size_t a3d_xattn_v1_layer_floats(int embed, int ffn) {
     if (embed == 60 && ffn == 60) return XaCfg<60, 4, 60>::LAYER_FLOATS;
     return 0;
 }
 
-extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride_n, const float* qpos, int batch,
+extern "C" int a3d_xattn_stack_v1(const float* x0, long x0_stride_b, long x0_stride_n, const float* qpos, int batch,
                                int nq, int nk, int embed, int heads, int ffn, int nlayers, const void* kv_base,
                                size_t kv_layer_stride_bytes, const float* w, float* feat_out, int feat_rows,
                                int feat_all_layers, const float* qvec, int nqv, float* logits, void* stream) {
-    A3D_REQUIRE(x0 && kv_base && w, "a3d_xattn_stack: null pointer");
-    A3D_REQUIRE(batch > 0 && nq > 0 && nk > 0 && nlayers > 0, "a3d_xattn_stack: empty problem (B=%d nq=%d nk=%d L=%d)", batch, nq, nk, nlayers);
-    A3D_REQUIRE(embed == 60 && heads == 4 && ffn == 60, "a3d_xattn_stack: (embed, heads, ffn) = (%d,%d,%d) not supported; built for (60,4,60)", embed, heads, ffn);
-    A3D_REQUIRE(!feat_out || feat_rows >= nq, "a3d_xattn_stack: feat_rows %d < nq %d", feat_rows, nq);
-    A3D_REQUIRE((logits == nullptr) == (qvec == nullptr || nqv == 0), "a3d_xattn_stack: qvec/logits must be given together");
-    A3D_REQUIRE(((uintptr_t)kv_base & 15) == 0 && (kv_layer_stride_bytes & 15) == 0, "a3d_xattn_stack: K/V cache must be 16-byte aligned");
-    A3D_REQUIRE(batch <= 65535, "a3d_xattn_stack: batch %d exceeds grid.y", batch);
+    A3D_REQUIRE(x0 && kv_base && w, "a3d_xattn_stack_v1: null pointer");
+    A3D_REQUIRE(batch > 0 && nq > 0 && nk > 0 && nlayers > 0, "a3d_xattn_stack_v1: empty problem (B=%d nq=%d nk=%d L=%d)", batch, nq, nk, nlayers);
+    A3D_REQUIRE(embed == 60 && heads == 4 && ffn == 60, "a3d_xattn_stack_v1: (embed, heads, ffn) = (%d,%d,%d) not supported; built for (60,4,60)", embed, heads, ffn);
+    A3D_REQUIRE(!feat_out || feat_rows >= nq, "a3d_xattn_stack_v1: feat_rows %d < nq %d", feat_rows, nq);
+    A3D_REQUIRE((logits == nullptr) == (qvec == nullptr || nqv == 0), "a3d_xattn_stack_v1: qvec/logits must be given together");
+    A3D_REQUIRE(((uintptr_t)kv_base & 15) == 0 && (kv_layer_stride_bytes & 15) == 0, "a3d_xattn_stack_v1: K/V cache must be 16-byte aligned");
+    A3D_REQUIRE(batch <= 65535, "a3d_xattn_stack_v1: batch %d exceeds grid.y", batch);
     using C = XaCfg<60, 4, 60>;
     XaArgs a;
     a.x0 = x0;
@@ -473,5 +475,5 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
         default: A3D_LAUNCH_XA(false, false); break;
     }
 #undef A3D_LAUNCH_XA
-    return check_launch("a3d_xattn_stack");
+    return check_launch("a3d_xattn_stack_v1");
 }

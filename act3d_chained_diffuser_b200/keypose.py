@@ -108,8 +108,8 @@ class Act3D(nn.Module):
             layers = [pack_xattn_layer(stack.attn_layers[l].multihead_attn, stack.attn_layers[l].norm,
                                        stack.ffw_layers[l], e, h) for l in range(stack.num_layers)]
             kv = [pack_kv_set(stack.attn_layers[l].multihead_attn, e, h) for l in range(stack.num_layers)]
-            return dict(w=torch.cat(layers).contiguous(), wkv=torch.stack([k[0] for k in kv]),
-                        bkv=torch.stack([k[1] for k in kv]))
+            return dict(w=torch.cat([x[0] for x in layers]).contiguous(), v=torch.cat([x[1] for x in layers]).contiguous(),
+                        wkv=torch.stack([k[0] for k in kv]), bkv=torch.stack([k[1] for k in kv]))
         return self._packs.get(tag, params, build)
 
     # ------------------------------------------------------------------ sampling
@@ -216,7 +216,7 @@ class Act3D(nn.Module):
                 pk = self._stack_pack(("vis", id(vi)), vi)
                 kv_i = lib.ctx_kv(instr, instr_zero_pos, n_instr, h, pk["wkv"], pk["bkv"], [0] * vi.num_layers)
                 lib.xattn_stack(tok, rows * e, e, None, b, n_vis + 1, n_instr, e, h, e, vi.num_layers, kv_i, 0,
-                                lib.kv_bytes(1, b, n_instr, h), pk["w"], feat_out=tok, feat_rows=rows)
+                                lib.kv_bytes(1, b, n_instr, h), pk["w"], pk["v"], feat_out=tok, feat_rows=rows)
                 tok[:, n_vis + 1:] = instr
                 pos[:, n_vis + 1:] = 0.0
 
@@ -238,7 +238,7 @@ class Act3D(nn.Module):
                 q_x0, q_sb = query_feat.contiguous(), e
                 q_pos = carried[-1].contiguous()
             lib.xattn_stack(q_x0, q_sb, 0, q_pos, b, 1, rows, e, h, e, lq, kv, lg * set_bytes, set_bytes, pq["w"],
-                            feat_out=q_all, feat_rows=1, feat_all_layers=True)
+                            pq["v"], feat_out=q_all, feat_rows=1, feat_all_layers=True)
             query_feat = q_all[-1, :, 0]                                     # (B, E)
 
             # ---- ghost points: fused attention stack + mask logits against both query layers
@@ -251,7 +251,7 @@ class Act3D(nn.Module):
             if prof is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"],
+            lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"], pg["v"],
                             feat_out=ghost_feats, feat_rows=ng, qvec=q_all.view(lq, b, e), logits=logits)
             if prof is not None:
                 ev1.record()

@@ -27,8 +27,9 @@ EXPORTS = {
     "a3d_ctx_kv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            ctypes.POINTER(c_int), c_int, c_void_p, c_void_p]),
     "a3d_xattn_layer_floats": (c_size_t, [c_int, c_int]),
+    "a3d_xattn_layer_words": (c_size_t, [c_int, c_int]),
     "a3d_xattn_stack": (c_int, [c_void_p, c_long, c_long, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                 c_void_p, c_void_p]),
     "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
@@ -175,13 +176,18 @@ def xattn_layer_floats(embed, ffn):
     return n
 
 
+def xattn_layer_words(embed, ffn):
+    return load().a3d_xattn_layer_words(embed, ffn)
+
+
 def xattn_stack(x0, x0_stride_b, x0_stride_n, qpos, batch, nq, nk, embed, heads, ffn, nlayers, kv, kv_offset_bytes,
-                kv_layer_stride, w, feat_out=None, feat_rows=0, feat_all_layers=False, qvec=None, logits=None):
+                kv_layer_stride, w, v, feat_out=None, feat_rows=0, feat_all_layers=False, qvec=None, logits=None):
     nqv = qvec.shape[0] if qvec is not None else 0
+    assert w.is_cuda and w.is_contiguous()
     _check(load().a3d_xattn_stack(_ptr(_f32(x0)), x0_stride_b, x0_stride_n, _ptr(qpos), batch, nq, nk, embed, heads,
-                                  ffn, nlayers, kv.data_ptr() + kv_offset_bytes, kv_layer_stride, _ptr(_f32(w)),
-                                  _ptr(feat_out), feat_rows, int(feat_all_layers), _ptr(qvec), nqv, _ptr(logits),
-                                  _stream()), "a3d_xattn_stack")
+                                  ffn, nlayers, kv.data_ptr() + kv_offset_bytes, kv_layer_stride, w.data_ptr(),
+                                  _ptr(_f32(v)), _ptr(feat_out), feat_rows, int(feat_all_layers), _ptr(qvec), nqv,
+                                  _ptr(logits), _stream()), "a3d_xattn_stack")
 
 
 def argmax_pick(logits, ghost):

@@ -29,23 +29,26 @@ def _kmajor(weight, width):
 
 
 def pack_xattn_layer(attn, norm, ffw, embed, heads):
-    """One layer of an Act3D stack -> flat tensor in the XaCfg order (csrc/a3d_xattn.cu):
-    W_Q[E][EP] B_Q[EP] W_O[E][EP] B_O G_1 BE_1 W_1[E][EP] B_1 W_2[FF][EP] B_2 G_2 BE_2.
-    The q projection carries hd^-1/2 (multihead_custom_attention.py:244,325) and log2(e) so the
-    kernel's softmax is a bare exp2."""
+    """One layer of an Act3D stack -> (w int32 fragments, v floats) in the Xa2 order (csrc/a3d_xattn2.cu):
+    w = {W_q, W_o, W_1, W_2} as fragment-ordered fp16 (hi, lo) [K=64][N=64] matrices, v = {b_q, b_o, g1, be1,
+    b_1, b_2, g2, be2} (64 floats each).  The q projection carries hd^-1/2 (multihead_custom_attention.py:244,325)
+    and log2(e) so the kernel's softmax is a bare exp2.  W_o's input (K) index is head-padded: k = 16 h + d
+    <- attention dim 15 h + d (the pad slot carries the softmax denominator in the kernel; its weight is 0)."""
     ep = 16 * heads
     e = embed
-    scale = (float(e // heads) ** -0.5) * LOG2E
+    hd = e // heads
+    scale = (float(hd) ** -0.5) * LOG2E
     w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
-    parts = [
-        _kmajor(w_in[:e] * scale, ep).reshape(-1), _pad_vec(b_in[:e] * scale, ep),
-        _kmajor(attn.out_proj.weight, ep).reshape(-1), _pad_vec(attn.out_proj.bias.detach().float(), ep),
-        _pad_vec(norm.weight.detach().float(), ep), _pad_vec(norm.bias.detach().float(), ep),
-        _kmajor(ffw.linear1.weight, ep).reshape(-1), _pad_vec(ffw.linear1.bias.detach().float(), ep),
-        _kmajor(ffw.linear2.weight, ep).reshape(-1), _pad_vec(ffw.linear2.bias.detach().float(), ep),
-        _pad_vec(ffw.norm.weight.detach().float(), ep), _pad_vec(ffw.norm.bias.detach().float(), ep),
-    ]
-    return torch.cat(parts)
+    wo = attn.out_proj.weight.detach().float()
+    wo_p = wo.new_zeros(e, ep)
+    for h in range(heads):
+        wo_p[:, 16 * h:16 * h + hd] = wo[:, hd * h:hd * (h + 1)]
+    w = torch.cat([pack_mma_weight(w_in[:e] * scale, ep, ep), pack_mma_weight(wo_p, ep, ep),
+                   pack_mma_weight(ffw.linear1.weight, ep, ep), pack_mma_weight(ffw.linear2.weight, ep, ep)])
+    vec = lambda t: _pad_vec(t.detach().float(), ep)
+    v = torch.cat([_pad_vec(b_in[:e] * scale, ep), vec(attn.out_proj.bias), vec(norm.weight), vec(norm.bias),
+                   vec(ffw.linear1.bias), vec(ffw.linear2.bias), vec(ffw.norm.weight), vec(ffw.norm.bias)])
+    return w.contiguous(), v.contiguous()
 
 
 def pack_kv_set(attn, embed, heads):

@@ -108,7 +108,10 @@ int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok_rows, int 
  * qpos [B][nq][3] or NULL (no rotary on this stack: K sets must then be unrotated).
  * kv[l] = K/V tile images of layer l for this context (a3d_ctx_kv), passed as kv_base +
  *     l * kv_layer_stride_bytes.
- * w: packed layer weights, see act3d_chained_diffuser_b200/packing.py (pack_xattn_layer).
+ * w / v: packed layer weights, see act3d_chained_diffuser_b200/packing.py (pack_xattn_layer): per layer four
+ *     fragment-ordered fp16 (hi, lo) [64][64] matrices {W_q, W_o, W_1, W_2} for the error-compensated
+ *     tensor-core GEMMs (csrc/a3d_mma_gemm.cuh) and eight fp32 vectors {b_q, b_o, g1, be1, b_1, b_2, g2, be2}.
+ *     x0 must be 8-byte aligned with even strides.
  * feat_out: NULL or [n_feat_layers][B][feat_rows][E]; rows [0,nq) written; if
  *     feat_all_layers==0 only the last layer is written (n_feat_layers = 1).
  * qvec [nqv][B][E] + logits [nqv][B][nq]: logits[j][b][n] = <qvec[j][b], x_last[b][n]>; NULL to skip.
@@ -116,10 +119,11 @@ int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok_rows, int 
  */
 int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride_n, const float* qpos,
                     int batch, int nq, int nk, int embed, int heads, int ffn, int nlayers,
-                    const void* kv_base, size_t kv_layer_stride_bytes, const float* w,
+                    const void* kv_base, size_t kv_layer_stride_bytes, const void* w, const float* v,
                     float* feat_out, int feat_rows, int feat_all_layers,
                     const float* qvec, int nqv, float* logits, void* stream);
-size_t a3d_xattn_layer_floats(int embed, int ffn);
+size_t a3d_xattn_layer_words(int embed, int ffn);   /* 32-bit words of fragment-ordered weights per layer (w) */
+size_t a3d_xattn_layer_floats(int embed, int ffn);  /* fp32 vector floats per layer (v) */
 
 /* ---------------------------------------------------------------------------------
  * Top ghost point.  Replaces torch.max(mask, -1).indices + position gather

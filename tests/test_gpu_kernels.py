@@ -176,8 +176,10 @@ def run_stack(lib, sd, layers, x0, x0_mode, q_xyz, ctx, c_xyz, qvec=None, all_la
     stack.load_state_dict(sd)
     b, nk = ctx.shape[0], ctx.shape[1]
     nq = q_xyz.shape[1] if q_xyz is not None else (x0.shape[1] if x0_mode == "rows" else 1)
-    w = torch.cat([pack_xattn_layer(stack.attn_layers[l].multihead_attn, stack.attn_layers[l].norm,
-                                    stack.ffw_layers[l], e, h) for l in range(layers)]).cuda()
+    lp = [pack_xattn_layer(stack.attn_layers[l].multihead_attn, stack.attn_layers[l].norm, stack.ffw_layers[l], e, h)
+          for l in range(layers)]
+    w = torch.cat([x[0] for x in lp]).cuda()
+    wv = torch.cat([x[1] for x in lp]).cuda()
     packs = [pack_kv_set(stack.attn_layers[l].multihead_attn, e, h) for l in range(layers)]
     wkv = torch.stack([p[0] for p in packs]).cuda()
     bkv = torch.stack([p[1] for p in packs]).cuda()
@@ -192,7 +194,7 @@ def run_stack(lib, sd, layers, x0, x0_mode, q_xyz, ctx, c_xyz, qvec=None, all_la
     else:
         sb, sn = nq * e, e
     lib.xattn_stack(dev(x0), sb, sn, dev(q_xyz) if (rope and q_xyz is not None) else None, b, nq, nk, e, h, e,
-                    layers, kv, 0, lib.kv_bytes(1, b, nk, h), w, feat_out=feat, feat_rows=nq,
+                    layers, kv, 0, lib.kv_bytes(1, b, nk, h), w, wv, feat_out=feat, feat_rows=nq,
                     feat_all_layers=all_layers, qvec=dev(qvec) if qvec is not None else None, logits=logits)
     torch.cuda.synchronize()
     return feat.cpu(), (logits.cpu() if logits is not None else None)
