@@ -415,7 +415,13 @@ using namespace a3d;
 
 // numerics variant of the attention core: bit0 = fp32 exp, bit1 = split-Q (see kernel comment)
 static int g_xattn_variant = 0;
+extern int g_xattn_poly;
 extern "C" int a3d_set_option(const char* name, int value) {
+    if (name && strcmp(name, "xattn_poly") == 0) {
+        A3D_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4, "a3d_set_option: xattn_poly must be 0, 2, 3 or 4");
+        g_xattn_poly = value;
+        return A3D_OK;
+    }
     if (name && strcmp(name, "xattn_variant") == 0) {
         A3D_REQUIRE(value >= 0 && value <= 3, "a3d_set_option: xattn_variant must be 0..3");
         g_xattn_variant = value;

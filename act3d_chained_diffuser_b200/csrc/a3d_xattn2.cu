@@ -60,6 +60,24 @@ __device__ __forceinline__ void mma_16816_c(float (&d)[4], const uint32_t (&a)[4
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative
+// error 7.5e-5 -- well below the fp16 rounding of P): used for a fraction of the scores so that the MUFU
+// unit (16 results / clk / SM, the measured ceiling of this kernel) and the FMA pipe work in parallel.
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = __fadd_rn(x, 12582912.0f);               // 1.5 * 2^23: rint(x) lands in the low mantissa bits
+    const float f = __fsub_rn(x, __fsub_rn(t, 12582912.0f));  // x - rint(x) in [-0.5, 0.5]
+    float p = fmaf(0.055170901f, f, 0.24260952f);
+    p = fmaf(p, f, 0.69326097f);
+    p = fmaf(p, f, 0.99992818f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+template <int PM, int IDX>
+__device__ __forceinline__ float exp2_sel(float x) {
+    if (PM & (1 << IDX)) return exp2_poly(x);
+    return exp2_fast(x);
+}
+
 // 16 x 64 (this warp's rows) times a fragment-ordered [64][64] weight; the A operand is taken straight from
 // accumulator-layout registers: k step ks <- column tiles 2ks, 2ks+1 (split into fp16 hi/lo on the fly).
 __device__ __forceinline__ void gemm_reg(const float (&src)[8][4], const uint4* __restrict__ wfrag, int lane,
@@ -131,6 +149,8 @@ __device__ __forceinline__ void layernorm_frag(float (&x)[8][4], int q4, const f
     }
 }
 
+// PM: bit i set -> the i-th of the 8 scores a thread exponentiates per 16-key step uses exp2_poly
+template <int PM>
 __global__ void __launch_bounds__(256, 2) xattn2_kernel(const Xa2Args a) {
     using C = Xa2;
     constexpr int E = C::E, H = C::H;
@@ -325,10 +345,10 @@ __global__ void __launch_bounds__(256, 2) xattn2_kernel(const Xa2Args a) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     uint32_t pa[4];
-                    pa[0] = pack_h2(exp2_fast(s[2 * kk][0]), exp2_fast(s[2 * kk][1]));
-                    pa[1] = pack_h2(exp2_fast(s[2 * kk][2]), exp2_fast(s[2 * kk][3]));
-                    pa[2] = pack_h2(exp2_fast(s[2 * kk + 1][0]), exp2_fast(s[2 * kk + 1][1]));
-                    pa[3] = pack_h2(exp2_fast(s[2 * kk + 1][2]), exp2_fast(s[2 * kk + 1][3]));
+                    pa[0] = pack_h2(exp2_sel<PM, 0>(s[2 * kk][0]), exp2_sel<PM, 1>(s[2 * kk][1]));
+                    pa[1] = pack_h2(exp2_sel<PM, 2>(s[2 * kk][2]), exp2_sel<PM, 3>(s[2 * kk][3]));
+                    pa[2] = pack_h2(exp2_sel<PM, 4>(s[2 * kk + 1][0]), exp2_sel<PM, 5>(s[2 * kk + 1][1]));
+                    pa[3] = pack_h2(exp2_sel<PM, 6>(s[2 * kk + 1][2]), exp2_sel<PM, 7>(s[2 * kk + 1][3]));
                     const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
                     const int chunk = lane >> 4;
                     uint32_t r[4];
@@ -457,6 +477,8 @@ __global__ void __launch_bounds__(256, 2) xattn2_kernel(const Xa2Args a) {
 
 using namespace a3d;
 
+int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
+
 extern "C" size_t a3d_xattn_layer_words(int embed, int ffn) {
     return (embed == 60 && ffn == 60) ? (size_t)Xa2::LAYER_W * 4 : 0;   // 32-bit words of fragment weights per layer
 }
@@ -498,16 +520,27 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.qvec = qvec;
     a.nqv = nqv;
     a.logits = logits;
-    static bool once = false;
-    if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(xattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Xa2::SMEM);
-        if (e != cudaSuccess) {
-            set_error("a3d_xattn_stack: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return A3D_ECUDA;
-        }
-        once = true;
-    }
     dim3 grid((nq + Xa2::ROWS - 1) / Xa2::ROWS, batch);
-    xattn2_kernel<<<grid, 256, Xa2::SMEM, (cudaStream_t)stream>>>(a);
+#define A3D_XA2(PM)                                                                                                   \
+    do {                                                                                                               \
+        static bool once = false;                                                                                      \
+        if (!once) {                                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(xattn2_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                                 (int)Xa2::SMEM);                                                      \
+            if (e != cudaSuccess) {                                                                                    \
+                set_error("a3d_xattn_stack: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                       \
+                return A3D_ECUDA;                                                                                      \
+            }                                                                                                          \
+            once = true;                                                                                               \
+        }                                                                                                              \
+        xattn2_kernel<PM><<<grid, 256, Xa2::SMEM, (cudaStream_t)stream>>>(a);                                          \
+    } while (0)
+    switch (g_xattn_poly) {   // fraction of exponentials evaluated on the FMA pipe: 0, 2/8, 3/8, 4/8
+        case 2: A3D_XA2(0x22); break;
+        case 3: A3D_XA2(0x2A); break;
+        case 4: A3D_XA2(0xAA); break;
+        default: A3D_XA2(0x00); break;
+    }
+#undef A3D_XA2
     return check_launch("a3d_xattn_stack");
 }

@@ -235,12 +235,13 @@ def run_ours(args, rank, world, device):
     if kern_ms:
         avg = sum(kern_ms) / len(kern_ms)
         ach = flops_launch / (avg * 1e-3) / 1e12
-        roof = {"kernel": "xattn_stack_kernel (ghost)", "bound": "tensor", "achieved": round(ach, 2),
+        roof = {"kernel": "xattn2_kernel (fused ghost-point cross-attention stack)", "bound": "tensor", "achieved": round(ach, 2),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
                 "traffic": None, "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
                 "share_of_step": round(sum(kern_ms) / ms_res, 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
-                "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample; the kernel is exp(MUFU)-bound at head_dim 15"}
+                "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample; at head_dim 15 the kernel is bound by the MUFU "
+                        "exp unit (16/clk/SM): ncu XU pipe 76 %, HMMA 40 % (profiles/r1_xattn_ghost_v2_ncu.txt)"}
 
     kf = w["batch"] * world * args.steps
     line = {
