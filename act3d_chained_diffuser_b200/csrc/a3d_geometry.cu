@@ -264,6 +264,35 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(const float* __restr
     }
 }
 
+// =================================================================== mask logits
+// logits[j][b][n] = <qvec[j][b], feat[b][n]>   (act3d.py:493-494).  One thread per ghost point, both query
+// vectors at once; HBM-bound: reads the (B, Ng, E) feature tensor once (16-byte loads), writes nqv floats/point.
+template <int E>
+__global__ void __launch_bounds__(256) mask_logits_kernel(const float* __restrict__ feat, const float* __restrict__ qvec,
+                                                          int batch, int ng, int nqv, float* __restrict__ logits) {
+    __shared__ float q[4][E];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < nqv * E; i += blockDim.x) q[i / E][i % E] = qvec[((size_t)(i / E) * batch + b) * E + i % E];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ng) return;
+    const float4* row = reinterpret_cast<const float4*>(feat + ((size_t)b * ng + n) * E);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) {
+        const float4 v = __ldg(row + c4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nqv) {
+                acc[j] = fmaf(v.x, q[j][4 * c4], acc[j]);
+                acc[j] = fmaf(v.y, q[j][4 * c4 + 1], acc[j]);
+                acc[j] = fmaf(v.z, q[j][4 * c4 + 2], acc[j]);
+                acc[j] = fmaf(v.w, q[j][4 * c4 + 3], acc[j]);
+            }
+    }
+    for (int j = 0; j < nqv; ++j) logits[((size_t)j * batch + b) * ng + n] = acc[j];
+}
+
 // =================================================================== top ghost pick
 __global__ void __launch_bounds__(1024) argmax_pick_kernel(const float* __restrict__ logits, const float* __restrict__ ghost,
                                                            int ng, int32_t* __restrict__ top_idx, float* __restrict__ pos) {
@@ -438,6 +467,17 @@ extern "C" int a3d_gather_tokens(const float* feat, const float* pcd, const int3
     else
         A3D_REQUIRE(false, "a3d_gather_tokens: embedding_dim %d not supported (60 or 120)", embed);
     return check_launch("a3d_gather_tokens");
+}
+
+extern "C" int a3d_mask_logits(const float* feat, const float* qvec, int batch, int ng, int embed, int nqv,
+                               float* logits, void* stream) {
+    A3D_REQUIRE(feat && qvec && logits && batch > 0 && ng > 0, "a3d_mask_logits: bad arguments");
+    A3D_REQUIRE(embed == 60, "a3d_mask_logits: built for embedding_dim 60 (got %d)", embed);
+    A3D_REQUIRE(nqv >= 1 && nqv <= 4, "a3d_mask_logits: 1..4 query vectors supported (got %d)", nqv);
+    A3D_REQUIRE(((uintptr_t)feat & 15) == 0, "a3d_mask_logits: features must be 16-byte aligned");
+    dim3 grid((ng + 255) / 256, batch);
+    mask_logits_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, qvec, batch, ng, nqv, logits);
+    return check_launch("a3d_mask_logits");
 }
 
 extern "C" int a3d_argmax_pick(const float* logits, const float* ghost, int batch, int ng, int32_t* top_idx,

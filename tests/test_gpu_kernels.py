@@ -302,3 +302,12 @@ def test_ghost_sampler_distribution(lib):
     assert (ball >= lo - 1e-6).all() and (ball <= hi + 1e-6).all()
     # uniform in the ball: radius^3 is uniform on [0,1] for the unclipped anchor
     assert abs(((d[0] / r) ** 3).mean() - 0.5) < 0.01
+
+
+def test_mask_logits_kernel(lib):
+    feat = synth.normal("ml.f", (3, 1000, 60))
+    qv = synth.normal("ml.q", (2, 3, 60))
+    out = torch.empty(2, 3, 1000).cuda()
+    lib.mask_logits(dev(feat), dev(qv), out)
+    want = torch.einsum("jbc,bnc->jbn", qv.double(), feat.double()).float()
+    assert (out.cpu() - want).abs().max() <= 2e-5 * want.abs().max()
