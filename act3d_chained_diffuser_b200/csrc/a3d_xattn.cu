@@ -416,7 +416,13 @@ using namespace a3d;
 // numerics variant of the attention core: bit0 = fp32 exp, bit1 = split-Q (see kernel comment)
 static int g_xattn_variant = 0;
 extern int g_xattn_poly;
+extern int g_xattn_core;
 extern "C" int a3d_set_option(const char* name, int value) {
+    if (name && strcmp(name, "xattn_core") == 0) {
+        A3D_REQUIRE(value == 2 || value == 3, "a3d_set_option: xattn_core must be 2 (mma.sync) or 3 (tcgen05)");
+        g_xattn_core = value;
+        return A3D_OK;
+    }
     if (name && strcmp(name, "xattn_poly") == 0) {
         A3D_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4, "a3d_set_option: xattn_poly must be 0, 2, 3 or 4");
         g_xattn_poly = value;

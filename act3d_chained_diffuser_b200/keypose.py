@@ -138,7 +138,7 @@ class Act3D(nn.Module):
                                 total_timesteps, n, self._sampler_seed, self._sampler_calls, device)
 
     # ------------------------------------------------------------------ visual trunk
-    def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras):
+    def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras, staged=None):
         """backbone + FPN (PyTorch) and the point pyramid (kernel).  Unlike act3d.py:359-392 no
         rotary table is built here: angles are evaluated inside the K/V kernel for the tokens that
         are actually attended to."""
@@ -150,6 +150,9 @@ class Act3D(nn.Module):
         else:
             feats = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
                                      needed=self.feature_map_pyramid[:self.num_sampling_level])
+        if staged is not None:      # point clouds were uploaded on the copy stream while the backbone ran
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            visible_pcd = staged[0]
         pcd = visible_pcd.reshape(b * num_cameras, *visible_pcd.shape[2:]).contiguous().float()
         feats_pyr, pcd_pyr, cache = [], [], {}
         for i in range(self.num_sampling_level):
@@ -168,8 +171,20 @@ class Act3D(nn.Module):
         instruction (B, 53, 512); curr_gripper (B, 8); gt_action (B, 8) or None.
         Returns the reference's output dict (act3d.py:340-357).
         """
+        staged = None
         if not visible_rgb.is_cuda:
-            raise RuntimeError("Act3D (B200) runs on CUDA tensors only: there is no CPU fallback path")
+            # Host inputs (e.g. straight from a DataLoader with pin_memory): upload here, images first so that the
+            # backbone starts while the point clouds / instruction are still crossing PCIe on the copy stream.
+            # The computation itself has no CPU path.
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("Act3D (B200) runs on a CUDA device only: there is no CPU fallback path")
+            visible_rgb = visible_rgb.to(dev, non_blocking=True)
+            copy = self._side_stream
+            copy.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy):
+                staged = [t.to(dev, non_blocking=True) if t is not None else None
+                          for t in (visible_pcd, instruction, curr_gripper, gt_action)]
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
                 "the fused kernels are forward-only in this round (backward kernels: DESIGN.md 'next'); "
@@ -181,7 +196,11 @@ class Act3D(nn.Module):
         gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None
         grip_xyz = curr_gripper[:, :3].float()
 
-        feats_pyr, pcd_pyr = self._compute_visual_features(visible_rgb, visible_pcd, ncam)
+        feats_pyr, pcd_pyr = self._compute_visual_features(visible_rgb, visible_pcd, ncam, staged)
+        if staged is not None:
+            visible_pcd, instruction, curr_gripper, gt_action = staged
+            gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None
+            grip_xyz = curr_gripper[:, :3].float()
 
         if self.use_instruction:
             instr = F.linear(instruction.float(), self.instruction_encoder.weight, self.instruction_encoder.bias)

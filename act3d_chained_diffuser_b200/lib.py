@@ -70,6 +70,10 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    core = os.environ.get("A3D_XATTN_CORE")          # profiling / A-B switch: 2 = mma.sync core, 3 = tcgen05 core
+    if core:
+        if lib.a3d_set_option(b"xattn_core", int(core)) != 0:
+            raise A3DError(f"A3D_XATTN_CORE={core}: " + lib.a3d_last_error().decode())
     return lib
 
 

@@ -186,9 +186,8 @@ def run_ours(args, rank, world, device):
 
     def step_e2e():
         with torch.no_grad():
-            ins = [t.to(device, non_blocking=True) for t in host]
-            out = model(*ins)
-            return torch.cat([out["position"], out["rotation"].reshape(len(ins[0]), -1), out["gripper"]], -1).cpu()
+            out = model(*host)          # pinned host tensors: the module uploads them (images first, rest overlapped)
+            return torch.cat([out["position"], out["rotation"].reshape(len(host[0]), -1), out["gripper"]], -1).cpu()
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):

@@ -69,24 +69,24 @@ def main():
                                            rope3d_table(q_xyz.double(), E), rope3d_table(c_xyz.double(), E))[-1].transpose(0, 1)
         lg64 = torch.einsum("jbc,bnc->jbn", qvec.double(), want64)
         rel = lambda a, r: ((a.double() - r).norm() / r.norm()).item()
-        for poly in (0, 4):
-            lib.set_option("xattn_poly", poly)
+        for core in (2, 3):
+            lib.set_option("xattn_core", core)
             feat, logits, _ = run(b, nq, nk, t)
-            print(json.dumps({"case": tag, "poly_of_8": poly, "feat_rel_l2": rel(feat[0], want64), "logit_rel_l2": rel(logits, lg64)}))
-        lib.set_option("xattn_poly", 0)
+            print(json.dumps({"case": tag, "core": core, "feat_rel_l2": rel(feat[0], want64), "logit_rel_l2": rel(logits, lg64)}))
+        lib.set_option("xattn_core", 2)
         feat, logits, _ = run(b, nq, nk, t)
         print(json.dumps({"case": tag, "feat_rel_l2": rel(feat[0], want64), "logit_rel_l2": rel(logits, lg64),
                           "feat_maxabs_over_max": ((feat[0].double() - want64).abs().max() / want64.abs().max()).item()}))
     b, nq, nk = 16, 16384, 4150
     t = setup(b, nq, nk, 1.0)
     flops = 4.0 * nq * nk * E * 2 * b
-    for poly in (0, 2, 3, 4):
-        lib.set_option("xattn_poly", poly)
+    for core in (2, 3):
+        lib.set_option("xattn_core", core)
         run(b, nq, nk, t, iters=2)
         _, _, ms = run(b, nq, nk, t, iters=5)
-        print(json.dumps({"shape": [b, nq, nk], "poly_of_8": poly, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
+        print(json.dumps({"shape": [b, nq, nk], "core": core, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
                           "score_elems_per_clk_per_sm@1.965GHz": b * nq * nk * H * 2 / (ms * 1e-3) / 148 / 1.965e9}))
-    lib.set_option("xattn_poly", 0)
+    lib.set_option("xattn_core", 2)
 
 
 if __name__ == "__main__":
