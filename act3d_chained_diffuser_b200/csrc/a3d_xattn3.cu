@@ -13,6 +13,11 @@
 // Two passes over the keys per layer: pass 1 finds the exact row maxima (S only), pass 2 recomputes S, forms
 // P = 2^(S - m) and accumulates O in tensor memory -- no running-max correction of O is ever needed, and the
 // extra QK^T pass is free on a tensor pipe that the MUFU-bound softmax leaves mostly idle.
+// Status (round 1): parity-green on every kernel / end-to-end test, 3.6 ms per C2 launch vs 2.8 ms for the mma.sync core,
+// so it is opt-in (a3d_set_option("xattn_core", 3) / A3D_XATTN_CORE=3).  ncu (profiles/r1_xattn_ghost_v3_ncu.txt): only
+// ~10 resident warps/SM, 21 % of stall samples in mbarrier spin loops, XU 58 %: the single issuing lane (several
+// ~100-cycle try_waits + 5 UMMAs per 8192-score unit) and 4 row warps per CTA are the limiters, not TMEM bandwidth
+// (21 %).  Next: single pass with conditional O correction, S and PV issue on separate warps, 8 row warps per CTA.
 // Tensor-memory map (256 columns): O = 4 heads x 16 columns at 0..63 (slot 15 = softmax denominator),
 // S/P buffer i (i = unit & 1) at 64 + 64 i (P overwrites the first 32 columns of S as packed fp16 pairs).
 #include "a3d_xattn_common.cuh"
@@ -355,18 +360,22 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
                     tmem_ld32(lane_addr + C::S_COL + 64 * i + 32, r1);
                     tmem_wait_ld();
                     const float mh = m[h];
+                    if (valid == kTileKeys) {      // full tile: no per-element masking code at all
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        float e0 = exp2_fast(__uint_as_float(r0[2 * c]) - mh), e1 = exp2_fast(__uint_as_float(r0[2 * c + 1]) - mh);
-                        float e2 = exp2_fast(__uint_as_float(r1[2 * c]) - mh), e3 = exp2_fast(__uint_as_float(r1[2 * c + 1]) - mh);
-                        if (valid != kTileKeys) {
-                            if (2 * c >= valid) e0 = 0.f;
-                            if (2 * c + 1 >= valid) e1 = 0.f;
-                            if (2 * c + 32 >= valid) e2 = 0.f;
-                            if (2 * c + 33 >= valid) e3 = 0.f;
+                        for (int c = 0; c < 16; ++c) {
+                            p[c] = pack_h2(exp2_fast(__uint_as_float(r0[2 * c]) - mh), exp2_fast(__uint_as_float(r0[2 * c + 1]) - mh));
+                            p[16 + c] = pack_h2(exp2_fast(__uint_as_float(r1[2 * c]) - mh), exp2_fast(__uint_as_float(r1[2 * c + 1]) - mh));
                         }
-                        p[c] = pack_h2(e0, e1);
-                        p[16 + c] = pack_h2(e2, e3);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float e0 = (2 * c < valid) ? exp2_fast(__uint_as_float(r0[2 * c]) - mh) : 0.f;
+                            const float e1 = (2 * c + 1 < valid) ? exp2_fast(__uint_as_float(r0[2 * c + 1]) - mh) : 0.f;
+                            const float e2 = (2 * c + 32 < valid) ? exp2_fast(__uint_as_float(r1[2 * c]) - mh) : 0.f;
+                            const float e3 = (2 * c + 33 < valid) ? exp2_fast(__uint_as_float(r1[2 * c + 1]) - mh) : 0.f;
+                            p[c] = pack_h2(e0, e1);
+                            p[16 + c] = pack_h2(e2, e3);
+                        }
                     }
                     tmem_st32(lane_addr + C::S_COL + 64 * i, p);
                     tmem_wait_st();
