@@ -143,3 +143,20 @@ def test_side_stream_query_overlap_is_equivalent():
     la, lb = a["ghost_pcd_masks_pyramid"][0], b["ghost_pcd_masks_pyramid"][0]
     for j in range(2):
         assert (la[j] - lb[j]).abs().max() <= 1e-4 * lb[j].abs().max()
+
+
+def test_host_inputs_are_uploaded_by_the_module():
+    """Pinned host tensors (DataLoader style) give the same result as device tensors."""
+    m, kw = build(False, num_ghost_points_val=3 * 500)
+    m = m.cuda()
+    host = {k: v.pin_memory() for k, v in cases.act3d_inputs(batch=2, ncam=1, seed=11).items()}
+    outs = []
+    for on_device in (True, False):
+        m.seed_ghost_sampler(5)
+        args = [host[k].cuda() if on_device else host[k] for k in ("visible_rgb", "visible_pcd", "instruction", "curr_gripper")]
+        with torch.no_grad():
+            outs.append(m(*args))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0]["position"], outs[1]["position"])
+    assert torch.equal(outs[0]["ghost_pcd_masks_pyramid"][2][1], outs[1]["ghost_pcd_masks_pyramid"][2][1])
+    assert outs[1]["position"].is_cuda
