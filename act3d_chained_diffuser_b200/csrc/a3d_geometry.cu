@@ -231,6 +231,27 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
 // A block moves 32 tokens x E channels through a padded shared tile so that the scattered
 // reads are issued token-major (one 32 B sector per (token, channel)) and the writes are
 // fully coalesced rows of E floats.
+// channels-last variant: feat[(b*ncam + cam)][pix][c] -- a token is one contiguous E-float row, so the gather is
+// a plain coalesced row copy (this is the layout cuDNN's NHWC kernels leave the FPN output in).
+template <int E>
+__global__ void __launch_bounds__(256) gather_tokens_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ pcd,
+                                                                 const int32_t* __restrict__ idx, int ncam, int hw, int k,
+                                                                 float* __restrict__ tok, float* __restrict__ pos,
+                                                                 int tok_rows) {
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int rr = wid; rr < 32; rr += 8) {
+        const int r = r0 + rr;
+        if (r >= k) break;
+        const int s = idx ? __ldg(idx + (long)b * k + r) : r;
+        const float* src = feat + ((long)b * ncam * hw + s) * E;
+        float* dst = tok + ((long)b * tok_rows + r) * E;
+        for (int c = lane; c < E; c += 32) dst[c] = __ldg(src + c);
+        if (lane < 3) pos[((long)b * tok_rows + r) * 3 + lane] = __ldg(pcd + ((long)b * ncam * hw + s) * 3 + lane);
+    }
+}
+
 template <int E>
 __global__ void __launch_bounds__(256) gather_tokens_kernel(const float* __restrict__ feat, const float* __restrict__ pcd,
                                                             const int32_t* __restrict__ idx, int ncam, int hw, int k,
@@ -455,11 +476,21 @@ extern "C" int a3d_traj_topk(const float* traj, int traj_len, const float* pts, 
 }
 
 extern "C" int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, int batch, int ncam,
-                                 int embed, int hw, int k, float* tok, float* pos, int tok_rows, void* stream) {
+                                 int embed, int hw, int k, float* tok, float* pos, int tok_rows, int channels_last,
+                                 void* stream) {
     A3D_REQUIRE(feat && pcd && tok && pos, "a3d_gather_tokens: null pointer");
     A3D_REQUIRE(batch > 0 && ncam > 0 && hw > 0 && k > 0 && k <= tok_rows, "a3d_gather_tokens: bad sizes (k=%d rows=%d)", k, tok_rows);
     A3D_REQUIRE(idx || k == ncam * hw, "a3d_gather_tokens: identity gather needs k == ncam*hw");
     dim3 grid((k + 31) / 32, batch);
+    if (channels_last) {
+        if (embed == 60)
+            gather_tokens_nhwc_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+        else if (embed == 120)
+            gather_tokens_nhwc_kernel<120><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+        else
+            A3D_REQUIRE(false, "a3d_gather_tokens: embedding_dim %d not supported (60 or 120)", embed);
+        return check_launch("a3d_gather_tokens");
+    }
     if (embed == 60)
         gather_tokens_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
     else if (embed == 120)

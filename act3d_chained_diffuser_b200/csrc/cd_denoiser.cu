@@ -20,6 +20,7 @@
 namespace a3d {
 namespace cd {
 
+constexpr int kCrossSplits = 4;            // key tiles of one (sample, head) are split over this many cd_cross CTAs
 constexpr int THREADS = 512;               // 16 warps: 4 m tiles x 4 n parts
 constexpr int LPR = THREADS / ROWS;        // lanes per row in the row-wise passes
 constexpr int NTW = 4;                     // n tiles per warp in the CTA GEMM
@@ -128,6 +129,45 @@ __device__ __forceinline__ void planes_from_tile(const float* __restrict__ src, 
         split_h2(v0, v1, h, l);
         *reinterpret_cast<uint32_t*>(hi + r * PITCH + c) = h;
         *reinterpret_cast<uint32_t*>(lo + r * PITCH + c) = l;
+    }
+}
+// planes of the cross-attention output: merge the kCrossSplits unnormalised partials of every (row, head)
+//   att[r][15h + d] = sum_s O_s[d] 2^(m_s - M) / sum_s l_s 2^(m_s - M),  M = max_s m_s
+__device__ __forceinline__ void planes_from_partials(const float* __restrict__ part_b, __half* __restrict__ hi,
+                                                     __half* __restrict__ lo) {
+    for (int i = threadIdx.x; i < ROWS * H; i += blockDim.x) {
+        const int r = i & 63, h = i >> 6;
+        float m[kCrossSplits], big = -INFINITY;
+#pragma unroll
+        for (int sp = 0; sp < kCrossSplits; ++sp) {
+            m[sp] = __ldg(part_b + (((size_t)sp * H + h) * ROWS + r) * 17 + 16);
+            big = fmaxf(big, m[sp]);
+        }
+        float acc[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < kCrossSplits; ++sp) {
+            const float wgt = (m[sp] == -INFINITY) ? 0.f : exp2f(m[sp] - big);
+            const float* src = part_b + (((size_t)sp * H + h) * ROWS + r) * 17;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[d] = fmaf(wgt, __ldg(src + d), acc[d]);
+        }
+        const float inv = 1.0f / acc[15];
+        // columns 15h .. 15h+14 of row r (pairs may straddle the 4-byte packing: write element-wise)
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            __half vh, vl;
+            split_h(acc[d] * inv, vh, vl);
+            hi[r * PITCH + h * HD + d] = vh;
+            lo[r * PITCH + h * HD + d] = vl;
+        }
+    }
+    // zero the padded columns 120..127
+    for (int i = threadIdx.x; i < ROWS * (EP - E); i += blockDim.x) {
+        const int r = i / (EP - E), c = E + i % (EP - E);
+        hi[r * PITCH + c] = __float2half_rn(0.f);
+        lo[r * PITCH + c] = __float2half_rn(0.f);
     }
 }
 // planes from a row-major global matrix [nrows][ld] (zero padded to 64 x 128)
@@ -343,7 +383,7 @@ struct StepArgs {
     int n_instr;
     // ---- post kernel
     const float* x_in;              // [B][64][E]
-    const float* att;               // [B][64][E] cross-attention output (heads concatenated)
+    const float* att;               // [B][kCrossSplits][H][64][17] partial cross-attention outputs of cd_cross
     const uint4* layer_w;           // AdaW of this layer
     const float* layer_v;           // AdaV
     int ada_layer;                  // index of this layer in the adaLN table
@@ -413,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) cd_post_kernel(const StepArgs a) {
     prefetch_w(s, lw + AdaW::C_WO);
     init_common(s, traj_b, a.nrows, 9, a.mask ? a.mask + (size_t)b * a.nrows : nullptr);
     load_tile(s.xs, a.x_in + (size_t)b * ROWS * E, ROWS, E);
-    planes_from_global(a.att + (size_t)b * ROWS * E, ROWS, E, E, s.ah, s.al);
+    planes_from_partials(a.att + (size_t)b * kCrossSplits * H * ROWS * 17, s.ah, s.al);
     __syncthreads();
     // ---- cross-attention epilogue: x = LN_12(x + att Wo^T + bo)          (layers.py:146-147)
     linear_tile(w, s, s.ah, s.al, lw + AdaW::C_WO, lv + AdaV::C_BO, s.t1);
@@ -512,7 +552,7 @@ struct CrossArgs {
     const __half* q;               // [B][H][64][16]
     const unsigned char* kv;       // tile images of this layer: [B][ntiles][2][H][64][16] fp16
     int nk, ntiles, batch;
-    float* att;                    // [B][64][E]
+    float* part;                   // [B][kCrossSplits][H][64][17]: unnormalised O (15) | pad | denominator l | row max m (log2 units)
 };
 
 __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
@@ -534,7 +574,12 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
     for (int i = tid; i < ROWS * 16; i += 128) qs[(i >> 4) * 24 + (i & 15)] = qg[i];
     __syncthreads();
     const size_t tile_bytes = (size_t)2 * H * 2048;
-    const unsigned char* kv_b = a.kv + (size_t)b * a.ntiles * tile_bytes;
+    // this CTA's slice of the key tiles
+    const int split = blockIdx.z;
+    const int per = (a.ntiles + kCrossSplits - 1) / kCrossSplits;
+    const int t_begin = min(split * per, a.ntiles), t_end = min(t_begin + per, a.ntiles);
+    const int my_tiles = t_end - t_begin;
+    const unsigned char* kv_b = a.kv + ((size_t)b * a.ntiles + t_begin) * tile_bytes;
     auto issue = [&](int t) {
         const int s = t % STAGES;
         if (t >= STAGES) mbar_wait(bar_empty + s, ((t / STAGES) - 1) & 1);
@@ -544,7 +589,7 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
         bulk_g2s(kvs[s] + 2048, src + (size_t)H * 2048 + (size_t)h * 2048, 2048, bar_full + s);
     };
     if (tid == 0)
-        for (int t = 0; t < STAGES - 1 && t < a.ntiles; ++t) issue(t);
+        for (int t = 0; t < STAGES - 1 && t < my_tiles; ++t) issue(t);
 
     uint32_t qf[4];
     {
@@ -554,9 +599,9 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
     float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float m0 = -INFINITY, m1 = -INFINITY;
     const bool tail_mask = (a.nk % kTileKeys) != 0;
-    for (int t = 0; t < a.ntiles; ++t) {
+    for (int t = 0; t < my_tiles; ++t) {
         const int stage = t % STAGES;
-        if (tid == 0 && t + STAGES - 1 < a.ntiles) issue(t + STAGES - 1);
+        if (tid == 0 && t + STAGES - 1 < my_tiles) issue(t + STAGES - 1);
         mbar_wait(bar_full + stage, (t / STAGES) & 1);
         const uint32_t kbase = smem_u32(kvs[stage]), vbase = kbase + 2048;
         float s[8][4];
@@ -573,12 +618,12 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
             mma_16816(s[2 * kk], qf, r[0], r[1]);
             mma_16816(s[2 * kk + 1], qf, r[2], r[3]);
         }
-        if (tail_mask && t == a.ntiles - 1) {
+        if (tail_mask && t_begin + t == a.ntiles - 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (t * kTileKeys + 8 * j + 2 * q4 + (e & 1) >= a.nk) s[j][e] = -INFINITY;
+                    if ((t_begin + t) * kTileKeys + 8 * j + 2 * q4 + (e & 1) >= a.nk) s[j][e] = -INFINITY;
         }
         float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
@@ -618,18 +663,21 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + stage);
     }
-    const float l0 = __shfl_sync(0xffffffffu, o[1][1], (lane & ~3) | 3);
-    const float l1 = __shfl_sync(0xffffffffu, o[1][3], (lane & ~3) | 3);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    float* out = a.att + (size_t)b * ROWS * E;
+    // unnormalised partial: columns 0..14 = O, 15 = denominator (rode in V's slot 15), 16 = row max (-inf if this
+    // slice was empty); cd_post merges the kCrossSplits partials of a row
+    float* out = a.part + (((size_t)b * kCrossSplits + split) * H + h) * ROWS * 17;
 #pragma unroll
     for (int n = 0; n < 2; ++n)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int d = 8 * n + 2 * q4 + (e & 1);
             const int row = warp * 16 + g + 8 * (e >> 1);
-            if (d < HD) out[(size_t)row * E + h * HD + d] = o[n][e] * ((e >> 1) ? i1 : i0);
+            out[(size_t)row * 17 + d] = o[n][e];
         }
+    if (q4 == 0) {
+        out[(size_t)(warp * 16 + g) * 17 + 16] = m0;
+        out[(size_t)(warp * 16 + g + 8) * 17 + 16] = m1;
+    }
 }
 
 }  // namespace cd
@@ -717,12 +765,14 @@ extern "C" int cd_step_begin(const float* traj, int batch, int length, const flo
     return check_launch("cd_step_begin");
 }
 
+extern "C" size_t cd_cross_part_floats(int batch) { return (size_t)batch * kCrossSplits * H * ROWS * 17; }
+
 extern "C" int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float* att, void* stream) {
     A3D_REQUIRE(q && kv && att, "cd_cross: null pointer");
     A3D_REQUIRE(heads == H && batch > 0 && nk > 0, "cd_cross: built for 8 heads (got %d)", heads);
     A3D_REQUIRE(((uintptr_t)kv & 15) == 0, "cd_cross: K/V cache must be 16-byte aligned");
     CrossArgs a{(const __half*)q, (const unsigned char*)kv, nk, (nk + kTileKeys - 1) / kTileKeys, batch, att};
-    dim3 grid(H, batch);
+    dim3 grid(H, batch, kCrossSplits);
     cd_cross_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     return check_launch("cd_cross");
 }

@@ -159,8 +159,8 @@ class Act3D(nn.Module):
             f = self.downscaling_factor_pyramid[i]
             if f not in cache:
                 cache[f] = lib.pcd_pyramid(pcd, f).view(b, -1, 3)
-            fm = feats[self.feature_map_pyramid[i]].contiguous().float()
-            feats_pyr.append(fm.view(b, num_cameras, *fm.shape[1:]))
+            fm = feats[self.feature_map_pyramid[i]].float()       # NCHW or channels-last: the gather reads either in place
+            feats_pyr.append(fm.unflatten(0, (b, num_cameras)))
             pcd_pyr.append(cache[f])
         return feats_pyr, pcd_pyr
 
@@ -227,7 +227,7 @@ class Act3D(nn.Module):
             # ---- context tokens: coarse grid (level 0) or the 1024*ncam nearest fine points
             tok = torch.empty(b, rows, e, device=dev)
             pos = torch.empty(b, rows, 3, device=dev)
-            fm = feats_pyr[i].reshape(b * ncam, e, -1, feats_pyr[i].shape[-1])
+            fm = feats_pyr[i].flatten(0, 1)
             if i == 0:
                 idx = None
             else:

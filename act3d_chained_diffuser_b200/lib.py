@@ -22,7 +22,7 @@ EXPORTS = {
     "a3d_local_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_traj_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p, c_int, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "a3d_kv_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "a3d_ctx_kv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            ctypes.POINTER(c_int), c_int, c_void_p, c_void_p]),
@@ -41,6 +41,7 @@ EXPORTS = {
     "cd_step_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                               c_void_p, c_void_p]),
+    "cd_cross_part_floats": (c_size_t, [c_int]),
     "cd_cross": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cd_post": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -149,11 +150,19 @@ def traj_topk(traj, pts, k, want_dist=False):
 
 
 def gather_tokens(feat, pcd, idx, batch, ncam, tok, pos):
-    """feat (B*ncam, E, h, w), pcd (B, ncam*h*w, 3), idx (B,K) int32 or None -> rows [0,K) of tok/pos."""
+    """feat (B*ncam, E, h, w) -- NCHW-contiguous or channels-last (NHWC storage, read in place) --,
+    pcd (B, ncam*h*w, 3), idx (B,K) int32 or None -> rows [0,K) of tok/pos."""
     e, hw = feat.shape[1], feat.shape[2] * feat.shape[3]
     k = idx.shape[1] if idx is not None else ncam * hw
-    _check(load().a3d_gather_tokens(_ptr(_f32(feat)), _ptr(_f32(pcd)), _ptr(idx), batch, ncam, e, hw, k,
-                                    _ptr(tok), _ptr(pos), tok.shape[1], _stream()), "a3d_gather_tokens")
+    assert feat.is_cuda and feat.dtype == torch.float32
+    if feat.is_contiguous():
+        nhwc = 0
+    elif feat.is_contiguous(memory_format=torch.channels_last):
+        nhwc = 1
+    else:
+        feat, nhwc = feat.contiguous(), 0
+    _check(load().a3d_gather_tokens(feat.data_ptr(), _ptr(_f32(pcd)), _ptr(idx), batch, ncam, e, hw, k,
+                                    _ptr(tok), _ptr(pos), tok.shape[1], nhwc, _stream()), "a3d_gather_tokens")
     return k
 
 
@@ -247,6 +256,10 @@ def cd_step_begin(traj, wp_pe, t_idx, ada, ada_layers, enc1, enc2, enc2_b, lang_
                                 _raw(enc1), _raw(enc2), _raw(enc2_b), _raw(lang_w), _raw(lang_v), _ptr(lang_k),
                                 _ptr(lang_vv), n_instr, _ptr(x_out), _raw(next_wq), _raw(next_bq), next_ada_layer,
                                 _ptr(q_out), _stream()), "cd_step_begin")
+
+
+def cd_cross_part_floats(batch):
+    return load().cd_cross_part_floats(batch)
 
 
 def cd_cross(q, kv, kv_offset_bytes, batch, nk, att):

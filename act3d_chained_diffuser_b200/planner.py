@@ -154,7 +154,7 @@ class DiffusionHead(nn.Module):
             fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
         else:
             fpn = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=("res3",))
-        fm = fpn["res3"].contiguous().float()
+        fm = fpn["res3"].float()                                  # NCHW or channels-last: the gather reads either in place
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
         nctx = pts.shape[1]
@@ -239,7 +239,8 @@ class DiffusionHead(nn.Module):
         if trajectory_mask is not None and bool(trajectory_mask.any()):
             mask_u8 = trajectory_mask.to(device=device, dtype=torch.uint8).contiguous()
         return dict(
-            x=torch.empty(nl + 1, b, 64, e, device=device), att=torch.empty(b, 64, e, device=device),
+            x=torch.empty(nl + 1, b, 64, e, device=device),
+            att=torch.empty(lib.cd_cross_part_floats(b), device=device),      # partial cross-attention results (cd_cross -> cd_post)
             q=torch.empty(b, 8, 64, 16, device=device, dtype=torch.float16),
             pos_upd=torch.empty(b, length, 3, device=device), rot_out=torch.empty(b, length, 6, device=device),
             wp_pe=sinusoidal(torch.arange(length, device=device), e).float().contiguous(), mask_u8=mask_u8)

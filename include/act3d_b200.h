@@ -72,11 +72,13 @@ int a3d_traj_topk(const float* traj, int traj_len, const float* pts, int batch, 
 /* ---------------------------------------------------------------------------------
  * Token gather.  Replaces rearrange "b ncam c h w -> b (ncam h w) c" + per-sample
  * index gather of features and positions (act3d.py:240-254, diffusion_head.py:290-302).
- * feat [B*ncam][E][hw], pcd [B][ncam*hw][3], idx [B][K] or NULL (identity, K = ncam*hw).
- * Writes rows [0,K) of tok [B][tok_rows][E] and pos [B][tok_rows][3].
+ * feat [B*ncam][E][hw] (channels_last = 0) or [B*ncam][hw][E] (channels_last = 1, the NHWC layout cuDNN
+ * leaves the FPN output in: one contiguous row per token), pcd [B][ncam*hw][3], idx [B][K] or NULL
+ * (identity, K = ncam*hw).  Writes rows [0,K) of tok [B][tok_rows][E] and pos [B][tok_rows][3].
  */
 int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, int batch, int ncam,
-                      int embed, int hw, int k, float* tok, float* pos, int tok_rows, void* stream);
+                      int embed, int hw, int k, float* tok, float* pos, int tok_rows, int channels_last,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Context K/V cache.  Replaces, for `nsets` attention layers that share one context,
@@ -186,7 +188,10 @@ int cd_step_begin(const float* traj, int batch, int length, const float* wp_pe, 
 
 /* Cross-attention of the waypoint tokens over the cached context K/V of one layer (tile images from
  * a3d_ctx_kv).  Replaces the cross_12 attention core of ParallelAttentionLayer (layers.py:135-145;
- * multihead_custom_attention.py:355-451).  q [B][H][64][16] fp16, att [B][64][E] (heads concatenated). */
+ * multihead_custom_attention.py:355-451).  q [B][H][64][16] fp16.  The key tiles of every (sample, head)
+ * are split over 4 CTAs; `att` receives their unnormalised partial results
+ * [B][4][H][64][17] = {O (15), pad, denominator, row max}: cd_cross_part_floats(B) floats, merged by cd_post. */
+size_t cd_cross_part_floats(int batch);
 int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float* att, void* stream);
 
 /* Rest of one adaLN layer.  Replaces out-proj + norm_12, the adaLN self-attention (rotary q/k,
@@ -194,6 +199,7 @@ int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float*
  * regressor head (diffusion_head.py:179-198, 357-363), the Q of the next layer, and -- on the last
  * layer of a step -- the denoiser output assembly (diffusion_head.py:271-274), inpainting of the
  * conditioned waypoints and the DDPM posterior step of both schedulers (diffusion_model.py:105-117).
+ * att = the partial cross-attention results written by cd_cross (merged here).
  * layer_w / layer_v = AdaW / AdaV of this layer, reg_w / reg_v = MlpW / MlpV or NULL.
  * coef_host = {c_x0, c_xt, sigma} for positions then rotations (act3d_chained_diffuser_b200/ddpm.py). */
 int cd_post(const float* traj, int batch, int length, const unsigned char* mask, const float* wp_pe,

@@ -311,3 +311,17 @@ def test_mask_logits_kernel(lib):
     lib.mask_logits(dev(feat), dev(qv), out)
     want = torch.einsum("jbc,bnc->jbn", qv.double(), feat.double()).float()
     assert (out.cpu() - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+def test_gather_tokens_channels_last(lib):
+    b, ncam, e = 2, 2, 60
+    feat = synth.normal("g2.feat", (b * ncam, e, 16, 16))
+    pcd = synth.points_in_bounds("g2.pcd", (b, ncam * 256))
+    idx = torch.from_numpy(np.stack([synth.rng_for(f"g2.idx{i}").permutation(ncam * 256)[:77] for i in range(b)])).int()
+    out = []
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        tok = torch.zeros(b, 80, e).cuda()
+        pos = torch.zeros(b, 80, 3).cuda()
+        lib.gather_tokens(feat.cuda().contiguous(memory_format=fmt), dev(pcd), dev(idx), b, ncam, tok, pos)
+        out.append((tok.cpu(), pos.cpu()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
