@@ -135,24 +135,36 @@ __device__ __forceinline__ float row_max(float v) {
 template <int LPR>
 __device__ __forceinline__ void residual_layernorm(float* __restrict__ x, const float* __restrict__ add,
                                                    const float* __restrict__ g, const float* __restrict__ b) {
+    constexpr int NC = E / LPR;                       // columns per lane (E = 120, LPR = 4 or 8: exact)
+    static_assert(E % LPR == 0, "row passes assume E divisible by the lanes per row");
     const int r = threadIdx.x / LPR, part = threadIdx.x % LPR;
+    // LayerNorm parameters first: their L1/L2 latency overlaps the reductions below
+    float gg[NC], bb[NC], v[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        gg[i] = __ldg(g + part + i * LPR);
+        bb[i] = __ldg(b + part + i * LPR);
+    }
     float s = 0.f;
-    for (int c = part; c < E; c += LPR) {
-        float v = x[c * RP + r];
-        if (add) v += add[c * RP + r];
-        x[c * RP + r] = v;
-        s += v;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = part + i * LPR;
+        v[i] = x[c * RP + r];
+        if (add) v[i] += add[c * RP + r];
+        s += v[i];
     }
     s = row_sum<LPR>(s);
     const float mean = s * (1.0f / E);
     float v2 = 0.f;
-    for (int c = part; c < E; c += LPR) {
-        const float d = x[c * RP + r] - mean;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const float d = v[i] - mean;
         v2 = fmaf(d, d, v2);
     }
     v2 = row_sum<LPR>(v2);
     const float rstd = 1.0f / sqrtf(v2 * (1.0f / E) + 1e-5f);
-    for (int c = part; c < E; c += LPR) x[c * RP + r] = (x[c * RP + r] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) x[(part + i * LPR) * RP + r] = (v[i] - mean) * rstd * gg[i] + bb[i];
 }
 
 // dst[c][r] = (src[c][r] + pe[r][c]) * (1 + scale[c]) + shift[c]; pe / scale / shift may be null

@@ -140,7 +140,7 @@ __device__ __forceinline__ void planes_from_partials(const float* __restrict__ p
         float m[kCrossSplits], big = -INFINITY;
 #pragma unroll
         for (int sp = 0; sp < kCrossSplits; ++sp) {
-            m[sp] = __ldg(part_b + (((size_t)sp * H + h) * ROWS + r) * 17 + 16);
+            m[sp] = __ldg(part_b + ((size_t)sp * H + h) * ROWS * 17 + 16 * ROWS + r);
             big = fmaxf(big, m[sp]);
         }
         float acc[16];
@@ -149,9 +149,9 @@ __device__ __forceinline__ void planes_from_partials(const float* __restrict__ p
 #pragma unroll
         for (int sp = 0; sp < kCrossSplits; ++sp) {
             const float wgt = (m[sp] == -INFINITY) ? 0.f : exp2f(m[sp] - big);
-            const float* src = part_b + (((size_t)sp * H + h) * ROWS + r) * 17;
+            const float* src = part_b + ((size_t)sp * H + h) * ROWS * 17 + r;   // [17][ROWS]: coalesced over rows
 #pragma unroll
-            for (int d = 0; d < 16; ++d) acc[d] = fmaf(wgt, __ldg(src + d), acc[d]);
+            for (int d = 0; d < 16; ++d) acc[d] = fmaf(wgt, __ldg(src + d * ROWS), acc[d]);
         }
         const float inv = 1.0f / acc[15];
         // columns 15h .. 15h+14 of row r (pairs may straddle the 4-byte packing: write element-wise)
@@ -188,7 +188,7 @@ __device__ __forceinline__ void planes_from_global(const float* __restrict__ src
 }
 
 // ---- the 64 x 128 GEMM of one CTA: warp = (m tile, n half), eight n tiles per warp, weights via the smem ring
-// epi(row, col, v0, v1) receives output elements (row, col) and (row, col + 1), col relative to the window
+// epi(n, row, col, v0, v1) receives output elements (row, col) and (row, col + 1) of the warp's n-th tile, col relative to the window
 template <class Epi>
 __device__ __forceinline__ void gemm64(const WarpMap& w, Smem& s, const __half* ah, const __half* al, const uint4* wfrag,
                                        int ntiles_total, int nt_base, Epi epi) {
@@ -197,10 +197,23 @@ __device__ __forceinline__ void gemm64(const WarpMap& w, Smem& s, const __half* 
 #pragma unroll
     for (int n = 0; n < NTW; ++n) {
         const int col = 8 * (NTW * w.nh + n) + 2 * w.q4;
-        epi(w.m0 + w.g, col, acc[n][0], acc[n][1]);
-        epi(w.m0 + w.g + 8, col, acc[n][2], acc[n][3]);
+        epi(n, w.m0 + w.g, col, acc[n][0], acc[n][1]);
+        epi(n, w.m0 + w.g + 8, col, acc[n][2], acc[n][3]);
     }
 }
+// this thread's 2 x NTW output-column biases, fetched BEFORE the GEMM so the load latency hides under the MMAs
+struct BiasFrag {
+    float v[NTW][2];
+    __device__ __forceinline__ BiasFrag(const WarpMap& w, const float* __restrict__ bias) {
+#pragma unroll
+        for (int n = 0; n < NTW; ++n) {
+            const int col = 8 * (NTW * w.nh + n) + 2 * w.q4;     // < 128: bias vectors are padded to 128 floats
+            v[n][0] = __ldg(bias + col);
+            v[n][1] = __ldg(bias + col + 1);
+        }
+    }
+};
+
 // early fetch of the first weight slabs of the next GEMM; legal right after a __syncthreads that follows the last GEMM
 __device__ __forceinline__ void prefetch_w(Smem& s, const uint4* wfrag, int ntiles_total = 16, int nt_base = 0) {
     ring_prefetch_head<8>(s.ring, wfrag, ntiles_total, nt_base);
@@ -209,10 +222,11 @@ __device__ __forceinline__ void prefetch_w(Smem& s, const uint4* wfrag, int ntil
 // out tile (K-major fp32) = A W^T + bias
 __device__ __forceinline__ void linear_tile(const WarpMap& w, Smem& s, const __half* ah, const __half* al, const uint4* wf,
                                             const float* __restrict__ bias, float* __restrict__ out) {
-    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+    const BiasFrag bf(w, bias);
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int n, int r, int c, float v0, float v1) {
         if (c < E) {
-            out[c * RP + r] = v0 + __ldg(bias + c);
-            out[(c + 1) * RP + r] = v1 + __ldg(bias + c + 1);
+            out[c * RP + r] = v0 + bf.v[n][0];
+            out[(c + 1) * RP + r] = v1 + bf.v[n][1];
         }
     });
 }
@@ -234,10 +248,11 @@ __device__ __forceinline__ void rotate_pair(const Smem& s, int r, int c, float& 
 }
 __device__ __forceinline__ void linear_rope_tile(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
                                                  const uint4* wf, const float* __restrict__ bias, float* __restrict__ out) {
-    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+    const BiasFrag bf(w, bias);
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int n, int r, int c, float v0, float v1) {
         if (c < E) {
-            v0 += __ldg(bias + c);
-            v1 += __ldg(bias + c + 1);
+            v0 += bf.v[n][0];
+            v1 += bf.v[n][1];
             rotate_pair(s, r, c, v0, v1);
             out[c * RP + r] = v0;
             out[(c + 1) * RP + r] = v1;
@@ -247,10 +262,11 @@ __device__ __forceinline__ void linear_rope_tile(const WarpMap& w, Smem& s, cons
 // rotary projection written straight to the global fp16 Q of the next cross-attention [H][64][16]
 __device__ __forceinline__ void linear_rope_q(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
                                               const uint4* wf, const float* __restrict__ bias, __half* __restrict__ q) {
-    gemm64(w, s, ah, al, wf, 16, 0, [&](int r, int c, float v0, float v1) {
+    const BiasFrag bf(w, bias);
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int n, int r, int c, float v0, float v1) {
         if (c < E) {
-            v0 += __ldg(bias + c);
-            v1 += __ldg(bias + c + 1);
+            v0 += bf.v[n][0];
+            v1 += bf.v[n][1];
             rotate_pair(s, r, c, v0, v1);
             const int h0 = c / HD, h1 = (c + 1) / HD;
             q[(h0 * ROWS + r) * 16 + (c - h0 * HD)] = __float2half_rn(v0);
@@ -272,9 +288,10 @@ __device__ __forceinline__ void ffn_tile(const WarpMap& w, Smem& s, const uint4*
         for (int e = 0; e < 4; ++e) sum[n][e] = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < FFP / 128; ++ch) {
-        gemm64(w, s, s.ah, s.al, w1, 64, 16 * ch, [&](int r, int c, float v0, float v1) {
-            v0 = fmaxf(v0 + __ldg(b1 + 128 * ch + c), 0.f);
-            v1 = fmaxf(v1 + __ldg(b1 + 128 * ch + c + 1), 0.f);
+        const BiasFrag bf(w, b1 + 128 * ch);
+        gemm64(w, s, s.ah, s.al, w1, 64, 16 * ch, [&](int n, int r, int c, float v0, float v1) {
+            v0 = fmaxf(v0 + bf.v[n][0], 0.f);
+            v1 = fmaxf(v1 + bf.v[n][1], 0.f);
             uint32_t h, l;
             split_h2(v0, v1, h, l);
             *reinterpret_cast<uint32_t*>(s.hh + r * PITCH + c) = h;
@@ -495,9 +512,10 @@ __global__ void __launch_bounds__(THREADS, 1) cd_post_kernel(const StepArgs a) {
     if (a.reg_w) {
         planes_from_tile(x, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
         __syncthreads();
-        gemm64(w, s, s.ah, s.al, a.reg_w + MlpW::W1, 16, 0, [&](int r, int c, float v0, float v1) {
-            v0 = fmaxf(v0 + __ldg(a.reg_v + MlpV::B1 + c), 0.f);
-            v1 = fmaxf(v1 + __ldg(a.reg_v + MlpV::B1 + c + 1), 0.f);
+        const BiasFrag breg(w, a.reg_v + MlpV::B1);
+        gemm64(w, s, s.ah, s.al, a.reg_w + MlpW::W1, 16, 0, [&](int n, int r, int c, float v0, float v1) {
+            v0 = fmaxf(v0 + breg.v[n][0], 0.f);
+            v1 = fmaxf(v1 + breg.v[n][1], 0.f);
             uint32_t h, l;
             split_h2(v0, v1, h, l);
             *reinterpret_cast<uint32_t*>(s.hh + r * PITCH + c) = h;
@@ -663,7 +681,7 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + stage);
     }
-    // unnormalised partial: columns 0..14 = O, 15 = denominator (rode in V's slot 15), 16 = row max (-inf if this
+    // unnormalised partial, stored [17][ROWS]: planes 0..14 = O, 15 = denominator (rode in V's slot 15), 16 = row max (-inf if this
     // slice was empty); cd_post merges the kCrossSplits partials of a row
     float* out = a.part + (((size_t)b * kCrossSplits + split) * H + h) * ROWS * 17;
 #pragma unroll
@@ -672,11 +690,11 @@ __global__ void __launch_bounds__(128) cd_cross_kernel(const CrossArgs a) {
         for (int e = 0; e < 4; ++e) {
             const int d = 8 * n + 2 * q4 + (e & 1);
             const int row = warp * 16 + g + 8 * (e >> 1);
-            out[(size_t)row * 17 + d] = o[n][e];
+            out[d * ROWS + row] = o[n][e];
         }
     if (q4 == 0) {
-        out[(size_t)(warp * 16 + g) * 17 + 16] = m0;
-        out[(size_t)(warp * 16 + g + 8) * 17 + 16] = m1;
+        out[16 * ROWS + warp * 16 + g] = m0;
+        out[16 * ROWS + warp * 16 + g + 8] = m1;
     }
 }
 

@@ -190,7 +190,7 @@ int cd_step_begin(const float* traj, int batch, int length, const float* wp_pe, 
  * a3d_ctx_kv).  Replaces the cross_12 attention core of ParallelAttentionLayer (layers.py:135-145;
  * multihead_custom_attention.py:355-451).  q [B][H][64][16] fp16.  The key tiles of every (sample, head)
  * are split over 4 CTAs; `att` receives their unnormalised partial results
- * [B][4][H][64][17] = {O (15), pad, denominator, row max}: cd_cross_part_floats(B) floats, merged by cd_post. */
+ * [B][4][H][17][64] = planes {O (15), denominator, row max} x 64 rows: cd_cross_part_floats(B) floats, merged by cd_post. */
 size_t cd_cross_part_floats(int batch);
 int cd_cross(const void* q, const void* kv, int batch, int nk, int heads, float* att, void* stream);
 
