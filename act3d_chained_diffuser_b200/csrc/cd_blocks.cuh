@@ -1,7 +1,7 @@
-// Building blocks of the ChainedDiffuser denoiser kernels: one CTA (256 threads) owns the 64-row
-// (50 waypoints + padding) token tile of one sample; activations live K-MAJOR in shared memory
-// ([channel][row], pitch 66 floats) so that the register-tiled GEMM of a3d_linear.cuh reads them
-// with 8-byte loads.  E = 120, H = 8, head_dim 15, FFN 480 (diffusion_head.py / layers.py:7-218).
+// Building blocks of the ChainedDiffuser denoiser kernels: one CTA owns the 64-row (50 waypoints +
+// padding) token tile of one sample; the fp32 residual stream lives K-MAJOR in shared memory
+// ([channel][row], pitch 66 floats).  E = 120, H = 8, head_dim 15, FFN 480
+// (diffusion_head.py / layers.py:7-218).  The tensor-core GEMMs and attention are in cd_denoiser.cu.
 #pragma once
 #include "a3d_linear.cuh"
 
@@ -67,56 +67,6 @@ __device__ __forceinline__ void linear_to_smem(const Map& m, const float* __rest
     }
 }
 
-// same, but accumulates into registers that the caller keeps (used to sum FFN chunks)
-template <int KD, int NP>
-__device__ __forceinline__ void linear_accumulate(const Map& m, const float* __restrict__ in, const float* __restrict__ wt,
-                                                  float (&sum)[2][16]) {
-    float acc[2][16];
-    gemm_2x16<KD, RP, NP>(in, wt, m.rg, m.cg, acc);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        sum[0][c] += acc[0][c];
-        sum[1][c] += acc[1][c];
-    }
-}
-
-// projection followed by the 3-D rotary rotation of channel pairs, computed on the accumulator
-// registers (a thread owns 8 complete pairs of 2 rows); xyz: [64][3] in shared memory.
-template <int KD, int NP>
-__device__ __forceinline__ void linear_rope_to_smem(const Map& m, const float* __restrict__ in, const float* __restrict__ wt,
-                                                    const float* __restrict__ bias, const float* __restrict__ xyz,
-                                                    const float* __restrict__ freq, bool rope, float* __restrict__ out) {
-    float acc[2][16];
-    gemm_2x16<KD, RP, NP>(in, wt, m.rg, m.cg, acc);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float b = __ldg(bias + 16 * m.cg + c);
-        acc[0][c] += b;
-        acc[1][c] += b;
-    }
-    if (rope) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int pi = 8 * m.cg + p;
-            if (pi < NPAIR) {
-                const int axis = pi / (E / 6), j = pi - axis * (E / 6);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const float ang = __fmul_rn(xyz[(2 * m.rg + r) * 3 + axis], freq[j]);
-                    float sv, cv;
-                    sincosf(ang, &sv, &cv);
-                    const float ev = acc[r][2 * p], od = acc[r][2 * p + 1];
-                    acc[r][2 * p] = ev * cv - od * sv;
-                    acc[r][2 * p + 1] = od * cv + ev * sv;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
-        *reinterpret_cast<float2*>(out + (16 * m.cg + c) * RP + 2 * m.rg) = make_float2(acc[0][c], acc[1][c]);
-}
-
 // x[c][r] <- LayerNorm_c( x[c][r] + add[c][r] ) * g + b, rows 0..63 (4 threads per row).  add may be null.
 // LPR = lanes cooperating on one row = blockDim.x / 64 (4 for 256 threads, 8 for 512)
 template <int LPR>
@@ -125,13 +75,6 @@ __device__ __forceinline__ float row_sum(float v) {
     for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-template <int LPR>
-__device__ __forceinline__ float row_max(float v) {
-#pragma unroll
-    for (int o = 1; o < LPR; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 template <int LPR>
 __device__ __forceinline__ void residual_layernorm(float* __restrict__ x, const float* __restrict__ add,
                                                    const float* __restrict__ g, const float* __restrict__ b) {
@@ -165,72 +108,6 @@ __device__ __forceinline__ void residual_layernorm(float* __restrict__ x, const 
     const float rstd = 1.0f / sqrtf(v2 * (1.0f / E) + 1e-5f);
 #pragma unroll
     for (int i = 0; i < NC; ++i) x[(part + i * LPR) * RP + r] = (v[i] - mean) * rstd * gg[i] + bb[i];
-}
-
-// dst[c][r] = (src[c][r] + pe[r][c]) * (1 + scale[c]) + shift[c]; pe / scale / shift may be null
-// (AdaLN, layers.py:282-290; the waypoint-index embedding is the reference's seq1_sem_pos).
-__device__ __forceinline__ void modulate(float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ pe,
-                                         const float* __restrict__ scale, const float* __restrict__ shift, int nrows) {
-    for (int i = threadIdx.x; i < ROWS * E; i += blockDim.x) {
-        const int c = i / ROWS, r = i - c * ROWS;
-        float v = src[c * RP + r];
-        if (pe && r < nrows) v += __ldg(pe + r * E + c);
-        if (scale) v = v * (1.0f + __ldg(scale + c)) + __ldg(shift + c);
-        dst[c * RP + r] = v;
-    }
-}
-
-// Small multi-head attention entirely in shared memory, fp32 (self-attention over <= 64 waypoints,
-// or attention to the 53 instruction tokens).  q, k, v, out: K-major tiles; q carries
-// hd^-1/2 * log2(e).  key_mask[j] != 0 => key j ignored (key_padding_mask, layers.py:178).
-// scores: [64][65] scratch.  out may alias q (each head's q columns are consumed before its
-// output columns are written).
-template <int LPR>
-__device__ __forceinline__ void small_mha(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                          int nk, const unsigned char* __restrict__ key_mask, float* __restrict__ scores,
-                                          float* __restrict__ out) {
-    const int i = threadIdx.x / LPR, part = threadIdx.x % LPR;
-    for (int h = 0; h < H; ++h) {
-        const int d0 = h * HD;
-        float qv[HD];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) qv[d] = q[(d0 + d) * RP + i];
-        float mx = -INFINITY;
-        for (int j = part; j < nk; j += LPR) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;   // three independent chains hide the FMA latency
-#pragma unroll
-            for (int d = 0; d < HD; d += 3) {
-                s0 = fmaf(qv[d], k[(d0 + d) * RP + j], s0);
-                s1 = fmaf(qv[d + 1], k[(d0 + d + 1) * RP + j], s1);
-                s2 = fmaf(qv[d + 2], k[(d0 + d + 2) * RP + j], s2);
-            }
-            float s = (s0 + s1) + s2;
-            if (key_mask && key_mask[j]) s = -INFINITY;
-            scores[i * 65 + j] = s;
-            mx = fmaxf(mx, s);
-        }
-        mx = row_max<LPR>(mx);
-        float sum = 0.f;
-        for (int j = part; j < nk; j += LPR) {
-            const float p = exp2f(scores[i * 65 + j] - mx);
-            scores[i * 65 + j] = p;
-            sum += p;
-        }
-        sum = row_sum<LPR>(sum);
-        const float inv = 1.0f / sum;
-        __syncwarp();   // the LPR lanes of a row share its score row
-        for (int d = part; d < HD; d += LPR) {
-            float o0 = 0.f, o1 = 0.f;
-            int j = 0;
-            for (; j + 1 < nk; j += 2) {
-                o0 = fmaf(scores[i * 65 + j], v[(d0 + d) * RP + j], o0);
-                o1 = fmaf(scores[i * 65 + j + 1], v[(d0 + d) * RP + j + 1], o1);
-            }
-            if (j < nk) o0 = fmaf(scores[i * 65 + j], v[(d0 + d) * RP + j], o0);
-            out[(d0 + d) * RP + i] = (o0 + o1) * inv;
-        }
-        __syncwarp();
-    }
 }
 
 }  // namespace cd

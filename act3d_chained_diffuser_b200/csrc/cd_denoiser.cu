@@ -53,8 +53,9 @@ constexpr size_t SMEM_BYTES = (size_t)4 * TILE_E * 4 + (size_t)4 * PLANE * 2 + (
                               64 * 3 * 4 + 32 * 4 + 64 + 16;
 
 struct Smem {
-    float *xs, *t1, *t2, *t3, *scores, *xyz, *freq;
+    float *xs, *t1, *t2, *t3, *xyz, *freq;
     __half *ah, *al, *hh, *hl;
+    __half *kh, *kl, *vh, *vl;       // head-padded K / V planes of the in-CTA attention (alias t1..t3)
     unsigned char* mask;
     WeightRing ring;
     __device__ explicit Smem(unsigned char* base) {
@@ -68,7 +69,10 @@ struct Smem {
         al = ah + PLANE;
         hh = al + PLANE;
         hl = hh + PLANE;
-        scores = reinterpret_cast<float*>(hh);          // aliases the hidden planes (never live together)
+        kh = reinterpret_cast<__half*>(t1);             // 4 planes = 69632 B inside the 95040 B of t1..t3
+        kl = kh + PLANE;
+        vh = kl + PLANE;
+        vl = vh + PLANE;
         xyz = reinterpret_cast<float*>(hl + PLANE);
         freq = xyz + 64 * 3;
         mask = reinterpret_cast<unsigned char*>(freq + 32);
@@ -246,19 +250,6 @@ __device__ __forceinline__ void rotate_pair(const Smem& s, int r, int c, float& 
         v1 = od * cv + ev * sv;
     }
 }
-__device__ __forceinline__ void linear_rope_tile(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
-                                                 const uint4* wf, const float* __restrict__ bias, float* __restrict__ out) {
-    const BiasFrag bf(w, bias);
-    gemm64(w, s, ah, al, wf, 16, 0, [&](int n, int r, int c, float v0, float v1) {
-        if (c < E) {
-            v0 += bf.v[n][0];
-            v1 += bf.v[n][1];
-            rotate_pair(s, r, c, v0, v1);
-            out[c * RP + r] = v0;
-            out[(c + 1) * RP + r] = v1;
-        }
-    });
-}
 // rotary projection written straight to the global fp16 Q of the next cross-attention [H][64][16]
 __device__ __forceinline__ void linear_rope_q(const WarpMap& w, Smem& s, const __half* ah, const __half* al,
                                               const uint4* wf, const float* __restrict__ bias, __half* __restrict__ q) {
@@ -276,6 +267,161 @@ __device__ __forceinline__ void linear_rope_q(const WarpMap& w, Smem& s, const _
             q[((c + 1 - E) * ROWS + r) * 16 + 15] = __float2half_rn(0.f);
         }
     });
+}
+
+
+// ---- in-CTA multi-head attention on the tensor cores -------------------------------------------
+// Operands live as fp16 (hi, lo) planes [64 rows][PITCH] whose 128 columns are HEAD-PADDED: column
+// 16 h + d holds channel 15 h + d, column 16 h + 15 is zero, so that one k16 step covers one head.
+__device__ __forceinline__ int head_slot(int c) { return c + c / HD; }
+
+// out planes (head-padded) = [rotary](A W^T + bias); the GEMM runs in the natural channel order (rotary
+// pairs (2p, 2p+1) straddle heads) and the epilogue scatters to the padded columns
+template <bool ROPE>
+__device__ __forceinline__ void linear_heads(const WarpMap& w, Smem& s, const __half* ah, const __half* al, const uint4* wf,
+                                             const float* __restrict__ bias, __half* __restrict__ oh, __half* __restrict__ ol) {
+    const BiasFrag bf(w, bias);
+    gemm64(w, s, ah, al, wf, 16, 0, [&](int n, int r, int c, float v0, float v1) {
+        if (c < E) {
+            v0 += bf.v[n][0];
+            v1 += bf.v[n][1];
+            if (ROPE) rotate_pair(s, r, c, v0, v1);
+            __half h0, l0, h1, l1;
+            split_h(v0, h0, l0);
+            split_h(v1, h1, l1);
+            const int s0 = r * PITCH + head_slot(c), s1 = r * PITCH + head_slot(c + 1);
+            oh[s0] = h0;
+            ol[s0] = l0;
+            oh[s1] = h1;
+            ol[s1] = l1;
+        } else {   // GEMM columns 120..127 own the zero pad column of head c - 120
+            const int s0 = r * PITCH + (c - E) * 16 + 15;
+            oh[s0] = ol[s0] = oh[s0 + 16] = ol[s0 + 16] = __float2half_rn(0.f);
+        }
+    });
+}
+// head-padded planes of a row-major fp32 global matrix [nrows][E] (rows >= nrows zero)
+__device__ __forceinline__ void head_planes_from_global(const float* __restrict__ src, int nrows, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo) {
+    for (int i = threadIdx.x; i < ROWS * EP; i += blockDim.x) {
+        const int r = i >> 7, slot = i & 127, h = slot >> 4, d = slot & 15;
+        const float v = (r < nrows && d < HD) ? __ldg(src + (size_t)r * E + h * HD + d) : 0.f;
+        __half vh, vl;
+        split_h(v, vh, vl);
+        hi[r * PITCH + slot] = vh;
+        lo[r * PITCH + slot] = vl;
+    }
+}
+
+// out planes (natural channel order, fp16 hi/lo) = softmax(q k^T) v per head; q carries hd^-1/2 log2(e).
+// warp = (head, 32-row half); all three products use the error-compensated split (hi hi + 2^-11 (hi lo + lo hi)),
+// the softmax is exact over the <= 64 keys (no online rescale), the denominator is summed in fp32.
+// nk keys are valid; key_mask[j] != 0 => key j ignored (key_padding_mask, layers.py:178).
+__device__ __forceinline__ void mma_mha(const WarpMap& w, const __half* __restrict__ qh, const __half* __restrict__ ql,
+                                        const __half* __restrict__ kh, const __half* __restrict__ kl,
+                                        const __half* __restrict__ vh, const __half* __restrict__ vl, int nk,
+                                        const unsigned char* __restrict__ key_mask, __half* __restrict__ oh,
+                                        __half* __restrict__ ol) {
+    const int h = w.warp & 7, lane = w.lane, g = w.g, q4 = w.q4;
+    // key validity of this thread's score columns (8 j + 2 q4 + {0, 1})
+    uint32_t dead = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int key = 8 * j + 2 * q4 + e;
+            if (key >= nk || (key_mask && key_mask[key])) dead |= 1u << (2 * j + e);
+        }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        const int m0 = 32 * (w.warp >> 3) + 16 * mt;
+        uint32_t fqh[4], fql[4];
+        {
+            const int row = m0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+            const int off = row * PITCH + 16 * h + 8 * (lane >> 4);
+            ldmatrix_x4(fqh, smem_u32(qh + off));
+            ldmatrix_x4(fql, smem_u32(ql + off));
+        }
+        float sc[8][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int key = kk * 16 + (lane & 7) + 8 * (lane >> 4);
+            const int off = key * PITCH + 16 * h + 8 * ((lane >> 3) & 1);
+            uint32_t bh[4], bl[4];
+            ldmatrix_x4(bh, smem_u32(kh + off));
+            ldmatrix_x4(bl, smem_u32(kl + off));
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f}, cor[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_16816(acc, fqh, bh[2 * t], bh[2 * t + 1]);
+                mma_16816(cor, fqh, bl[2 * t], bl[2 * t + 1]);
+                mma_16816(cor, fql, bh[2 * t], bh[2 * t + 1]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool off_key = (dead >> (2 * (2 * kk + t) + (e & 1))) & 1u;
+                    sc[2 * kk + t][e] = off_key ? -INFINITY : fmaf(cor[e], kLoScaleInv, acc[e]);
+                }
+            }
+        }
+        float mx0 = sc[0][0], mx1 = sc[0][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j][0] = exp2f(sc[j][0] - mx0);
+            sc[j][1] = exp2f(sc[j][1] - mx0);
+            sc[j][2] = exp2f(sc[j][2] - mx1);
+            sc[j][3] = exp2f(sc[j][3] - mx1);
+            l0 += sc[j][0] + sc[j][1];
+            l1 += sc[j][2] + sc[j][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, oc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t ph[4], pl[4];
+            split_h2(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]);
+            split_h2(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
+            split_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]);
+            split_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
+            const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+            const int off = key * PITCH + 16 * h + 8 * (lane >> 4);
+            uint32_t bh[4], bl[4];
+            ldmatrix_x4_trans(bh, smem_u32(vh + off));
+            ldmatrix_x4_trans(bl, smem_u32(vl + off));
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                mma_16816(o[n], ph, bh[2 * n], bh[2 * n + 1]);
+                mma_16816(oc[n], ph, bl[2 * n], bl[2 * n + 1]);
+                mma_16816(oc[n], pl, bh[2 * n], bh[2 * n + 1]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = 8 * n + 2 * q4 + (e & 1);
+                if (d < HD) {
+                    const int row = m0 + g + 8 * (e >> 1);
+                    __half vh_, vl_;
+                    split_h(fmaf(oc[n][e], kLoScaleInv, o[n][e]) * ((e >> 1) ? i1 : i0), vh_, vl_);
+                    oh[row * PITCH + h * HD + d] = vh_;
+                    ol[row * PITCH + h * HD + d] = vl_;
+                }
+            }
+    }
 }
 
 // FFN 120 -> 480 -> 120 in four 128-wide hidden chunks; y planes in (ah, al); result (+b2) -> out tile
@@ -329,15 +475,13 @@ __device__ __forceinline__ void lang_attention(const WarpMap& w, Smem& s, const 
                                                const float* g, const float* b, const float* kin, const float* vin,
                                                int n_instr) {
     planes_from_tile(s.xs, pe, nullptr, nullptr, nrows, s.ah, s.al, nullptr);
-    load_tile(s.t2, kin, n_instr, E);
-    load_tile(s.t3, vin, n_instr, E);
+    head_planes_from_global(kin, n_instr, s.kh, s.kl);
+    head_planes_from_global(vin, n_instr, s.vh, s.vl);
     __syncthreads();
-    linear_tile(w, s, s.ah, s.al, wq, bq, s.t1);
+    linear_heads<false>(w, s, s.ah, s.al, wq, bq, s.hh, s.hl);
     __syncthreads();
     prefetch_w(s, wo);
-    small_mha<LPR>(s.t1, s.t2, s.t3, n_instr, nullptr, s.scores, s.t1);
-    __syncthreads();
-    planes_from_tile(s.t1, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
+    mma_mha(w, s.hh, s.hl, s.kh, s.kl, s.vh, s.vl, n_instr, nullptr, s.ah, s.al);   // (ah, al): pad columns stay zero
     __syncthreads();
     linear_tile(w, s, s.ah, s.al, wo, bo, s.t2);
     __syncthreads();
@@ -475,21 +619,21 @@ __global__ void __launch_bounds__(THREADS, 1) cd_post_kernel(const StepArgs a) {
     // ---- cross-attention epilogue: x = LN_12(x + att Wo^T + bo)          (layers.py:146-147)
     linear_tile(w, s, s.ah, s.al, lw + AdaW::C_WO, lv + AdaV::C_BO, s.t1);
     __syncthreads();
-    prefetch_w(s, lw + AdaW::S_WQ);
+    prefetch_w(s, lw + AdaW::S_WV);
     residual_layernorm<LPR>(s.xs, s.t1, lv + AdaV::G12, lv + AdaV::B12);
     __syncthreads();
     // ---- self-attention: q = k = adaLN_1(x + pe), v = adaLN_1(x), rotary on q and k, padding mask (layers.py:165-182)
     planes_from_tile(s.xs, a.wp_pe, ada + 2 * EP, ada + 3 * EP, a.nrows, s.ah, s.al, nullptr);
     planes_from_tile(s.xs, nullptr, ada + 2 * EP, ada + 3 * EP, a.nrows, s.hh, s.hl, nullptr);
     __syncthreads();
-    linear_rope_tile(w, s, s.ah, s.al, lw + AdaW::S_WQ, lv + AdaV::S_BQ, s.t1);
-    linear_rope_tile(w, s, s.ah, s.al, lw + AdaW::S_WK, lv + AdaV::S_BK, s.t2);
-    linear_tile(w, s, s.hh, s.hl, lw + AdaW::S_WV, lv + AdaV::S_BV, s.t3);
+    // V first: its input planes (hh, hl) are then free to receive Q (every warp has left the V GEMM's k loop
+    // once it passes the first barrier of the K GEMM)
+    linear_heads<false>(w, s, s.hh, s.hl, lw + AdaW::S_WV, lv + AdaV::S_BV, s.vh, s.vl);
+    linear_heads<true>(w, s, s.ah, s.al, lw + AdaW::S_WK, lv + AdaV::S_BK, s.kh, s.kl);
+    linear_heads<true>(w, s, s.ah, s.al, lw + AdaW::S_WQ, lv + AdaV::S_BQ, s.hh, s.hl);
     __syncthreads();
     prefetch_w(s, lw + AdaW::S_WO);
-    small_mha<LPR>(s.t1, s.t2, s.t3, a.nrows, a.mask ? s.mask : nullptr, s.scores, s.t1);
-    __syncthreads();
-    planes_from_tile(s.t1, nullptr, nullptr, nullptr, 0, s.ah, s.al, nullptr);
+    mma_mha(w, s.hh, s.hl, s.kh, s.kl, s.vh, s.vl, a.nrows, a.mask ? s.mask : nullptr, s.ah, s.al);
     __syncthreads();
     linear_tile(w, s, s.ah, s.al, lw + AdaW::S_WO, lv + AdaV::S_BO, s.t2);
     __syncthreads();
