@@ -237,7 +237,7 @@ template <int E>
 __global__ void __launch_bounds__(256) gather_tokens_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ pcd,
                                                                  const int32_t* __restrict__ idx, int ncam, int hw, int k,
                                                                  float* __restrict__ tok, float* __restrict__ pos,
-                                                                 int tok_rows) {
+                                                                 int tok_rows, const float* __restrict__ bias) {
     const int b = blockIdx.y;
     const int r0 = blockIdx.x * 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) gather_tokens_nhwc_kernel(const float* __
         const int s = idx ? __ldg(idx + (long)b * k + r) : r;
         const float* src = feat + ((long)b * ncam * hw + s) * E;
         float* dst = tok + ((long)b * tok_rows + r) * E;
-        for (int c = lane; c < E; c += 32) dst[c] = __ldg(src + c);
+        for (int c = lane; c < E; c += 32) dst[c] = bias ? __fadd_rn(__ldg(src + c), __ldg(bias + c)) : __ldg(src + c);
         if (lane < 3) pos[((long)b * tok_rows + r) * 3 + lane] = __ldg(pcd + ((long)b * ncam * hw + s) * 3 + lane);
     }
 }
@@ -256,7 +256,7 @@ template <int E>
 __global__ void __launch_bounds__(256) gather_tokens_kernel(const float* __restrict__ feat, const float* __restrict__ pcd,
                                                             const int32_t* __restrict__ idx, int ncam, int hw, int k,
                                                             float* __restrict__ tok, float* __restrict__ pos,
-                                                            int tok_rows) {
+                                                            int tok_rows, const float* __restrict__ bias) {
     __shared__ float tile[32][E + 1];
     __shared__ int src[32];
     const int b = blockIdx.y;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) gather_tokens_kernel(const float* __restr
     __syncthreads();
     for (int i = t; i < 32 * E; i += 256) {
         const int r = i / E, c = i - r * E;
-        if (r0 + r < k) tok[((long)b * tok_rows + r0 + r) * E + c] = tile[r][c];
+        if (r0 + r < k) tok[((long)b * tok_rows + r0 + r) * E + c] = bias ? __fadd_rn(tile[r][c], __ldg(bias + c)) : tile[r][c];
     }
     if (t < 96) {
         const int r = t / 3, c = t - 3 * r;
@@ -477,24 +477,24 @@ extern "C" int a3d_traj_topk(const float* traj, int traj_len, const float* pts, 
 
 extern "C" int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, int batch, int ncam,
                                  int embed, int hw, int k, float* tok, float* pos, int tok_rows, int channels_last,
-                                 void* stream) {
+                                 const float* feat_bias, void* stream) {
     A3D_REQUIRE(feat && pcd && tok && pos, "a3d_gather_tokens: null pointer");
     A3D_REQUIRE(batch > 0 && ncam > 0 && hw > 0 && k > 0 && k <= tok_rows, "a3d_gather_tokens: bad sizes (k=%d rows=%d)", k, tok_rows);
     A3D_REQUIRE(idx || k == ncam * hw, "a3d_gather_tokens: identity gather needs k == ncam*hw");
     dim3 grid((k + 31) / 32, batch);
     if (channels_last) {
         if (embed == 60)
-            gather_tokens_nhwc_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+            gather_tokens_nhwc_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows, feat_bias);
         else if (embed == 120)
-            gather_tokens_nhwc_kernel<120><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+            gather_tokens_nhwc_kernel<120><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows, feat_bias);
         else
             A3D_REQUIRE(false, "a3d_gather_tokens: embedding_dim %d not supported (60 or 120)", embed);
         return check_launch("a3d_gather_tokens");
     }
     if (embed == 60)
-        gather_tokens_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+        gather_tokens_kernel<60><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows, feat_bias);
     else if (embed == 120)
-        gather_tokens_kernel<120><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows);
+        gather_tokens_kernel<120><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, pcd, idx, ncam, hw, k, tok, pos, tok_rows, feat_bias);
     else
         A3D_REQUIRE(false, "a3d_gather_tokens: embedding_dim %d not supported (60 or 120)", embed);
     return check_launch("a3d_gather_tokens");

@@ -146,10 +146,11 @@ class Act3D(nn.Module):
         rgb = visible_rgb.reshape(b * num_cameras, *visible_rgb.shape[2:])
         if self.training or not self.fold_trunk or not isinstance(self.backbone, torch.nn.Module) \
                 or isinstance(self.backbone, torch.nn.Identity):
-            feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+            feats, feat_bias = self.feature_pyramid(self.backbone(self.normalize(rgb))), {}
         else:
-            feats = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
-                                     needed=self.feature_map_pyramid[:self.num_sampling_level])
+            feats, feat_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
+                                                needed=self.feature_map_pyramid[:self.num_sampling_level],
+                                                defer_bias=True)
         if staged is not None:      # point clouds were uploaded on the copy stream while the backbone ran
             torch.cuda.current_stream().wait_stream(self._side_stream)
             visible_pcd = staged[0]
@@ -162,6 +163,8 @@ class Act3D(nn.Module):
             fm = feats[self.feature_map_pyramid[i]].float()       # NCHW or channels-last: the gather reads either in place
             feats_pyr.append(fm.unflatten(0, (b, num_cameras)))
             pcd_pyr.append(cache[f])
+        # output-convolution biases that the trunk left to the token gather (None: already applied)
+        self._feat_bias = [feat_bias.get(self.feature_map_pyramid[i]) for i in range(self.num_sampling_level)]
         return feats_pyr, pcd_pyr
 
     # ------------------------------------------------------------------ forward
@@ -233,7 +236,7 @@ class Act3D(nn.Module):
             else:
                 idx = lib.local_topk(carried[-1][:, 0].contiguous(), pcd_pyr[i], n_vis)
             topk_log.append(idx)
-            lib.gather_tokens(fm, pcd_pyr[i], idx, b, ncam, tok, pos)
+            lib.gather_tokens(fm, pcd_pyr[i], idx, b, ncam, tok, pos, bias=self._feat_bias[i])
             tok[:, n_vis] = self.curr_gripper_embed.weight[0]
             pos[:, n_vis] = grip_xyz
 

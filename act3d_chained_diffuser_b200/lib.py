@@ -22,7 +22,12 @@ EXPORTS = {
     "a3d_local_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_traj_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "a3d_trunk_normalize": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), c_int, c_int,
+                                    c_void_p, c_void_p]),
+    "a3d_trunk_maxpool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "a3d_trunk_fpn_topdown": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p]),
     "a3d_kv_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "a3d_ctx_kv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            ctypes.POINTER(c_int), c_int, c_void_p, c_void_p]),
@@ -149,9 +154,10 @@ def traj_topk(traj, pts, k, want_dist=False):
     return (idx, dist) if want_dist else idx
 
 
-def gather_tokens(feat, pcd, idx, batch, ncam, tok, pos):
+def gather_tokens(feat, pcd, idx, batch, ncam, tok, pos, bias=None):
     """feat (B*ncam, E, h, w) -- NCHW-contiguous or channels-last (NHWC storage, read in place) --,
-    pcd (B, ncam*h*w, 3), idx (B,K) int32 or None -> rows [0,K) of tok/pos."""
+    pcd (B, ncam*h*w, 3), idx (B,K) int32 or None -> rows [0,K) of tok/pos.  bias (E,) or None is added to
+    every gathered feature row (the deferred bias of the FPN output convolution)."""
     e, hw = feat.shape[1], feat.shape[2] * feat.shape[3]
     k = idx.shape[1] if idx is not None else ncam * hw
     assert feat.is_cuda and feat.dtype == torch.float32
@@ -162,8 +168,49 @@ def gather_tokens(feat, pcd, idx, batch, ncam, tok, pos):
     else:
         feat, nhwc = feat.contiguous(), 0
     _check(load().a3d_gather_tokens(feat.data_ptr(), _ptr(_f32(pcd)), _ptr(idx), batch, ncam, e, hw, k,
-                                    _ptr(tok), _ptr(pos), tok.shape[1], nhwc, _stream()), "a3d_gather_tokens")
+                                    _ptr(tok), _ptr(pos), tok.shape[1], nhwc, _ptr(_f32(bias)) if bias is not None else None,
+                                    _stream()), "a3d_gather_tokens")
     return k
+
+
+def _nhwc_like(images, channels, h, w, device):
+    """fp32 tensor of logical shape (images, channels, h, w) stored channels-last."""
+    return torch.empty(images, h, w, channels, device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+
+
+def trunk_normalize(rgb, mean, std):
+    """(N,3,H,W) NCHW fp32 -> (x - mean) / std as a channels-last tensor (transforms.Normalize + layout change)."""
+    assert rgb.is_cuda and rgb.dim() == 4 and rgb.shape[1] == 3
+    rgb = _f32(rgb)
+    n, _, h, w = rgb.shape
+    out = _nhwc_like(n, 3, h, w, rgb.device)
+    m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+    _check(load().a3d_trunk_normalize(_ptr(rgb), m3, s3, n, h * w, out.data_ptr(), _stream()), "a3d_trunk_normalize")
+    return out
+
+
+def _as_nhwc(x):
+    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+
+
+def trunk_maxpool(x):
+    """3x3 / stride 2 / padding 1 max-pool of a channels-last (N,C,H,W) map."""
+    x = _as_nhwc(x.float())
+    n, c, h, w = x.shape
+    out = _nhwc_like(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.device)
+    _check(load().a3d_trunk_maxpool(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "a3d_trunk_maxpool")
+    return out
+
+
+def trunk_fpn_topdown(lat, bias, top, out=None):
+    """(lat + bias) + nearest-upsampled top, channels-last maps; written into `out` (default: in place on lat)."""
+    lat, top = _as_nhwc(lat.float()), _as_nhwc(top.float())
+    n, c, h, w = lat.shape
+    out = lat if out is None else out
+    _check(load().a3d_trunk_fpn_topdown(lat.data_ptr(), _ptr(_f32(bias)) if bias is not None else None, top.data_ptr(),
+                                        n, h, w, top.shape[2], top.shape[3], c, out.data_ptr(), _stream()),
+           "a3d_trunk_fpn_topdown")
+    return out
 
 
 def kv_bytes(nsets, batch, nk, heads):

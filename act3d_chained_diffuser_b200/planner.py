@@ -151,9 +151,10 @@ class DiffusionHead(nn.Module):
         w = self._weights(num_timesteps, dev)
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:])
         if self.training or not self.fold_trunk or isinstance(self.backbone, torch.nn.Identity):
-            fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+            fpn, fpn_bias = self.feature_pyramid(self.backbone(self.normalize(rgb))), {}
         else:
-            fpn = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=("res3",))
+            fpn, fpn_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=("res3",),
+                                             defer_bias=True)
         fm = fpn["res3"].float()                                  # NCHW or channels-last: the gather reads either in place
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
@@ -161,7 +162,7 @@ class DiffusionHead(nn.Module):
         rows = nctx + 1 + int(self.use_goal)
         tok = torch.empty(b, rows, e, device=dev)
         pos = torch.empty(b, rows, 3, device=dev)
-        lib.gather_tokens(fm, pts, None, b, ncam, tok, pos)
+        lib.gather_tokens(fm, pts, None, b, ncam, tok, pos, bias=fpn_bias.get("res3"))
 
         ctx = dict(nk=rows, batch=b)
         if self.use_instruction:

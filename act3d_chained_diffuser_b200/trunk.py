@@ -6,8 +6,11 @@ package and its downloaded RN50 weights (reference: model/utils/clip.py:9-43), e
 the reference -- it raises ImportError here when that package is absent.
 """
 import torch
+from torch.nn.modules.utils import _pair
 from torchvision import transforms
 from torchvision.models.resnet import Bottleneck, ResNet
+
+from . import lib
 
 
 class ResNetStages(ResNet):
@@ -65,6 +68,9 @@ class EvalTrunk:
       * for torchvision ResNets, cuDNN's fused conv+bias+ReLU and conv+bias+residual+ReLU entry points
         (`torch.cudnn_convolution_relu`, `torch.cudnn_convolution_add_relu`) instead of separate bias / add /
         clamp kernels;
+      * the memory-bound glue around the convolutions as single-pass kernels of this library (input
+        normalisation + layout, the stem max-pool, the FPN top-down merge with the lateral bias folded in) and
+        the shortcut / output-convolution biases folded or deferred instead of separate elementwise launches;
       * only the FPN levels the model reads are computed (the reference evaluates all five output
         convolutions and discards three of them).
     Only used in eval mode: while training, the reference keeps the frozen backbone's BN in train mode
@@ -113,7 +119,10 @@ class EvalTrunk:
             blocks = []
             for blk in stage:
                 down = self._conv_args(blk.downsample[0]) if blk.downsample is not None else None
-                blocks.append((self._conv_args(blk.conv1), self._conv_args(blk.conv2), self._conv_args(blk.conv3), down))
+                c3 = self._conv_args(blk.conv3)
+                if down is not None:     # relu(conv3 + b3 + (down + bd)) = relu(conv3 + (b3 + bd) + down_nobias)
+                    c3 = (c3[0], c3[1] + down[1]) + c3[2:]
+                blocks.append((self._conv_args(blk.conv1), self._conv_args(blk.conv2), c3, down))
             plan["stages"].append(blocks)
         return plan
 
@@ -122,10 +131,17 @@ class EvalTrunk:
         cr, car = torch.cudnn_convolution_relu, torch.cudnn_convolution_add_relu
         stem = cr(x, *plan["stem"])
         feats = {"res1": stem}
-        y = plan["pool"](stem)
+        pool = plan["pool"]
+        if (_pair(pool.kernel_size), _pair(pool.stride), _pair(pool.padding), _pair(pool.dilation), pool.ceil_mode) == \
+                ((3, 3), (2, 2), (1, 1), (1, 1), False) and stem.shape[1] % 4 == 0:
+            y = lib.trunk_maxpool(stem)               # one NHWC pass (ATen's NHWC pool runs at ~1.2 TB/s here)
+        else:
+            y = pool(stem)
         for i, blocks in enumerate(plan["stages"]):
             for c1, c2, c3, down in blocks:
-                ident = y if down is None else torch.nn.functional.conv2d(y, down[0], down[1], down[2], down[3], down[4], down[5])
+                # projection shortcut: its (BN-folded) bias is carried by conv3's bias (plan), so the
+                # shortcut convolution runs bias-free instead of paying a separate elementwise add
+                ident = y if down is None else torch.nn.functional.conv2d(y, down[0], None, down[2], down[3], down[4], down[5])
                 o = cr(y, *c1)
                 o = cr(o, *c2)
                 y = car(o, c3[0], ident, 1.0, c3[1], c3[2], c3[3], c3[4], c3[5])
@@ -133,40 +149,56 @@ class EvalTrunk:
         return feats
 
     @staticmethod
-    def _run_fpn(fpn, feats, needed):
+    def _run_fpn(fpn, feats, needed, defer_bias):
         """torchvision FeaturePyramidNetwork.forward restricted to the requested output levels
-        (identical arithmetic for those levels)."""
+        (identical arithmetic for those levels).  The top-down merge  (lateral conv + bias) + upsample(top)
+        is one kernel (lib.trunk_fpn_topdown) fed by a bias-free lateral convolution; with `defer_bias` the
+        bias of the 3x3 output convolutions is not applied to the full map but returned, and the token
+        gather adds it to the rows it reads."""
         names = list(feats.keys())
         lowest = min(names.index(n) for n in needed)
         conv = torch.nn.functional.conv2d
-
-        def inner(i):
-            m = fpn.inner_blocks[i][0]
-            return conv(feats[names[i]], m.weight, m.bias)
+        fusable = fpn.inner_blocks[0][0].out_channels % 4 == 0
 
         def layer(i, t):
             m = fpn.layer_blocks[i][0]
+            if defer_bias:
+                biases[names[i]] = m.bias
+                return conv(t, m.weight, None, padding=1)
             return conv(t, m.weight, m.bias, padding=1)
-        out = {}
-        last = inner(len(names) - 1)
+        out, biases = {}, {}
+        top = fpn.inner_blocks[len(names) - 1][0]
+        last = conv(feats[names[-1]], top.weight, top.bias)
         if names[-1] in needed:
             out[names[-1]] = layer(len(names) - 1, last)
         for i in range(len(names) - 2, lowest - 1, -1):
-            lat = inner(i)
-            last = lat + torch.nn.functional.interpolate(last, size=lat.shape[-2:], mode="nearest")
+            m = fpn.inner_blocks[i][0]
+            if fusable:
+                last = lib.trunk_fpn_topdown(conv(feats[names[i]], m.weight, None), m.bias, last)
+            else:
+                lat = conv(feats[names[i]], m.weight, m.bias)
+                last = lat + torch.nn.functional.interpolate(last, size=lat.shape[-2:], mode="nearest")
             if names[i] in needed:
                 out[names[i]] = layer(i, last)
-        return out
+        return (out, biases) if defer_bias else out
 
-    def __call__(self, normalize, backbone, fpn, rgb, needed=("res1", "res3")):
+    def __call__(self, normalize, backbone, fpn, rgb, needed=("res1", "res3"), defer_bias=False):
+        """Returns {level: map}; with defer_bias=True returns ({level: map without the output-conv bias},
+        {level: bias}) for consumers that add the bias themselves (lib.gather_tokens)."""
         sig = self._signature(backbone)
         if self._fused is None or sig != self._sig:
             self._fused, self._sig = self._fold_modules(backbone), sig
             self._plan = self._resnet_plan(self._fused) if isinstance(backbone, ResNet) else None
-        x = normalize(rgb).contiguous(memory_format=torch.channels_last)
+        if rgb.is_cuda and isinstance(normalize, transforms.Normalize) and rgb.shape[1] == 3 and len(normalize.mean) == 3:
+            x = lib.trunk_normalize(rgb.float().contiguous(), normalize.mean, normalize.std)
+        else:
+            x = normalize(rgb).contiguous(memory_format=torch.channels_last)
         if self._plan is not None and self._fused_ok and x.is_cuda:
             try:
-                return self._run_fpn(fpn, self._run_resnet(self._plan, x), set(needed))
-            except RuntimeError:          # cuDNN fused entry points unavailable for this build / shape
+                return self._run_fpn(fpn, self._run_resnet(self._plan, x), set(needed), defer_bias)
+            except RuntimeError as exc:   # cuDNN fused entry points unavailable for this build / shape
+                if "libact3d_b200" in str(exc) or "a3d_" in str(exc):
+                    raise
                 self._fused_ok = False
-        return fpn(self._fused(x))
+        out = fpn(self._fused(x))
+        return (out, {}) if defer_bias else out

@@ -75,10 +75,31 @@ int a3d_traj_topk(const float* traj, int traj_len, const float* pts, int batch, 
  * feat [B*ncam][E][hw] (channels_last = 0) or [B*ncam][hw][E] (channels_last = 1, the NHWC layout cuDNN
  * leaves the FPN output in: one contiguous row per token), pcd [B][ncam*hw][3], idx [B][K] or NULL
  * (identity, K = ncam*hw).  Writes rows [0,K) of tok [B][tok_rows][E] and pos [B][tok_rows][3].
+ * feat_bias [E] or NULL: per-channel bias added to every gathered feature row -- the bias of the FPN
+ * output convolution, deferred from the full 128 x 128 map to the rows that are actually read.
  */
 int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, int batch, int ncam,
                       int embed, int hw, int k, float* tok, float* pos, int tok_rows, int channels_last,
-                      void* stream);
+                      const float* feat_bias, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Memory-bound glue of the image trunk; the convolutions themselves stay on cuDNN.  All maps are
+ * fp32 NHWC ([images][h][w][channels]); results are bit-identical to the ATen ops they replace.
+ *
+ * a3d_trunk_normalize: out[n][p][c] = (rgb[n][c][p] - mean[c]) / std[c] for the 3 colour planes
+ *   (NCHW in, NHWC out).  Replaces transforms.Normalize (act3d.py:62, diffusion_head.py:40) and the
+ *   channels-last conversion.  mean / std are HOST arrays of 3 floats.
+ * a3d_trunk_maxpool: 3x3, stride 2, padding 1 (the ResNet stem pool, utils/resnet.py:44);
+ *   out [images][(h-1)/2+1][(w-1)/2+1][channels]; channels % 4 == 0.
+ * a3d_trunk_fpn_topdown: out = (lat + bias) + nearest_upsample(top) -- the top-down merge of
+ *   torchvision's FeaturePyramidNetwork.forward with the lateral 1x1 convolution's bias folded in
+ *   (bias may be NULL); lat/out [images][h][w][channels] (out may alias lat), top
+ *   [images][top_h][top_w][channels]; channels % 4 == 0. */
+int a3d_trunk_normalize(const float* rgb, const float* mean_host, const float* std_host, int images, int hw,
+                        float* out, void* stream);
+int a3d_trunk_maxpool(const float* in, int images, int h, int w, int channels, float* out, void* stream);
+int a3d_trunk_fpn_topdown(const float* lat, const float* bias, const float* top, int images, int h, int w,
+                          int top_h, int top_w, int channels, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Context K/V cache.  Replaces, for `nsets` attention layers that share one context,

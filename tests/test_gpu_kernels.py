@@ -325,3 +325,53 @@ def test_gather_tokens_channels_last(lib):
         lib.gather_tokens(feat.cuda().contiguous(memory_format=fmt), dev(pcd), dev(idx), b, ncam, tok, pos)
         out.append((tok.cpu(), pos.cpu()))
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_gather_tokens_deferred_bias(lib):
+    b, ncam, e = 2, 2, 60
+    feat = synth.normal("g3.feat", (b * ncam, e, 16, 16))
+    bias = synth.normal("g3.bias", (e,))
+    pcd = synth.points_in_bounds("g3.pcd", (b, ncam * 256))
+    idx = torch.from_numpy(np.stack([synth.rng_for(f"g3.idx{i}").permutation(ncam * 256)[:77] for i in range(b)])).int()
+    want = (feat + bias.view(1, e, 1, 1)).view(b, ncam, e, 256).permute(0, 1, 3, 2).reshape(b, ncam * 256, e)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        tok = torch.zeros(b, 80, e).cuda()
+        pos = torch.zeros(b, 80, 3).cuda()
+        lib.gather_tokens(feat.cuda().contiguous(memory_format=fmt), dev(pcd), dev(idx), b, ncam, tok, pos, bias=dev(bias))
+        for i in range(b):
+            assert torch.equal(tok[i, :77].cpu(), want[i][idx[i].long()])
+
+
+# ------------------------------------------------------------------------------- trunk glue
+def test_trunk_normalize_bit_exact(lib):
+    from torchvision import transforms
+    x = synth.uniform("tn.rgb", (5, 3, 37, 41))
+    norm = transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    got = lib.trunk_normalize(dev(x), norm.mean, norm.std)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got.cpu(), norm(x))
+    assert torch.equal(got.cpu(), norm(dev(x)).cpu())
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 32, 32), (2, 8, 17, 23), (1, 4, 1, 5)])
+def test_trunk_maxpool_bit_exact(lib, shape):
+    x = synth.normal("tp.x", shape)
+    want = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+    got = lib.trunk_maxpool(dev(x).contiguous(memory_format=torch.channels_last))
+    assert got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("hw,thw", [((16, 16), (8, 8)), ((15, 9), (8, 5)), ((12, 20), (4, 7))])
+def test_trunk_fpn_topdown_bit_exact(lib, hw, thw):
+    n, c = 3, 60
+    lat = synth.normal("tf.lat", (n, c, *hw))
+    top = synth.normal("tf.top", (n, c, *thw))
+    bias = synth.normal("tf.bias", (c,))
+    want = (lat + bias.view(1, c, 1, 1)) + torch.nn.functional.interpolate(top, size=hw, mode="nearest")
+    cl = torch.channels_last
+    got = lib.trunk_fpn_topdown(dev(lat).contiguous(memory_format=cl), dev(bias), dev(top).contiguous(memory_format=cl))
+    assert torch.equal(got.cpu(), want)
+    want_nobias = lat + torch.nn.functional.interpolate(top, size=hw, mode="nearest")
+    got = lib.trunk_fpn_topdown(dev(lat).contiguous(memory_format=cl), None, dev(top).contiguous(memory_format=cl))
+    assert torch.equal(got.cpu(), want_nobias)

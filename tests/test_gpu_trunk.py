@@ -37,5 +37,14 @@ def test_fused_eval_trunk_matches_plain_modules():
         for k in fused:
             rel = ((fused[k].float() - plain[k]).norm() / plain[k].norm()).item()
             assert rel < 2e-5, (k, rel)
+        # deferred output-conv bias: map + bias must reproduce the full map
+        with torch.no_grad():
+            maps, biases = m._eval_trunk(m.normalize, m.backbone, m.feature_pyramid, x, needed=("res3", "res1"),
+                                         defer_bias=True)
+        assert set(biases) == {"res1", "res3"}
+        for k in maps:
+            full = maps[k].float() + biases[k].view(1, -1, 1, 1)
+            rel = ((full - plain[k]).norm() / plain[k].norm()).item()
+            assert rel < 2e-5, (k, rel)
     finally:
         torch.backends.cudnn.allow_tf32 = True
