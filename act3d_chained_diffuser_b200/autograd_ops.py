@@ -1,0 +1,96 @@
+"""torch.autograd bindings of the training kernels (csrc/a3d_train.cu).
+
+Training keeps the reference's parameterisation (ordinary nn.Parameters, stock DDP gradient
+all-reduce, engine.py:121-124) and replaces the memory-heavy part of its autograd graph -- the
+(B*H, Nq, Nk) attention scores, their softmax and both gradients, and the full-map rotary tables
+(multihead_custom_attention.py:391-415, position_encodings.py:58-97) -- by kernels that recompute
+probabilities tile by tile.  Everything here is CUDA-only: there is no eager fallback.
+"""
+import torch
+
+from . import lib
+
+
+def _seed_from_torch():
+    """Dropout seed drawn from torch's CPU generator: follows torch.manual_seed, costs no device sync."""
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+class _RopeApply(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        x = x.contiguous()
+        pos = pos.contiguous().float()
+        ctx.save_for_backward(pos)
+        return lib.rope_apply(x, pos, transpose=False)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (pos,) = ctx.saved_tensors
+        return lib.rope_apply(grad.contiguous(), pos, transpose=True), None
+
+
+def rope_apply(x, pos):
+    """x (B, N, E) fp32, pos (B, N, 3): 3-D rotary embedding of the full E vector
+    (position_encodings.py:31-34 over the table of :58-97; positions carry no gradient)."""
+    return _RopeApply.apply(x, pos)
+
+
+class _AttnCore(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_mask, heads, dropout_p, seed):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = lib.attn_fwd(q, k, v, key_mask, heads, dropout_p, seed)
+        ctx.save_for_backward(q, k, v, o, lse, key_mask if key_mask is not None else torch.empty(0))
+        ctx.heads, ctx.dropout_p, ctx.seed, ctx.has_mask = heads, dropout_p, seed, key_mask is not None
+        return o
+
+    @staticmethod
+    def backward(ctx, grad):
+        q, k, v, o, lse, key_mask = ctx.saved_tensors
+        dq, dk, dv = lib.attn_bwd(q, k, v, key_mask if ctx.has_mask else None, o, grad.contiguous(), lse, ctx.heads,
+                                  ctx.dropout_p, ctx.seed)
+        return dq, dk, dv, None, None, None, None
+
+
+def attention_core(q, k, v, heads, key_padding_mask=None, dropout_p=0.0):
+    """softmax(q k^T [+ -inf on masked keys]) v per head without the score tensor.
+    q (B, Nq, E) already scaled and rotated, k / v (B, Nk, E); head h = channels [15h, 15h+15)
+    (multihead_custom_attention.py:355-359, 391-415).  key_padding_mask (B, Nk) bool, True = ignore."""
+    mask = None
+    if key_padding_mask is not None:
+        mask = key_padding_mask.to(device=q.device, dtype=torch.uint8).contiguous()
+    seed = _seed_from_torch() if dropout_p > 0.0 else 0
+    return _AttnCore.apply(q, k, v, mask, heads, float(dropout_p), seed)
+
+
+class _GatherTokens(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, feat, pcd, idx, batch, ncam, k):
+        e = feat.shape[1]
+        tok = torch.empty(batch, k, e, device=feat.device)
+        pos = torch.empty(batch, k, 3, device=feat.device)
+        if not (feat.is_contiguous() or feat.is_contiguous(memory_format=torch.channels_last)):
+            feat = feat.contiguous()
+        lib.gather_tokens(feat, pcd, idx, batch, ncam, tok, pos)
+        ctx.save_for_backward(idx if idx is not None else torch.empty(0, dtype=torch.int32))
+        ctx.meta = (batch, ncam, k, idx is not None, tuple(feat.shape), not feat.is_contiguous())
+        ctx.mark_non_differentiable(pos)
+        return tok, pos
+
+    @staticmethod
+    def backward(ctx, dtok, _dpos):
+        (idx,) = ctx.saved_tensors
+        batch, ncam, k, has_idx, shape, channels_last = ctx.meta
+        dfeat = lib.gather_tokens_bwd(dtok.contiguous(), idx if has_idx else None, batch, ncam, k, shape, channels_last)
+        return dfeat, None, None, None, None, None
+
+
+def gather_tokens(feat, pcd, idx, batch, ncam):
+    """feat (B*ncam, E, h, w) [requires grad], pcd (B, ncam*h*w, 3), idx (B, K) int32 or None ->
+    tok (B, K, E) differentiable w.r.t. feat, pos (B, K, 3)   (act3d.py:236-254)."""
+    k = idx.shape[1] if idx is not None else ncam * feat.shape[2] * feat.shape[3]
+    return _GatherTokens.apply(feat, pcd, idx, batch, ncam, k)

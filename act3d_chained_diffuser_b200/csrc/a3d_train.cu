@@ -1,0 +1,444 @@
+// Training path of libact3d_b200: the attention core with its backward, rotary apply (forward and
+// transposed), and the token gather's backward.  All fp32 on the CUDA cores: training batches are two
+// orders of magnitude smaller than the inference workload (333 ghost points per level instead of
+// 16384) and gradients need fp32-class accuracy, so these kernels favour exactness and
+// simplicity; the tensor-core kernels (a3d_xattn2.cu, cd_denoiser.cu) stay the inference path.
+//
+// Attention core = softmax(q k^T [+ key padding]) v per head, head_dim 15, without ever materialising the
+// (B*H, Nq, Nk) score tensor the reference builds (multihead_custom_attention.py:391-415):
+//   forward  : one lane per query row, 4 warps split every 64-key tile, online softmax, log-sum-exp saved;
+//   backward : recomputes p = exp(s - lse) tile by tile (flash-attention style):
+//                dq kernel  (row-parallel):  ds = p (dO.v - D),  dq += ds k,    D = dO.O
+//                dkv kernel (key-parallel):  dv += p dO,         dk += ds q     (atomics over query chunks)
+// Dropout on the attention weights (p = 0.1 in ChainedDiffuser training, multihead_custom_attention.py:413)
+// is a counter-based Bernoulli keyed on (seed, b, h, row, key): the same mask is regenerated in backward.
+#include "a3d_common.cuh"
+
+namespace a3d {
+namespace {
+
+constexpr int HD = kHeadDim;       // 15
+constexpr int kRows = 32;          // query rows per CTA (one per lane)
+constexpr int kSplit = 4;          // warps per CTA; each takes 16 keys of every tile
+constexpr int kTile = 64;          // keys per shared-memory tile
+constexpr int kKeysPerWarp = kTile / kSplit;
+constexpr int kQChunk = 256;       // query rows per dkv CTA (grid.z splits the rest)
+
+__device__ __forceinline__ uint32_t drop_bits(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+struct Tile {
+    float k[kTile][16];
+    float v[kTile][16];
+    int live[kTile];
+};
+
+// K/V rows [t0, t0+64) of head h, sample b -> shared memory (15 floats per row, slot 15 = 0)
+__device__ __forceinline__ void load_tile(Tile& t, const float* __restrict__ k, const float* __restrict__ v,
+                                          const unsigned char* __restrict__ mask, int b, int h, int nk, int E, int t0) {
+    for (int i = threadIdx.x; i < kTile * 16; i += kRows * kSplit) {
+        const int key = i >> 4, d = i & 15, gk = t0 + key;
+        float kk = 0.f, vv = 0.f;
+        if (gk < nk && d < HD) {
+            const long off = ((long)b * nk + gk) * E + h * HD + d;
+            kk = __ldg(k + off);
+            vv = __ldg(v + off);
+        }
+        t.k[key][d] = kk;
+        t.v[key][d] = vv;
+    }
+    if (threadIdx.x < kTile) {
+        const int gk = t0 + threadIdx.x;
+        t.live[threadIdx.x] = (gk < nk) && !(mask && mask[(long)b * nk + gk]);
+    }
+}
+
+__device__ __forceinline__ float dot15(const float (&a)[HD], const float* __restrict__ row) {
+    const float4 r0 = *reinterpret_cast<const float4*>(row), r1 = *reinterpret_cast<const float4*>(row + 4),
+                 r2 = *reinterpret_cast<const float4*>(row + 8), r3 = *reinterpret_cast<const float4*>(row + 12);
+    float s = a[0] * r0.x;
+    s = fmaf(a[1], r0.y, s); s = fmaf(a[2], r0.z, s); s = fmaf(a[3], r0.w, s);
+    s = fmaf(a[4], r1.x, s); s = fmaf(a[5], r1.y, s); s = fmaf(a[6], r1.z, s); s = fmaf(a[7], r1.w, s);
+    s = fmaf(a[8], r2.x, s); s = fmaf(a[9], r2.y, s); s = fmaf(a[10], r2.z, s); s = fmaf(a[11], r2.w, s);
+    s = fmaf(a[12], r3.x, s); s = fmaf(a[13], r3.y, s); s = fmaf(a[14], r3.z, s);
+    return s;
+}
+__device__ __forceinline__ void axpy15(float (&acc)[HD], float a, const float* __restrict__ row) {
+    const float4 r0 = *reinterpret_cast<const float4*>(row), r1 = *reinterpret_cast<const float4*>(row + 4),
+                 r2 = *reinterpret_cast<const float4*>(row + 8), r3 = *reinterpret_cast<const float4*>(row + 12);
+    acc[0] = fmaf(a, r0.x, acc[0]); acc[1] = fmaf(a, r0.y, acc[1]); acc[2] = fmaf(a, r0.z, acc[2]);
+    acc[3] = fmaf(a, r0.w, acc[3]); acc[4] = fmaf(a, r1.x, acc[4]); acc[5] = fmaf(a, r1.y, acc[5]);
+    acc[6] = fmaf(a, r1.z, acc[6]); acc[7] = fmaf(a, r1.w, acc[7]); acc[8] = fmaf(a, r2.x, acc[8]);
+    acc[9] = fmaf(a, r2.y, acc[9]); acc[10] = fmaf(a, r2.z, acc[10]); acc[11] = fmaf(a, r2.w, acc[11]);
+    acc[12] = fmaf(a, r3.x, acc[12]); acc[13] = fmaf(a, r3.y, acc[13]); acc[14] = fmaf(a, r3.z, acc[14]);
+}
+
+// ================================================================================ forward
+// grid (ceil(nq/32), B*H), 128 threads.  q/o [B][nq][E], k/v [B][nk][E] (head h = columns h*15..h*15+14),
+// lse [B*H][nq].
+template <bool kDrop>
+__global__ void __launch_bounds__(kRows* kSplit) attn_fwd_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const unsigned char* __restrict__ mask, int H, int nq, int nk, int E, float* __restrict__ o,
+    float* __restrict__ lse, uint32_t drop_thresh, float keep_scale, uint64_t seed) {
+    __shared__ __align__(16) Tile tile;
+    __shared__ float part[kSplit][kRows][HD + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int row = blockIdx.x * kRows + lane;
+    const bool live = row < nq;
+
+    float qr[HD], acc[HD];
+    {
+        const float* qp = q + ((long)b * nq + (live ? row : 0)) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            qr[d] = live ? __ldg(qp + d) : 0.f;
+            acc[d] = 0.f;
+        }
+    }
+    float m = -INFINITY, l = 0.f;
+    const uint64_t drop_row = ((uint64_t)bh * nq + (uint64_t)(live ? row : 0)) * (uint64_t)nk;
+
+    for (int t0 = 0; t0 < nk; t0 += kTile) {
+        __syncthreads();
+        load_tile(tile, k, v, mask, b, h, nk, E, t0);
+        __syncthreads();
+        float s[kKeysPerWarp];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kKeysPerWarp; ++j) {
+            const int key = warp * kKeysPerWarp + j;
+            const float a = dot15(qr, tile.k[key]);
+            s[j] = tile.live[key] ? a : -INFINITY;
+            cmax = fmaxf(cmax, s[j]);
+        }
+        if (cmax > m) {
+            const float r = __expf(m - cmax);      // m = -inf -> 0
+            l *= r;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] *= r;
+            m = cmax;
+        }
+        if (m > -INFINITY) {
+#pragma unroll
+            for (int j = 0; j < kKeysPerWarp; ++j) {
+                const int key = warp * kKeysPerWarp + j;
+                float p = __expf(s[j] - m);        // masked key: exp(-inf) = 0
+                l += p;
+                if (kDrop) {
+                    const bool keep = drop_bits(seed, drop_row + (uint64_t)(t0 + key)) >= drop_thresh;
+                    p = keep ? p * keep_scale : 0.f;
+                }
+                axpy15(acc, p, tile.v[key]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) part[warp][lane][d] = acc[d];
+    part[warp][lane][HD] = m;
+    part[warp][lane][HD + 1] = l;
+    __syncthreads();
+    if (warp == 0 && live) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kSplit; ++w) M = fmaxf(M, part[w][lane][HD]);
+        float L = 0.f, out[HD];
+#pragma unroll
+        for (int d = 0; d < HD; ++d) out[d] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSplit; ++w) {
+            const float mw = part[w][lane][HD];
+            const float sc = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+            L = fmaf(part[w][lane][HD + 1], sc, L);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) out[d] = fmaf(part[w][lane][d], sc, out[d]);
+        }
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        float* op = o + ((long)b * nq + row) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) op[d] = out[d] * inv;
+        lse[(long)bh * nq + row] = L > 0.f ? M + logf(L) : 0.f;
+    }
+}
+
+// ================================================================================ backward: dq (+ D)
+template <bool kDrop>
+__global__ void __launch_bounds__(kRows* kSplit) attn_bwd_dq_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const unsigned char* __restrict__ mask, const float* __restrict__ o, const float* __restrict__ dout,
+    const float* __restrict__ lse, int H, int nq, int nk, int E, float* __restrict__ dq, float* __restrict__ dsum,
+    uint32_t drop_thresh, float keep_scale, uint64_t seed) {
+    __shared__ __align__(16) Tile tile;
+    __shared__ float part[kSplit][kRows][HD + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int row = blockIdx.x * kRows + lane;
+    const bool live = row < nq;
+
+    float qr[HD], gr[HD], acc[HD];
+    float D = 0.f, ls = 0.f;
+    {
+        const long base = ((long)b * nq + (live ? row : 0)) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            qr[d] = live ? __ldg(q + base + d) : 0.f;
+            gr[d] = live ? __ldg(dout + base + d) : 0.f;
+            const float ov = live ? __ldg(o + base + d) : 0.f;
+            D = fmaf(gr[d], ov, D);
+            acc[d] = 0.f;
+        }
+        if (live) ls = lse[(long)bh * nq + row];
+    }
+    const uint64_t drop_row = ((uint64_t)bh * nq + (uint64_t)(live ? row : 0)) * (uint64_t)nk;
+
+    for (int t0 = 0; t0 < nk; t0 += kTile) {
+        __syncthreads();
+        load_tile(tile, k, v, mask, b, h, nk, E, t0);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < kKeysPerWarp; ++j) {
+            const int key = warp * kKeysPerWarp + j;
+            if (!tile.live[key]) continue;                     // uniform across the warp
+            const float p = __expf(dot15(qr, tile.k[key]) - ls);
+            float dp = dot15(gr, tile.v[key]);
+            if (kDrop) {
+                const bool keep = drop_bits(seed, drop_row + (uint64_t)(t0 + key)) >= drop_thresh;
+                dp = keep ? dp * keep_scale : 0.f;
+            }
+            axpy15(acc, p * (dp - D), tile.k[key]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) part[warp][lane][d] = acc[d];
+    __syncthreads();
+    if (warp == 0 && live) {
+        float* dp = dq + ((long)b * nq + row) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) dp[d] = (part[0][lane][d] + part[1][lane][d]) + (part[2][lane][d] + part[3][lane][d]);
+        dsum[(long)bh * nq + row] = D;
+    }
+}
+
+// ================================================================================ backward: dk, dv
+// grid (ceil(nk/128), B*H, query chunks), 128 threads = 128 keys.  dk/dv [B][nk][E] must be zero-filled by
+// the caller; every CTA adds its chunk's contribution with fp32 atomics.
+struct QTile {
+    float q[kRows][16];
+    float g[kRows][16];
+    float lse[kRows];
+    float dsum[kRows];
+};
+
+template <bool kDrop>
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const unsigned char* __restrict__ mask, const float* __restrict__ dout, const float* __restrict__ lse,
+    const float* __restrict__ dsum, int H, int nq, int nk, int E, float* __restrict__ dk, float* __restrict__ dv,
+    uint32_t drop_thresh, float keep_scale, uint64_t seed) {
+    __shared__ __align__(16) QTile qt;
+    const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+    const int key = blockIdx.x * 128 + threadIdx.x;
+    const bool valid = key < nk && !(mask && mask[(long)b * nk + key]);
+    const int r_begin = blockIdx.z * kQChunk;
+    const int r_end = min(nq, r_begin + kQChunk);
+
+    float kr[HD], vr[HD], gk[HD], gv[HD];
+    {
+        const long base = ((long)b * nk + (key < nk ? key : 0)) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            kr[d] = valid ? __ldg(k + base + d) : 0.f;
+            vr[d] = valid ? __ldg(v + base + d) : 0.f;
+            gk[d] = 0.f;
+            gv[d] = 0.f;
+        }
+    }
+    for (int r0 = r_begin; r0 < r_end; r0 += kRows) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kRows * 16; i += 128) {
+            const int r = i >> 4, d = i & 15, grow = r0 + r;
+            float qq = 0.f, gg = 0.f;
+            if (grow < r_end && d < HD) {
+                const long off = ((long)b * nq + grow) * E + h * HD + d;
+                qq = __ldg(q + off);
+                gg = __ldg(dout + off);
+            }
+            qt.q[r][d] = qq;
+            qt.g[r][d] = gg;
+        }
+        if (threadIdx.x < kRows) {
+            const int grow = r0 + threadIdx.x;
+            qt.lse[threadIdx.x] = grow < r_end ? lse[(long)bh * nq + grow] : 0.f;
+            qt.dsum[threadIdx.x] = grow < r_end ? dsum[(long)bh * nq + grow] : 0.f;
+        }
+        __syncthreads();
+        const int nrows = min(kRows, r_end - r0);
+        if (valid) {
+            for (int r = 0; r < nrows; ++r) {
+                const float p = __expf(dot15(kr, qt.q[r]) - qt.lse[r]);
+                float dp = dot15(vr, qt.g[r]);
+                float pd = p;
+                if (kDrop) {
+                    const uint64_t idx = ((uint64_t)bh * nq + (uint64_t)(r0 + r)) * (uint64_t)nk + (uint64_t)key;
+                    const bool keep = drop_bits(seed, idx) >= drop_thresh;
+                    pd = keep ? p * keep_scale : 0.f;
+                    dp = keep ? dp * keep_scale : 0.f;
+                }
+                axpy15(gv, pd, qt.g[r]);
+                axpy15(gk, p * (dp - qt.dsum[r]), qt.q[r]);
+            }
+        }
+    }
+    if (valid) {
+        const long base = ((long)b * nk + key) * E + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            atomicAdd(dk + base + d, gk[d]);
+            atomicAdd(dv + base + d, gv[d]);
+        }
+    }
+}
+
+// ================================================================================ rotary apply
+// out[2i] = x[2i] c - x[2i+1] s,  out[2i+1] = x[2i+1] c + x[2i] s   (position_encodings.py:31-34) with the
+// angle of pair i taken from xyz as in RotaryPositionEncoding3D (position_encodings.py:58-97).
+// sign = -1 applies the transposed (= inverse) rotation: the backward of sign = +1.
+template <int E>
+__global__ void __launch_bounds__(256) rope_apply_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                         long rows, float sign, float* __restrict__ out) {
+    constexpr int P = E / 2;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * P) return;
+    const long row = i / P;
+    const int pr = (int)(i - row * P);
+    const int axis = (2 * pr) / (E / 3);
+    const int j = pr - axis * (E / 6);
+    const float ang = __fmul_rn(__ldg(pos + row * 3 + axis), rope_freq<E>(j));
+    float s, c;
+    sincosf(ang, &s, &c);
+    s *= sign;
+    const float2 xv = *reinterpret_cast<const float2*>(x + row * E + 2 * pr);
+    float2 ov;
+    ov.x = xv.x * c - xv.y * s;
+    ov.y = xv.y * c + xv.x * s;
+    *reinterpret_cast<float2*>(out + row * E + 2 * pr) = ov;
+}
+
+// ================================================================================ token gather backward
+// dfeat[(b*ncam + cam)][c][pix] (NCHW) or [(b*ncam + cam)][pix][c] (NHWC) += dtok[b][r][c] for r < k, where
+// (cam, pix) = divmod(idx[b][r] or r, hw).  top-k indices are unique per sample, so plain adds would do;
+// atomics keep the kernel correct for arbitrary index lists.
+__global__ void __launch_bounds__(256) gather_tokens_bwd_kernel(const float* __restrict__ dtok, const int32_t* __restrict__ idx,
+                                                                int ncam, int E, int hw, int k, int tok_rows,
+                                                                int channels_last, float* __restrict__ dfeat, long total) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % E);
+    const long br = i / E;
+    const int r = (int)(br % k);
+    const int b = (int)(br / k);
+    const int src = idx ? idx[(long)b * k + r] : r;
+    const int cam = src / hw, pix = src - cam * hw;
+    const float g = dtok[((long)b * tok_rows + r) * E + c];
+    const long img = (long)b * ncam + cam;
+    const long off = channels_last ? (img * hw + pix) * E + c : (img * E + c) * hw + pix;
+    atomicAdd(dfeat + off, g);
+}
+
+int drop_args(float p, uint32_t* thresh, float* scale) {
+    if (p <= 0.f) {
+        *thresh = 0;
+        *scale = 1.f;
+        return 0;
+    }
+    const double t = (double)p * 4294967296.0;
+    *thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    *scale = 1.f / (1.f - p);
+    return 1;
+}
+
+}  // namespace
+}  // namespace a3d
+
+using namespace a3d;
+
+extern "C" int a3d_attn_fwd(const float* q, const float* k, const float* v, const unsigned char* key_mask, int batch,
+                            int heads, int nq, int nk, int embed, float* o, float* lse, float dropout_p,
+                            uint64_t seed, void* stream) {
+    A3D_REQUIRE(q && k && v && o && lse, "a3d_attn_fwd: null pointer");
+    A3D_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0, "a3d_attn_fwd: bad sizes");
+    A3D_REQUIRE(embed == heads * HD, "a3d_attn_fwd: built for head_dim 15 (embed=%d heads=%d)", embed, heads);
+    A3D_REQUIRE(batch * heads <= 65535, "a3d_attn_fwd: batch*heads=%d exceeds 65535", batch * heads);
+    A3D_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "a3d_attn_fwd: dropout_p=%f not in [0,1)", dropout_p);
+    uint32_t th;
+    float sc;
+    const int drop = drop_args(dropout_p, &th, &sc);
+    dim3 grid((nq + kRows - 1) / kRows, batch * heads);
+    if (drop)
+        attn_fwd_kernel<true><<<grid, kRows * kSplit, 0, (cudaStream_t)stream>>>(q, k, v, key_mask, heads, nq, nk, embed, o, lse, th, sc, seed);
+    else
+        attn_fwd_kernel<false><<<grid, kRows * kSplit, 0, (cudaStream_t)stream>>>(q, k, v, key_mask, heads, nq, nk, embed, o, lse, th, sc, seed);
+    return check_launch("a3d_attn_fwd");
+}
+
+extern "C" int a3d_attn_bwd(const float* q, const float* k, const float* v, const unsigned char* key_mask,
+                            const float* o, const float* dout, const float* lse, int batch, int heads, int nq, int nk,
+                            int embed, float* dq, float* dk, float* dv, float* dsum, float dropout_p, uint64_t seed,
+                            void* stream) {
+    A3D_REQUIRE(q && k && v && o && dout && lse && dq && dk && dv && dsum, "a3d_attn_bwd: null pointer");
+    A3D_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0, "a3d_attn_bwd: bad sizes");
+    A3D_REQUIRE(embed == heads * HD, "a3d_attn_bwd: built for head_dim 15 (embed=%d heads=%d)", embed, heads);
+    A3D_REQUIRE(batch * heads <= 65535, "a3d_attn_bwd: batch*heads=%d exceeds 65535", batch * heads);
+    A3D_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "a3d_attn_bwd: dropout_p=%f not in [0,1)", dropout_p);
+    uint32_t th;
+    float sc;
+    const int drop = drop_args(dropout_p, &th, &sc);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g1((nq + kRows - 1) / kRows, batch * heads);
+    const int chunks = (nq + kQChunk - 1) / kQChunk;
+    A3D_REQUIRE(chunks <= 65535, "a3d_attn_bwd: nq=%d too large", nq);
+    dim3 g2((nk + 127) / 128, batch * heads, chunks);
+    if (drop) {
+        attn_bwd_dq_kernel<true><<<g1, kRows * kSplit, 0, st>>>(q, k, v, key_mask, o, dout, lse, heads, nq, nk, embed, dq, dsum, th, sc, seed);
+        attn_bwd_dkv_kernel<true><<<g2, 128, 0, st>>>(q, k, v, key_mask, dout, lse, dsum, heads, nq, nk, embed, dk, dv, th, sc, seed);
+    } else {
+        attn_bwd_dq_kernel<false><<<g1, kRows * kSplit, 0, st>>>(q, k, v, key_mask, o, dout, lse, heads, nq, nk, embed, dq, dsum, th, sc, seed);
+        attn_bwd_dkv_kernel<false><<<g2, 128, 0, st>>>(q, k, v, key_mask, dout, lse, dsum, heads, nq, nk, embed, dk, dv, th, sc, seed);
+    }
+    return check_launch("a3d_attn_bwd");
+}
+
+extern "C" int a3d_rope_apply(const float* x, const float* pos, long rows, int embed, int transpose, float* out,
+                              void* stream) {
+    A3D_REQUIRE(x && pos && out && rows > 0, "a3d_rope_apply: bad arguments");
+    A3D_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)out & 7) == 0, "a3d_rope_apply: buffers must be 8-byte aligned");
+    const float sign = transpose ? -1.f : 1.f;
+    const long pairs = rows * (embed / 2);
+    const unsigned blocks = (unsigned)((pairs + 255) / 256);
+    if (embed == 60)
+        rope_apply_kernel<60><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, pos, rows, sign, out);
+    else if (embed == 120)
+        rope_apply_kernel<120><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, pos, rows, sign, out);
+    else
+        A3D_REQUIRE(false, "a3d_rope_apply: embedding_dim %d not supported (60 or 120)", embed);
+    return check_launch("a3d_rope_apply");
+}
+
+extern "C" int a3d_gather_tokens_bwd(const float* dtok, const int32_t* idx, int batch, int ncam, int embed, int hw,
+                                     int k, int tok_rows, int channels_last, float* dfeat, void* stream) {
+    A3D_REQUIRE(dtok && dfeat, "a3d_gather_tokens_bwd: null pointer");
+    A3D_REQUIRE(batch > 0 && ncam > 0 && hw > 0 && k > 0 && k <= tok_rows && embed > 0,
+                "a3d_gather_tokens_bwd: bad sizes (k=%d rows=%d)", k, tok_rows);
+    A3D_REQUIRE(idx || k == ncam * hw, "a3d_gather_tokens_bwd: identity gather needs k == ncam*hw");
+    const long total = (long)batch * k * embed;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    gather_tokens_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dtok, idx, ncam, embed, hw, k, tok_rows,
+                                                                      channels_last, dfeat, total);
+    return check_launch("a3d_gather_tokens_bwd");
+}

@@ -13,7 +13,8 @@ import torch.nn.functional as F
 from torch import nn
 from torchvision.ops import FeaturePyramidNetwork
 
-from . import lib
+from . import lib, train_layers
+from .autograd_ops import gather_tokens
 from .packing import PackCache, pack_kv_set, pack_xattn_layer
 from .params import XAttnStackParams, mlp
 from .rotations import normalise_quat, ortho6d_to_matrix
@@ -188,11 +189,14 @@ class Act3D(nn.Module):
             with torch.cuda.stream(copy):
                 staged = [t.to(dev, non_blocking=True) if t is not None else None
                           for t in (visible_pcd, instruction, curr_gripper, gt_action)]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "the fused kernels are forward-only in this round (backward kernels: DESIGN.md 'next'); "
-                "call under torch.no_grad()")
         lib.load()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # differentiable path: attention core / rotary / gather kernels with their backward (csrc/a3d_train.cu),
+            # projections and norms as torch.nn ops; the fused inference kernels below are forward-only
+            if staged is not None:
+                torch.cuda.current_stream().wait_stream(self._side_stream)
+                visible_pcd, instruction, curr_gripper, gt_action = staged
+            return self._forward_train(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
         e, h = self.embedding_dim, self.num_attn_heads
         b, ncam, _, height, width = visible_rgb.shape
         dev = visible_rgb.device
@@ -342,6 +346,102 @@ class Act3D(nn.Module):
             "ghost_pcd_pyramid": ghost_pyramid,
             "fine_ghost_pcd_offsets": offsets if self.regress_position_offset else None,
             "visible_rgb_features_pyramid": feats_pyr,
+            "visible_pcd_pyramid": pcd_pyr,
+            "query_features": query_feat.unsqueeze(0),
+            "instruction_features": instr.transpose(0, 1) if instr is not None else None,
+            "instruction_dummy_pos": self._identity_rope(b, n_instr, dev) if instr is not None else None,
+        }
+
+    # ------------------------------------------------------------------ differentiable forward (training)
+    def _forward_train(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action=None):
+        """Same computation and output dict as forward() with an autograd graph to every trainable
+        parameter the reference trains: FPN, embeddings, instruction encoder, the
+        three attention stacks and the heads.  Index selection (top-k, argmax) and ghost sampling run in
+        the same kernels as inference and carry no gradient (act3d.py:233-314)."""
+        e, h = self.embedding_dim, self.num_attn_heads
+        b, ncam = visible_rgb.shape[:2]
+        dev = visible_rgb.device
+        gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None
+        grip_xyz = curr_gripper[:, :3].float()
+
+        rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:]).float()
+        feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
+        feats_pyr, pcd_pyr, cache = [], [], {}
+        for i in range(self.num_sampling_level):
+            f = self.downscaling_factor_pyramid[i]
+            if f not in cache:
+                cache[f] = lib.pcd_pyramid(pcd, f).view(b, -1, 3)
+            feats_pyr.append(feats[self.feature_map_pyramid[i]].float())
+            pcd_pyr.append(cache[f])
+
+        if self.use_instruction:
+            instr = self.instruction_encoder(instruction.float())                    # (B, 53, E)
+            n_instr = instr.shape[1]
+            instr_pos = torch.zeros(b, n_instr, 3, device=dev)
+        else:
+            instr, n_instr = None, 0
+        grip_tok = self.curr_gripper_embed.weight.unsqueeze(0).expand(b, 1, e)
+        n_vis = 32 * 32 * ncam
+
+        position_pyramid, masks_pyramid, ghost_pyramid, carried, topk_log = [], [], [], [], []
+        query_feat, ghost_feats = None, None
+        for i in range(self.num_sampling_level):
+            anchor = None if i == 0 else (gt_position if gt_position is not None else carried[-1])
+            with torch.no_grad():
+                ghost = self._sample_ghost_points(b, dev, level=i, anchor=anchor).contiguous().float()
+                idx = None if i == 0 else lib.local_topk(carried[-1][:, 0].contiguous(), pcd_pyr[i], n_vis)
+            topk_log.append(idx)
+            tok, pos = gather_tokens(feats_pyr[i], pcd_pyr[i], idx, b, ncam)           # (B, n_vis, E), (B, n_vis, 3)
+            ctx = torch.cat([tok, grip_tok], dim=1)
+            ctx_pos = torch.cat([pos, grip_xyz.unsqueeze(1)], dim=1)
+            if self.use_instruction:                                                  # act3d.py:261-270
+                ctx = train_layers.xattn_stack(self.vis_ins_attn_pyramid[i], ctx, instr)[-1]
+                ctx = torch.cat([ctx, instr], dim=1)
+                ctx_pos = torch.cat([ctx_pos, instr_pos], dim=1)
+
+            ng = ghost.shape[1]
+            g0 = self.ghost_points_embed_pyramid[i].weight.unsqueeze(0).expand(b, ng, e)
+            ghost_feats = train_layers.xattn_stack(self.ghost_point_cross_attn_pyramid[i], g0, ctx, ghost, ctx_pos)[-1]
+
+            if i == 0:                                                                # act3d.py:281-301
+                q0 = self.query_embed.weight.unsqueeze(0).expand(b, 1, e)
+                q_layers = train_layers.xattn_stack(self.query_cross_attn_pyramid[i], q0, ctx)
+            else:
+                q_layers = train_layers.xattn_stack(self.query_cross_attn_pyramid[i], query_feat.unsqueeze(1), ctx,
+                                                    carried[-1].contiguous(), ctx_pos)
+            query_feat = q_layers[-1][:, 0]
+            masks = [torch.einsum("be,bne->bn", ql[:, 0], ghost_feats) for ql in q_layers]   # act3d.py:493-494
+            with torch.no_grad():
+                top_idx, top_pos = lib.argmax_pick(masks[-1].detach().contiguous(), ghost)
+            position_i = top_pos.unsqueeze(1)
+            ghost_pyramid.append(ghost.transpose(1, 2))
+            position_pyramid.append(position_i)
+            masks_pyramid.append(masks)
+            carried.append(self._teacher_positions[i].to(dev) if self._teacher_positions is not None else position_i)
+        self._last_topk = topk_log
+
+        top_idx_l = top_idx.long()
+        ar = torch.arange(b, device=dev)
+        offsets, position = None, top_pos
+        if self.regress_position_offset:
+            offsets = self.ghost_point_offset_predictor(ghost_feats).permute(0, 2, 1)        # (B, 3, Ng)
+            position = position + offsets[ar, :, top_idx_l]
+        feats_head = ghost_feats[ar, top_idx_l] if "top_ghost" in self.rotation_parametrization else query_feat
+        pred = self.gripper_state_predictor(feats_head)
+        if "quat" in self.rotation_parametrization:
+            rotation = normalise_quat(pred[:, :self.rotation_dim])
+        else:
+            rotation = ortho6d_to_matrix(pred[:, :self.rotation_dim])
+        gripper = torch.sigmoid(pred[:, self.rotation_dim:])
+        return {
+            "position": position, "rotation": rotation, "gripper": gripper,
+            "position_pyramid": position_pyramid,
+            "visible_rgb_mask_pyramid": [None] * self.num_sampling_level,
+            "ghost_pcd_masks_pyramid": masks_pyramid,
+            "ghost_pcd_pyramid": ghost_pyramid,
+            "fine_ghost_pcd_offsets": offsets if self.regress_position_offset else None,
+            "visible_rgb_features_pyramid": [f.unflatten(0, (b, ncam)) for f in feats_pyr],
             "visible_pcd_pyramid": pcd_pyr,
             "query_features": query_feat.unsqueeze(0),
             "instruction_features": instr.transpose(0, 1) if instr is not None else None,

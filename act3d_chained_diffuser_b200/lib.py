@@ -40,6 +40,13 @@ EXPORTS = {
     "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
                                  c_void_p, c_void_p]),
+    "a3d_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                             c_void_p, c_float, c_uint64, c_void_p]),
+    "a3d_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_uint64, c_void_p]),
+    "a3d_rope_apply": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
+    "a3d_gather_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
     "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                             c_int, c_void_p]),
@@ -273,6 +280,52 @@ def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device):
     _check(load().a3d_sample_ghost(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
                                    int(stream_id), _ptr(out), _stream()), "a3d_sample_ghost")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training path
+def attn_fwd(q, k, v, key_mask, heads, dropout_p=0.0, seed=0):
+    """q (B,Nq,E), k/v (B,Nk,E), key_mask (B,Nk) uint8 or None -> o (B,Nq,E), lse (B*H,Nq)."""
+    b, nq, e = q.shape
+    nk = k.shape[1]
+    o = torch.empty_like(q)
+    lse = torch.empty(b * heads, nq, device=q.device, dtype=torch.float32)
+    _check(load().a3d_attn_fwd(_ptr(_f32(q)), _ptr(_f32(k)), _ptr(_f32(v)), _ptr(key_mask), b, heads, nq, nk, e,
+                               _ptr(o), _ptr(lse), float(dropout_p), int(seed) & (2**64 - 1), _stream()), "a3d_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(q, k, v, key_mask, o, dout, lse, heads, dropout_p=0.0, seed=0):
+    """-> dq (B,Nq,E), dk (B,Nk,E), dv (B,Nk,E)"""
+    b, nq, e = q.shape
+    nk = k.shape[1]
+    dq = torch.empty_like(q)
+    dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+    dsum = torch.empty_like(lse)
+    _check(load().a3d_attn_bwd(_ptr(_f32(q)), _ptr(_f32(k)), _ptr(_f32(v)), _ptr(key_mask), _ptr(_f32(o)),
+                               _ptr(_f32(dout)), _ptr(_f32(lse)), b, heads, nq, nk, e, _ptr(dq), _ptr(dk), _ptr(dv),
+                               _ptr(dsum), float(dropout_p), int(seed) & (2**64 - 1), _stream()), "a3d_attn_bwd")
+    return dq, dk, dv
+
+
+def rope_apply(x, pos, transpose=False):
+    """x (..., E), pos (..., 3) with the same leading shape -> rotary(x) (inverse rotation if transpose)."""
+    e = x.shape[-1]
+    rows = x.numel() // e
+    assert pos.numel() == rows * 3, "rope_apply: one xyz per row expected"
+    out = torch.empty_like(x)
+    _check(load().a3d_rope_apply(_ptr(_f32(x)), _ptr(_f32(pos)), rows, e, int(transpose), _ptr(out), _stream()),
+           "a3d_rope_apply")
+    return out
+
+
+def gather_tokens_bwd(dtok, idx, batch, ncam, k, feat_shape, channels_last):
+    """dtok (B, rows, E) -> gradient w.r.t. the (B*ncam, E, h, w) feature map, NCHW or channels-last storage."""
+    _, e, h, w = feat_shape
+    dfeat = torch.empty(feat_shape, device=dtok.device, dtype=torch.float32,
+                        memory_format=torch.channels_last if channels_last else torch.contiguous_format).zero_()
+    _check(load().a3d_gather_tokens_bwd(_ptr(_f32(dtok)), _ptr(idx), batch, ncam, e, h * w, k, dtok.shape[1],
+                                        int(channels_last), dfeat.data_ptr(), _stream()), "a3d_gather_tokens_bwd")
+    return dfeat
 
 
 # ------------------------------------------------------------------------------------------------ planner

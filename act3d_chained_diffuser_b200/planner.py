@@ -19,7 +19,8 @@ import torch.nn.functional as F
 from torch import nn
 from torchvision.ops import FeaturePyramidNetwork
 
-from . import lib
+from . import lib, train_layers
+from .autograd_ops import gather_tokens
 from .ddpm import PosteriorTable
 from .packing import PackCache, pack_ada_layer, pack_kv_set, pack_lang_layer, pack_mlp, pack_traj_encoder
 from .params import ParallelStackParams, mlp
@@ -253,7 +254,8 @@ class DiffusionHead(nn.Module):
         if not trajectory.is_cuda:
             raise RuntimeError("DiffusionHead (B200) runs on CUDA tensors only: there is no CPU fallback path")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the denoiser kernels are forward-only in this round; call under torch.no_grad()")
+            return self._forward_train(trajectory, trajectory_mask, timestep, visible_rgb, visible_pcd, curr_gripper,
+                                       goal_gripper, instruction)
         n_t = int(timestep.max().item()) + 1
         ctx = self.encode_context(visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, max(n_t, 100))
         b, length, _ = trajectory.shape
@@ -261,6 +263,53 @@ class DiffusionHead(nn.Module):
         traj = trajectory.float().contiguous()
         pos_upd, rot = self.denoise(ctx, traj, trajectory_mask, timestep.to(torch.int32).contiguous(), work)
         return [torch.cat((traj[..., :3] + pos_upd, rot), -1)]
+
+
+    # ------------------------------------------------------------------ differentiable forward (training)
+    def _forward_train(self, trajectory, trajectory_mask, timestep, visible_rgb, visible_pcd, curr_gripper,
+                       goal_gripper, instruction):
+        """One denoiser evaluation with an autograd graph to every trainable parameter
+        (diffusion_head.py:200-363, encoder.py:81-203).  Attention cores (with the reference's 0.1 dropout on
+        the attention weights in train mode), rotary embedding and token gather are the kernels of
+        csrc/a3d_train.cu; projections, adaLN, LayerNorm, FFN and the regressors are torch.nn ops."""
+        lib.load()
+        e = self.embedding_dim
+        b, ncam = visible_rgb.shape[:2]
+        dev = trajectory.device
+        training = self.training
+        rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:]).float()
+        fm = self.feature_pyramid(self.backbone(self.normalize(rgb)))["res3"].float()
+        pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
+        pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
+        ctx, ctx_pos = gather_tokens(fm, pts, None, b, ncam)                          # (B, ncam*1024, E)
+        instr = None
+        if self.use_instruction:
+            instr = self.instruction_encoder(instruction.float())
+            ctx = train_layers.parallel_stack(self.vl_attention[0], ctx, None, instr, training=training)
+        cur = self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight
+        ctx = torch.cat([ctx, cur.unsqueeze(1)], dim=1)
+        ctx_pos = torch.cat([ctx_pos, curr_gripper[:, None, :3].float()], dim=1)
+        if self.use_goal:
+            goal = self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight
+            ctx = torch.cat([ctx, goal.unsqueeze(1)], dim=1)
+            ctx_pos = torch.cat([ctx_pos, goal_gripper[:, None, :3].float()], dim=1)
+
+        traj = trajectory.float()
+        x = self.traj_encoder(traj)
+        traj_pos = traj[..., :3].detach().contiguous()
+        t_emb = sinusoidal(timestep.to(dev), e).float()                               # encoder.py:199
+        wp_pe = sinusoidal(torch.arange(traj.shape[1], device=dev), e).float()[None]  # diffusion_head.py:326-328
+        mask = trajectory_mask if trajectory_mask is not None and bool(trajectory_mask.any()) else None
+        if self.use_instruction:                                                      # diffusion_head.py:330-336
+            x = train_layers.parallel_stack(self.traj_lang_attention[0], x, mask, instr, sem_pos=wp_pe,
+                                            training=training)
+        common = dict(x_mask=mask, ctx=ctx, x_pos=traj_pos, ctx_pos=ctx_pos, sem_pos=wp_pe, t_emb=t_emb,
+                      training=training)
+        x = train_layers.parallel_stack(self.traj_attention[0], x, **common)
+        pos_f = train_layers.parallel_stack(self.pos_attention[0], x, **common)
+        rot_f = train_layers.parallel_stack(self.rot_attention[0], x, **common)
+        upd = torch.cat((self.pos_regressor[0](pos_f), self.rot_regressor[0](rot_f)), -1)
+        return [torch.cat((traj[..., :3] + upd[..., :3], upd[..., 3:]), -1)]          # diffusion_head.py:271-274
 
 
 class DiffusionPlanner(nn.Module):
@@ -429,10 +478,7 @@ class DiffusionPlanner(nn.Module):
                 run_inference=False):
         if run_inference:
             return self.compute_trajectory(trajectory_mask, rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the denoiser kernels are forward-only in this round (backward: DESIGN.md 'next'); "
-                                      "the training loss can be evaluated under torch.no_grad()")
-        # ---- training objective, forward only (diffusion_model.py:253-324)
+        # ---- training objective (diffusion_model.py:253-324); differentiable when grad is enabled
         dev = rgb_obs.device
         gt = gt_trajectory.float().clone()
         gt[:, :, :3] = self.normalize_pos(gt[:, :, :3])

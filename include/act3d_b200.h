@@ -176,6 +176,38 @@ int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host
                      uint64_t seed, uint64_t stream_id, float* out, void* stream);
 
 /* =================================================================================
+ * Training path (fp32, gradients).  The reference trains both models through autograd over the eager
+ * attention (multihead_custom_attention.py:157-462), which materialises the (B*H, Nq, Nk) scores, the
+ * softmax and their gradients.  These entry points are the attention core and its backward without that
+ * tensor; projections / LayerNorm / FFN around them stay torch.nn ops in the training path
+ * (act3d_chained_diffuser_b200/autograd_ops.py, train_layers.py).  head_dim 15 (embed == 15 * heads).
+ *
+ * a3d_attn_fwd: o = dropout(softmax(q k^T + key_mask)) v per head.  q / o [B][Nq][E], k / v [B][Nk][E]
+ *   (head h = columns 15h .. 15h+14, the reference's head split :355-359; q already scaled by 15^-1/2 and
+ *   rotated), key_mask [B][Nk] bytes (non-zero = ignore key, :398-404) or NULL, lse [B*H][Nq] =
+ *   log sum exp of each score row (saved for backward).  dropout_p in [0,1) on the attention weights
+ *   (:413) from a counter-based generator keyed on (seed, b, h, row, key); 0 disables it.
+ * a3d_attn_bwd: gradients of the above.  dq [B][Nq][E] is written; dk / dv [B][Nk][E] are ACCUMULATED
+ *   into (fp32 atomics over query chunks: zero-fill them first); dsum [B*H][Nq] is scratch (dO . O).
+ *   The same dropout_p / seed as the forward call regenerate the same mask.
+ * a3d_rope_apply: out = rotary(x; pos) on channel pairs (2i, 2i+1) of the full E vector
+ *   (position_encodings.py:31-34 with the 3-D table of :58-97 evaluated on the fly); x / out [rows][E],
+ *   pos [rows][3].  transpose != 0 applies the inverse rotation = the backward of the forward call.
+ * a3d_gather_tokens_bwd: backward of a3d_gather_tokens w.r.t. the feature map: dfeat (NCHW or channels-last
+ *   like the forward's `feat`, zero-filled by the caller) += rows [0, k) of dtok [B][tok_rows][E].
+ */
+int a3d_attn_fwd(const float* q, const float* k, const float* v, const unsigned char* key_mask, int batch,
+                 int heads, int nq, int nk, int embed, float* o, float* lse, float dropout_p, uint64_t seed,
+                 void* stream);
+int a3d_attn_bwd(const float* q, const float* k, const float* v, const unsigned char* key_mask, const float* o,
+                 const float* dout, const float* lse, int batch, int heads, int nq, int nk, int embed, float* dq,
+                 float* dk, float* dv, float* dsum, float dropout_p, uint64_t seed, void* stream);
+int a3d_rope_apply(const float* x, const float* pos, long rows, int embed, int transpose, float* out,
+                   void* stream);
+int a3d_gather_tokens_bwd(const float* dtok, const int32_t* idx, int batch, int ncam, int embed, int hw, int k,
+                          int tok_rows, int channels_last, float* dfeat, void* stream);
+
+/* =================================================================================
  * ChainedDiffuser trajectory denoiser (embedding_dim 120, 8 heads, FFN 480, <= 64 waypoints).
  * Linear layers run as error-compensated fp16-split tensor-core GEMMs (csrc/a3d_mma_gemm.cuh):
  * every weight matrix is passed as a fragment-ordered (hi, lo) fp16 buffer ("W" packs, void*) plus

@@ -1,0 +1,342 @@
+"""GPU: the training path (csrc/a3d_train.cu behind autograd) against the CPU oracle's autograd.
+
+Kernel level: attention core forward / backward incl. key padding, ragged sizes, multi-chunk dK/dV and
+dropout (the kernel's own mask is recovered with a probe call, then a dense torch reference with that
+mask must match forward and backward); rotary apply and its transpose; token-gather backward.
+Model level: Act3D and the denoiser produce the same outputs as the forward-only inference kernels and
+the same parameter gradients as the oracle differentiated on the CPU (fp32; tolerance 1e-3 rel-L2 per
+tensor, gradients are fp32 end to end so they land around 1e-5)."""
+import pytest
+import torch
+
+from oracle import act3d_ref, planner_ref
+from oracle.rope import rope3d_table, rotate_pairs
+from tests.golden import cases, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def leaf_state_dict(module):
+    """state_dict as autograd leaves for the oracle; tied entries (weight_tying / gp_emb_tying register one
+    module under several keys) share ONE leaf so that their gradient contributions are summed like in the module."""
+    leaves, sd = {}, {}
+    for k, v in module.state_dict().items():
+        if v.data_ptr() not in leaves:
+            leaves[v.data_ptr()] = v.detach().clone().requires_grad_(v.is_floating_point())
+        sd[k] = leaves[v.data_ptr()]
+    return sd
+
+
+def dense_attention(q, k, v, heads, key_mask=None, keep=None, keep_scale=1.0):
+    """fp64 reference: q (B,Nq,E), k/v (B,Nk,E), key_mask (B,Nk) bool, keep (B,H,Nq,Nk) 0/1."""
+    b, nq, e = q.shape
+    hd = e // heads
+    qh = q.view(b, nq, heads, hd).transpose(1, 2)
+    kh = k.view(b, -1, heads, hd).transpose(1, 2)
+    vh = v.view(b, -1, heads, hd).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    if keep is not None:
+        p = p * keep * keep_scale
+    return (p @ vh).transpose(1, 2).reshape(b, nq, e)
+
+
+@pytest.mark.parametrize("b,heads,nq,nk,masked", [
+    (2, 4, 70, 150, False), (2, 8, 50, 50, True), (3, 4, 1, 333, False), (2, 4, 300, 4150, False),
+    (1, 4, 600, 53, False), (2, 8, 33, 129, True)])
+def test_attention_core_forward_backward(b, heads, nq, nk, masked):
+    from act3d_chained_diffuser_b200.autograd_ops import attention_core
+    e = 15 * heads
+    q = synth.normal("tr.q", (b, nq, e), 0.6).double()
+    k = synth.normal("tr.k", (b, nk, e), 1.0).double()
+    v = synth.normal("tr.v", (b, nk, e), 1.0).double()
+    g = synth.normal("tr.g", (b, nq, e), 1.0).double()
+    mask = None
+    if masked:
+        mask = torch.zeros(b, nk, dtype=torch.bool)
+        mask[0, nk - 7:] = True
+        mask[-1, ::3] = True
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    want = dense_attention(qr, kr, vr, heads, mask)
+    want.backward(g)
+    qc, kc, vc = (t.float().cuda().requires_grad_(True) for t in (q, k, v))
+    got = attention_core(qc, kc, vc, heads, mask.cuda() if masked else None)
+    got.backward(g.float().cuda())
+    torch.cuda.synchronize()
+    assert rel(got.detach().cpu().double(), want.detach()) <= 2e-6
+    for name, a, r in (("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+        assert rel(a.cpu().double(), r) <= 2e-5, (name, rel(a.cpu().double(), r))
+
+
+def test_attention_dropout_mask_is_consistent_between_forward_and_backward():
+    from act3d_chained_diffuser_b200 import lib
+    b, heads, nq, nk, p = 2, 4, 40, 15, 0.3
+    e = 15 * heads
+    seed = 1234567
+    # probe: q = 0 -> uniform probabilities 1/nk; v = one-hot per key -> o[., d] = keep[., key d] * scale / nk
+    q0 = torch.zeros(b, nq, e, device="cuda")
+    k0 = torch.zeros(b, nk, e, device="cuda")
+    v0 = torch.zeros(b, nk, e, device="cuda")
+    for h in range(heads):
+        v0[:, torch.arange(nk), h * 15 + torch.arange(nk)] = 1.0
+    o, _ = lib.attn_fwd(q0, k0, v0, None, heads, p, seed)
+    keep = (o.view(b, nq, heads, 15).transpose(1, 2) * nk * (1 - p)).round().cpu().double()     # (B,H,Nq,Nk)
+    assert set(keep.unique().tolist()) <= {0.0, 1.0}
+    frac = keep.mean().item()
+    assert abs(frac - (1 - p)) < 0.05, frac
+    q = synth.normal("dr.q", (b, nq, e), 0.6).double()
+    k = synth.normal("dr.k", (b, nk, e), 1.0).double()
+    v = synth.normal("dr.v", (b, nk, e), 1.0).double()
+    g = synth.normal("dr.g", (b, nq, e), 1.0).double()
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    want = dense_attention(qr, kr, vr, heads, None, keep, 1.0 / (1 - p))
+    want.backward(g)
+    qc, kc, vc = (t.float().cuda() for t in (q, k, v))
+    got, lse = lib.attn_fwd(qc, kc, vc, None, heads, p, seed)
+    dq, dk, dv = lib.attn_bwd(qc, kc, vc, None, got, g.float().cuda(), lse, heads, p, seed)
+    assert rel(got.cpu().double(), want.detach()) <= 2e-6
+    for name, a, r in (("dq", dq, qr.grad), ("dk", dk, kr.grad), ("dv", dv, vr.grad)):
+        assert rel(a.cpu().double(), r) <= 2e-5, (name, rel(a.cpu().double(), r))
+    # another seed gives another mask
+    o2, _ = lib.attn_fwd(q0, k0, v0, None, heads, p, seed + 1)
+    assert not torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("e", [60, 120])
+def test_rope_apply_and_transpose(e):
+    from act3d_chained_diffuser_b200 import lib
+    x = synth.normal("rp.x", (3, 77, e), 1.0)
+    pos = synth.points_in_bounds("rp.p", (3, 77))
+    tab = rope3d_table(pos, e)
+    want = rotate_pairs(x, tab[..., 0], tab[..., 1])
+    got = lib.rope_apply(x.cuda(), pos.cuda())
+    assert (got.cpu() - want).abs().max() <= 2e-6
+    back = lib.rope_apply(got, pos.cuda(), transpose=True)
+    assert (back.cpu() - x).abs().max() <= 2e-6
+    # the transpose is the adjoint: <R x, y> = <x, R^T y>
+    y = synth.normal("rp.y", (3, 77, e), 1.0).cuda()
+    lhs = (got * y).sum()
+    rhs = (x.cuda() * lib.rope_apply(y, pos.cuda(), transpose=True)).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-3 * abs(lhs.item()) + 1e-3
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_gather_tokens_backward(channels_last):
+    from act3d_chained_diffuser_b200.autograd_ops import gather_tokens
+    b, ncam, e, h, w, k = 2, 2, 60, 16, 16, 100
+    feat = synth.normal("gt.f", (b * ncam, e, h, w), 1.0)
+    pcd = synth.points_in_bounds("gt.p", (b, ncam * h * w))
+    idx = torch.stack([torch.randperm(ncam * h * w, generator=torch.Generator().manual_seed(i))[:k] for i in range(b)])
+    g = synth.normal("gt.g", (b, k, e), 1.0)
+    fr = feat.clone().requires_grad_(True)
+    flat = fr.view(b, ncam, e, h * w).permute(0, 1, 3, 2).reshape(b, ncam * h * w, e)
+    want = torch.stack([flat[i][idx[i]] for i in range(b)])
+    want.backward(g)
+    fc = feat.cuda()
+    if channels_last:
+        fc = fc.contiguous(memory_format=torch.channels_last)
+    fc.requires_grad_(True)
+    tok, pos = gather_tokens(fc, pcd.cuda(), idx.int().cuda(), b, ncam)
+    tok.backward(g.cuda())
+    assert torch.equal(tok.detach().cpu(), want.detach())
+    assert torch.equal(pos.cpu(), torch.stack([pcd[i][idx[i]] for i in range(b)]))
+    assert torch.equal(fc.grad.cpu(), fr.grad)
+    # identity gather (level 0): gradient is the transposed copy
+    fc2 = feat.cuda().requires_grad_(True)
+    tok2, _ = gather_tokens(fc2, pcd.cuda(), None, b, ncam)
+    g2 = synth.normal("gt.g2", (b, ncam * h * w, e), 1.0)
+    tok2.backward(g2.cuda())
+    want2 = g2.view(b, ncam, h * w, e).permute(0, 1, 3, 2).reshape(b * ncam, e, h, w)
+    assert torch.equal(fc2.grad.cpu(), want2)
+
+
+# ------------------------------------------------------------------------------------------------ Act3D
+def _act3d(use_instruction, **over):
+    from model import Act3D
+    kw = dict(cases.ACT3D_KW, use_instruction=use_instruction, **over)
+    m = Act3D(**kw).eval()           # eval: the synthetic trunk has no BN, dropout is 0 in Act3D anyway
+    cases.install_synth_trunk(m, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict())
+    return m, kw
+
+
+def _act3d_loss(out, tag):
+    """Fixed random linear functional of everything the reference's loss reads (main_keypose.py:353-429)."""
+    loss = 0.0
+    for lvl, masks in enumerate(out["ghost_pcd_masks_pyramid"]):
+        for j, mk in enumerate(masks):
+            w = synth.normal(f"{tag}.m{lvl}{j}", tuple(mk.shape), 1.0).to(mk.device)
+            loss = loss + (torch.log_softmax(mk, dim=-1) * torch.softmax(w, dim=-1)).sum() + 0.05 * (mk * w).sum()
+    loss = loss + (out["rotation"] * synth.normal(f"{tag}.r", tuple(out["rotation"].shape), 1.0).to(loss.device)).sum()
+    loss = loss + (out["gripper"] * synth.normal(f"{tag}.g", tuple(out["gripper"].shape), 1.0).to(loss.device)).sum()
+    if out.get("fine_ghost_pcd_offsets") is not None:
+        off = out["fine_ghost_pcd_offsets"]
+        loss = loss + (off * synth.normal(f"{tag}.o", tuple(off.shape), 1.0).to(loss.device)).sum()
+    return loss
+
+
+@pytest.mark.parametrize("use_instruction,over", [
+    (True, {}),
+    (False, dict(rotation_parametrization="6D_from_top_ghost", regress_position_offset=True, weight_tying=False,
+                 gp_emb_tying=False))])
+def test_act3d_training_gradients_match_oracle(use_instruction, over):
+    n_ghost = 200
+    m, kw = _act3d(use_instruction, num_ghost_points=3 * n_ghost, num_ghost_points_val=3 * n_ghost, **over)
+    inp = cases.act3d_inputs(batch=2, ncam=2, seed=4)
+    sampler = synth.make_ghost_sampler(2, n_ghost, seed=4)
+    cfg = act3d_ref.Act3DConfig(gripper_loc_bounds=synth.BOUNDS, use_instruction=use_instruction,
+                                ghost_points_per_level=n_ghost,
+                                rotation_parametrization=kw["rotation_parametrization"],
+                                regress_position_offset=kw["regress_position_offset"])
+    gt_action = torch.cat([synth.points_in_bounds("tr.gt", (2,), 4), torch.zeros(2, 5)], -1)
+
+    # ---- oracle: autograd on the CPU restatement, parameters = leaf copies of the state dict
+    sd = leaf_state_dict(m)
+    rgb_ref = inp["visible_rgb"].clone().requires_grad_(True)
+    want = act3d_ref.act3d_forward(sd, cfg, act3d_ref.trunk_from_module(m), rgb_ref, inp["visible_pcd"],
+                                   inp["instruction"], inp["curr_gripper"], gt_action=gt_action, ghost_sampler=sampler)
+    teacher = [p.detach().clone() for p in want["position_pyramid"]]
+    _act3d_loss(want, "a3dloss").backward()
+
+    # ---- ours on the GPU
+    m = m.cuda()
+    m._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor).to(device)
+    m._teacher_positions = teacher
+    rgb = inp["visible_rgb"].cuda().requires_grad_(True)
+    out = m(rgb, inp["visible_pcd"].cuda(), inp["instruction"].cuda(), inp["curr_gripper"].cuda(),
+            gt_action=gt_action.cuda())
+    for lvl in range(3):
+        for j in range(2):
+            got, ref = out["ghost_pcd_masks_pyramid"][lvl][j].detach().cpu(), want["ghost_pcd_masks_pyramid"][lvl][j].detach()
+            assert rel(got, ref) <= 1e-4, (lvl, j, rel(got, ref))
+    _act3d_loss(out, "a3dloss").backward()
+    torch.cuda.synchronize()
+
+    checked = 0
+    for name, p in m.named_parameters():
+        ref = sd[name].grad
+        if ref is None or ref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max() <= 1e-6, name
+            continue
+        assert p.grad is not None, f"{name}: no gradient reached this parameter"
+        assert rel(p.grad.cpu(), ref) <= 1e-3, (name, rel(p.grad.cpu(), ref))
+        checked += 1
+    assert checked >= (40 if use_instruction else 30), checked
+    # gradient through the token gather into the feature maps (and on to the images)
+    assert rel(rgb.grad.cpu(), rgb_ref.grad) <= 1e-3
+
+    # ---- the differentiable path and the fused inference kernels agree on the forward
+    with torch.no_grad():
+        fused = m(inp["visible_rgb"].cuda(), inp["visible_pcd"].cuda(), inp["instruction"].cuda(),
+                  inp["curr_gripper"].cuda(), gt_action=gt_action.cuda())
+    for lvl in range(3):
+        a, b_ = fused["ghost_pcd_masks_pyramid"][lvl][-1], out["ghost_pcd_masks_pyramid"][lvl][-1].detach()
+        assert rel(a, b_) <= 2e-3
+
+
+def test_act3d_training_step_reduces_loss():
+    """A few AdamW steps on one fixed batch through the reference's parameter groups shape (engine.py:89-101)."""
+    m, kw = _act3d(True, num_ghost_points=3 * 128)
+    m = m.cuda().train()
+    sampler = synth.make_ghost_sampler(2, 128, seed=8)
+    m._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor).to(device)
+    inp = {k: v.cuda() for k, v in cases.act3d_inputs(batch=2, ncam=1, seed=8).items()}
+    gt = torch.cat([synth.points_in_bounds("tr.gt2", (2,), 8), torch.zeros(2, 5)], -1).cuda()
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+    losses = []
+    for _ in range(6):
+        out = m(inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"], gt_action=gt)
+        loss = 0.0
+        for lvl in range(3):                                   # soft cross-entropy toward the ghost points nearest gt
+            gp = out["ghost_pcd_pyramid"][lvl].transpose(1, 2)
+            label = torch.softmax(-(gp - gt[:, None, :3]).norm(dim=-1) / 0.01, dim=-1)
+            for mk in out["ghost_pcd_masks_pyramid"][lvl]:
+                loss = loss - (label * torch.log_softmax(mk, dim=-1)).sum(-1).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0], losses
+
+
+# ------------------------------------------------------------------------------------------------ planner
+def _planner(**over):
+    from model import DiffusionPlanner
+    kw = dict(cases.PLANNER_KW, **over)
+    m = DiffusionPlanner(**kw).eval()
+    cases.install_synth_trunk(m.prediction_head, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    return m, kw
+
+
+def test_denoiser_training_gradients_match_oracle():
+    m, kw = _planner()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.7)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    t = torch.tensor([37, 5])
+    gw = synth.normal("cd.gw", (b, length, 9), 1.0)
+    cfg = planner_ref.PlannerConfig(gripper_loc_bounds=synth.BOUNDS)
+    head = m.prediction_head
+    pcd_n = m.normalize_pos(inp["pcd_obs"].permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+
+    sd = leaf_state_dict(head)
+    rgb_ref = inp["rgb_obs"].clone().requires_grad_(True)
+    ctx = planner_ref.encode_context(sd, cfg, act3d_ref.trunk_from_module(head), rgb_ref, pcd_n, inp["instruction"],
+                                     cur, goal)
+    want = planner_ref.denoise_once(sd, cfg, ctx, traj, inp["trajectory_mask"], t)
+    (want * gw).sum().backward()
+
+    m = m.cuda()
+    rgb = inp["rgb_obs"].cuda().requires_grad_(True)
+    got = m.prediction_head(traj.cuda(), inp["trajectory_mask"].cuda(), t.cuda(), rgb, pcd_n.cuda(), cur.cuda(),
+                            goal.cuda(), inp["instruction"].cuda())[-1]
+    assert rel(got.detach().cpu(), want.detach()) <= 1e-4
+    (got * gw.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    checked = 0
+    for name, p in m.prediction_head.named_parameters():
+        ref = sd[name].grad
+        if ref is None or ref.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max() <= 1e-6, name
+            continue
+        assert p.grad is not None, f"{name}: no gradient reached this parameter"
+        assert rel(p.grad.cpu(), ref) <= 1e-3, (name, rel(p.grad.cpu(), ref))
+        checked += 1
+    assert checked >= 100, checked
+    assert rel(rgb.grad.cpu(), rgb_ref.grad) <= 1e-3
+
+
+def test_planner_training_loss_backward_with_dropout():
+    """DiffusionPlanner.forward in train mode (dropout on, incl. the in-kernel attention-weight dropout):
+    finite scalar loss, gradients on every trainable tensor the loss depends on, and a step reduces it."""
+    m, kw = _planner()
+    m = m.cuda().train()
+    inp = {k: v.cuda() for k, v in cases.planner_inputs(batch=2, ncam=1, length=12).items()}
+    gt = torch.cat([synth.points_in_bounds("cd.gt", (2, 12)), torch.nn.functional.normalize(
+        synth.normal("cd.gtq", (2, 12, 4)), dim=-1)], -1).cuda()
+    params = [p for p in m.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=3e-4)
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(5):
+        torch.manual_seed(1)          # same noise / timestep / dropout masks every iteration
+        loss = m(gt, inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"], inp["instruction"], inp["curr_gripper"],
+                 inp["goal_gripper"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert loss.dim() == 0 and all(torch.isfinite(torch.tensor(losses)))
+    with_grad = sum(p.grad is not None and bool(p.grad.abs().max() > 0) for p in params)
+    assert with_grad >= 100, with_grad
+    assert losses[-1] < losses[0], losses
