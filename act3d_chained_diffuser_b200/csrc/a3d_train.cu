@@ -351,6 +351,63 @@ __global__ void __launch_bounds__(256) gather_tokens_bwd_kernel(const float* __r
     atomicAdd(dfeat + off, g);
 }
 
+// ================================================================================ soft cross-entropy over ghost points
+// Per sample b (one CTA): label = softmax_n(-||ghost_n - gt|| / spread) (+ label smoothing),
+// loss_b = -sum_n label_n log_softmax(logits)_n, dlogits_n = softmax(logits)_n - label_n
+// (LossAndMetrics._compute_position_loss, main_keypose.py:387-403: F.cross_entropy with probability targets).
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                       // red[] may still be read from the previous reduction
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    float r = lane < nw ? red[lane] : (is_max ? -INFINITY : 0.f);
+    r = is_max ? warp_max(r) : warp_sum(r);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) soft_ce_kernel(const float* __restrict__ logits, const float* __restrict__ ghost,
+                                                      const float* __restrict__ gt, int ng, float inv_spread,
+                                                      float smoothing, float* __restrict__ loss,
+                                                      float* __restrict__ dlogits) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const float gx = gt[b * 3], gy = gt[b * 3 + 1], gz = gt[b * 3 + 2];
+    const float* lg = logits + (long)b * ng;
+    const float* gp = ghost + (long)b * ng * 3;
+    float amax = -INFINITY, xmax = -INFINITY;
+    for (int n = threadIdx.x; n < ng; n += blockDim.x) {
+        const float dx = gp[n * 3] - gx, dy = gp[n * 3 + 1] - gy, dz = gp[n * 3 + 2] - gz;
+        const float a = -sqrtf(dx * dx + dy * dy + dz * dz) * inv_spread;
+        amax = fmaxf(amax, a);
+        xmax = fmaxf(xmax, lg[n]);
+    }
+    amax = block_reduce(amax, true, red);
+    xmax = block_reduce(xmax, true, red);
+    float sa = 0.f, sx = 0.f;
+    for (int n = threadIdx.x; n < ng; n += blockDim.x) {
+        const float dx = gp[n * 3] - gx, dy = gp[n * 3 + 1] - gy, dz = gp[n * 3 + 2] - gz;
+        const float a = -sqrtf(dx * dx + dy * dy + dz * dz) * inv_spread;
+        sa += expf(a - amax);
+        sx += expf(lg[n] - xmax);
+    }
+    sa = block_reduce(sa, false, red);
+    sx = block_reduce(sx, false, red);
+    const float log_sx = logf(sx), inv_sa = 1.f / sa, inv_sx = 1.f / sx, uni = smoothing / (float)ng;
+    float acc = 0.f;
+    for (int n = threadIdx.x; n < ng; n += blockDim.x) {
+        const float dx = gp[n * 3] - gx, dy = gp[n * 3 + 1] - gy, dz = gp[n * 3 + 2] - gz;
+        const float a = -sqrtf(dx * dx + dy * dy + dz * dz) * inv_spread;
+        const float t = expf(a - amax) * inv_sa * (1.f - smoothing) + uni;
+        const float z = lg[n] - xmax;
+        acc -= t * (z - log_sx);
+        if (dlogits) dlogits[(long)b * ng + n] = expf(z) * inv_sx - t;
+    }
+    acc = block_reduce(acc, false, red);
+    if (threadIdx.x == 0) loss[b] = acc;
+}
+
 int drop_args(float p, uint32_t* thresh, float* scale) {
     if (p <= 0.f) {
         *thresh = 0;
@@ -441,4 +498,12 @@ extern "C" int a3d_gather_tokens_bwd(const float* dtok, const int32_t* idx, int 
     gather_tokens_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dtok, idx, ncam, embed, hw, k, tok_rows,
                                                                       channels_last, dfeat, total);
     return check_launch("a3d_gather_tokens_bwd");
+}
+
+extern "C" int a3d_soft_ce(const float* logits, const float* ghost, const float* gt, int batch, int ng, float spread,
+                           float label_smoothing, float* loss, float* dlogits, void* stream) {
+    A3D_REQUIRE(logits && ghost && gt && loss && batch > 0 && ng > 0, "a3d_soft_ce: bad arguments");
+    A3D_REQUIRE(spread > 0.f && label_smoothing >= 0.f && label_smoothing < 1.f, "a3d_soft_ce: bad spread / smoothing");
+    soft_ce_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(logits, ghost, gt, ng, 1.f / spread, label_smoothing, loss, dlogits);
+    return check_launch("a3d_soft_ce");
 }

@@ -47,6 +47,7 @@ EXPORTS = {
     "a3d_rope_apply": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
     "a3d_gather_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                       c_void_p]),
+    "a3d_soft_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
     "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                             c_int, c_void_p]),
@@ -326,6 +327,16 @@ def gather_tokens_bwd(dtok, idx, batch, ncam, k, feat_shape, channels_last):
     _check(load().a3d_gather_tokens_bwd(_ptr(_f32(dtok)), _ptr(idx), batch, ncam, e, h * w, k, dtok.shape[1],
                                         int(channels_last), dfeat.data_ptr(), _stream()), "a3d_gather_tokens_bwd")
     return dfeat
+
+
+def soft_ce(logits, ghost, gt, spread, label_smoothing=0.0, want_grad=True):
+    """logits (B,Ng), ghost (B,Ng,3), gt (B,3) -> per-sample loss (B,), dlogits (B,Ng) or None."""
+    b, ng = logits.shape
+    loss = torch.empty(b, device=logits.device, dtype=torch.float32)
+    dlog = torch.empty_like(logits) if want_grad else None
+    _check(load().a3d_soft_ce(_ptr(_f32(logits)), _ptr(_f32(ghost)), _ptr(_f32(gt)), b, ng, float(spread),
+                              float(label_smoothing), _ptr(loss), _ptr(dlog), _stream()), "a3d_soft_ce")
+    return loss, dlog
 
 
 # ------------------------------------------------------------------------------------------------ planner

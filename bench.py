@@ -28,6 +28,7 @@ import torch  # noqa: E402
 
 WORKLOAD = dict(name="act3d_C2", batch=16, ncam=4, hw=256, ghost_per_level=16384, levels=3, embed=60, heads=4,
                 use_instruction=True)
+TRAIN_WORKLOAD = dict(name="act3d_C4_train", batch=16, ncam=4, ghost_total=1000, embed=60, heads=4)
 PLANNER_WORKLOAD = dict(name="planner_C3", batch=32, ncam=4, hw=256, length=50, steps=100, embed=120, heads=8)
 
 
@@ -169,8 +170,59 @@ def run_planner(rank, world, device, iters=3):
             "workload": "ChainedDiffuser compute_trajectory C3: batch 32/GPU, 50 waypoints, 100 DDPM steps, 4 views, E=120 H=8"}
 
 
+def run_train(rank, world, device, local, iters=6, warmup=3):
+    """Secondary figure: Act3D training step (forward + keypose loss + backward + AdamW) under stock DDP
+    (gradient all-reduce over NCCL only, engine.py:121-124), synthetic batch of TRAIN_WORKLOAD per GPU."""
+    from tests.golden import synth
+    from model import Act3D
+    from act3d_chained_diffuser_b200.losses import keypose_loss
+    w = TRAIN_WORKLOAD
+    torch.manual_seed(0)
+    model = Act3D(backbone="resnet", image_size=(256, 256), embedding_dim=w["embed"], num_attn_heads=w["heads"],
+                  gripper_loc_bounds=synth.BOUNDS, num_ghost_points=w["ghost_total"], num_sampling_level=3,
+                  use_instruction=True).to(device).train()
+    model.seed_ghost_sampler(99 + rank)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                        find_unused_parameters=True)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    rgb, pcd, instr, grip = [t.to(device) for t in act3d_inputs(w["batch"], w["ncam"], seed=300 + rank)]
+    gt = grip.clone()
+    gt[:, :3] += 0.02
+
+    def step():
+        out = net(rgb, pcd, instr, grip, gt_action=gt)
+        loss = sum(keypose_loss(out, gt).values())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    return {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+            "final_loss": round(float(loss), 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
+            "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
+                        "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
-def run_ours(args, rank, world, device):
+def run_ours(args, rank, world, device, local=0):
     from act3d_chained_diffuser_b200 import lib
     lib.load()
     w = WORKLOAD
@@ -261,6 +313,8 @@ def run_ours(args, rank, world, device):
     }
     if not args.no_planner:
         line["secondary"] = run_planner(rank, world, device)
+    if not args.no_train:
+        line["secondary_train"] = run_train(rank, world, device, local)
     return line
 
 
@@ -317,6 +371,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-planner", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
 
@@ -334,7 +389,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=device)
     args.warmup = max(args.warmup, 3)
-    line = run_ours(args, rank, world, device)
+    line = run_ours(args, rank, world, device, local)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -207,6 +207,15 @@ int a3d_rope_apply(const float* x, const float* pos, long rows, int embed, int t
 int a3d_gather_tokens_bwd(const float* dtok, const int32_t* idx, int batch, int ncam, int embed, int hw, int k,
                           int tok_rows, int channels_last, float* dfeat, void* stream);
 
+/* Position loss of the keypose trainer in one pass.  Replaces the label construction + F.cross_entropy with
+ * probability targets of LossAndMetrics._compute_position_loss (main_keypose.py:387-403) for one pyramid level:
+ *   label_n = softmax_n(-||ghost_n - gt|| / spread) * (1 - label_smoothing) + label_smoothing / Ng
+ *   loss[b] = -sum_n label_n * log_softmax(logits[b])_n          dlogits[b][n] = softmax(logits[b])_n - label_n
+ * logits [B][Ng], ghost [B][Ng][3], gt [B][3]; dlogits may be NULL (evaluation).  The mean over B and the loss
+ * coefficients are applied by the caller (act3d_chained_diffuser_b200/losses.py). */
+int a3d_soft_ce(const float* logits, const float* ghost, const float* gt, int batch, int ng, float spread,
+                float label_smoothing, float* loss, float* dlogits, void* stream);
+
 /* =================================================================================
  * ChainedDiffuser trajectory denoiser (embedding_dim 120, 8 heads, FFN 480, <= 64 waypoints).
  * Linear layers run as error-compensated fp16-split tensor-core GEMMs (csrc/a3d_mma_gemm.cuh):

@@ -60,3 +60,28 @@ def small_attention_case(e=60, heads=4, lq=40, lk=70, batch=2, seed=0):
         c_xyz=synth.points_in_bounds("att.cx", (batch, lk), seed),
         e=e, heads=heads,
     )
+
+
+def keypose_loss_case(batch=3, ng=97, levels=3, layers=2, seed=0, with_offsets=True):
+    """A synthetic Act3D output dict + ground truth for the keypose objective (main_keypose.py:353-429)."""
+    gt_pos = synth.points_in_bounds("loss.gt", (batch,), seed)
+    quat = synth.normal("loss.q", (batch, 4), seed=seed)
+    gt = torch.cat([gt_pos, quat / quat.norm(dim=-1, keepdim=True), (synth.uniform("loss.o", (batch, 1), seed=seed) > 0.5).float()], -1)
+    pred = dict(ghost_pcd_masks_pyramid=[], ghost_pcd_pyramid=[])
+    for i in range(levels):
+        # ghost points in a shrinking ball around the ground truth so that the Gaussian label is not one-hot
+        off = synth.normal(f"loss.g{i}", (batch, ng, 3), 0.03 / (2 ** i), seed)
+        pred["ghost_pcd_pyramid"].append((gt_pos[:, None] + off).transpose(1, 2))
+        pred["ghost_pcd_masks_pyramid"].append([synth.normal(f"loss.m{i}{j}", (batch, ng), 2.0, seed) for j in range(layers)])
+    rot = synth.normal("loss.r", (batch, 4), seed=seed)
+    pred["rotation"] = rot / rot.norm(dim=-1, keepdim=True)
+    pred["gripper"] = torch.sigmoid(synth.normal("loss.gr", (batch, 1), seed=seed))
+    pred["position"] = synth.points_in_bounds("loss.p", (batch,), seed)
+    pred["fine_ghost_pcd_offsets"] = synth.normal("loss.off", (batch, 3, ng), 0.002, seed) if with_offsets else None
+    return pred, gt
+
+
+LOSS_VARIANTS = [
+    dict(),
+    dict(compute_loss_at_all_layers=True, label_smoothing=0.1, symmetric_rotation_loss=True, ground_truth_gaussian_spread=0.02),
+]

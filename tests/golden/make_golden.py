@@ -131,6 +131,68 @@ def gen_planner(ref):
     save("planner_100step", dict(trajectory=traj, check=synth.checksum(inp["curr_gripper"], inp["goal_gripper"])))
 
 
+def reference_loss_class():
+    """LossAndMetrics straight from the reference's main_keypose.py source (the module itself cannot be
+    imported here: tap / blosc / datasets are missing).  Only the class statement is executed."""
+    import ast
+    from oracle.ref_import import REFERENCE_ROOT
+    src = open(os.path.join(REFERENCE_ROOT, "main_keypose.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "LossAndMetrics")
+    ns = {"torch": torch, "F": torch.nn.functional, "np": __import__("numpy")}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "main_keypose.py", "exec"), ns)
+    return ns["LossAndMetrics"]
+
+
+def _loss_obj(cls, **kw):
+    args = dict(position_loss="ce", rotation_parametrization="quat_from_query", ground_truth_gaussian_spread=0.01,
+                compute_loss_at_all_layers=False, label_smoothing=0.0, position_loss_coeff=1.0,
+                position_offset_loss_coeff=10000.0, rotation_loss_coeff=10.0, gripper_loss_coeff=1.0,
+                symmetric_rotation_loss=False)
+    args.update(kw)
+    import inspect
+    params = inspect.signature(cls.__init__).parameters
+    return cls(**{k: v for k, v in args.items() if k in params})
+
+
+def gen_keypose_loss(ref):
+    cls = reference_loss_class()
+    out = {}
+    for vi, variant in enumerate(cases.LOSS_VARIANTS):
+        pred, gt = cases.keypose_loss_case()
+        leaves = [m.requires_grad_(True) for lvl in pred["ghost_pcd_masks_pyramid"] for m in lvl]
+        pred["rotation"].requires_grad_(True)
+        pred["gripper"].requires_grad_(True)
+        pred["fine_ghost_pcd_offsets"].requires_grad_(True)
+        losses = _loss_obj(cls, **variant).compute_loss(pred, {"action": gt})
+        sum(losses.values()).backward()
+        out[f"v{vi}"] = dict(losses={k: v.detach() for k, v in losses.items()},
+                             dmasks=[m.grad if m.grad is not None else torch.zeros_like(m) for m in leaves],
+                             drotation=pred["rotation"].grad, dgripper=pred["gripper"].grad,
+                             doffsets=pred["fine_ghost_pcd_offsets"].grad, check=synth.checksum(gt, *[m.detach() for m in leaves]))
+    save("keypose_loss", out)
+
+
+def gen_act3d_train_grads(ref):
+    """Reference Act3D with autograd + the reference's own loss: parameter gradients (pins the oracle's autograd)."""
+    cls = reference_loss_class()
+    kw = dict(cases.ACT3D_KW, use_instruction=True, num_ghost_points=3 * 96)
+    torch.manual_seed(0)
+    model = ref.Act3D(**kw).train()
+    cases.install_synth_trunk(model, kw["embedding_dim"])
+    synth.fill_state_dict(model.state_dict())
+    inp = cases.act3d_inputs(batch=2, ncam=1)
+    gt = cases.keypose_loss_case(batch=2)[1]
+    sampler = synth.make_ghost_sampler(2, model.num_ghost_points, diameter=kw["fine_sampling_ball_diameter"])
+    model._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor)
+    out = model(inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"], gt_action=gt)
+    losses = _loss_obj(cls).compute_loss(out, {"action": gt})
+    sum(losses.values()).backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    save("act3d_train_grads", dict(grads=grads, losses={k: v.detach() for k, v in losses.items()},
+                                   position_pyramid=[p.detach() for p in out["position_pyramid"]],
+                                   check=synth.checksum(gt, inp["curr_gripper"])))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = load_reference()
@@ -141,6 +203,8 @@ def main():
     gen_parallel_attention(ref)
     gen_diffusion_head(ref)
     gen_planner(ref)
+    gen_keypose_loss(ref)
+    gen_act3d_train_grads(ref)
 
 
 if __name__ == "__main__":

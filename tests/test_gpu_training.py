@@ -340,3 +340,67 @@ def test_planner_training_loss_backward_with_dropout():
     with_grad = sum(p.grad is not None and bool(p.grad.abs().max() > 0) for p in params)
     assert with_grad >= 100, with_grad
     assert losses[-1] < losses[0], losses
+
+
+# ------------------------------------------------------------------------------------------------ objective + golden
+def test_keypose_loss_kernel_matches_reference_golden():
+    """losses.keypose_loss (soft-CE kernel, forward + gradient in one pass) against the values and gradients the
+    reference's own LossAndMetrics produced (tests/golden/keypose_loss.pt)."""
+    import os
+    from act3d_chained_diffuser_b200.losses import keypose_loss
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "keypose_loss.pt"), weights_only=False)
+    for vi, variant in enumerate(cases.LOSS_VARIANTS):
+        want = g[f"v{vi}"]
+        pred, gt = cases.keypose_loss_case()
+        pred["ghost_pcd_pyramid"] = [p.transpose(1, 2).contiguous().cuda().transpose(1, 2) for p in pred["ghost_pcd_pyramid"]]
+        pred["ghost_pcd_masks_pyramid"] = [[m.cuda().requires_grad_(True) for m in lvl] for lvl in pred["ghost_pcd_masks_pyramid"]]
+        for k in ("rotation", "gripper", "fine_ghost_pcd_offsets"):
+            pred[k] = pred[k].cuda().requires_grad_(True)
+        pred["position"] = pred["position"].cuda()
+        losses = keypose_loss(pred, gt.cuda(), **variant)
+        assert set(losses) == set(want["losses"])
+        for k, v in losses.items():
+            assert abs(v.item() - want["losses"][k].item()) <= 2e-5 * max(1.0, abs(want["losses"][k].item())), k
+        sum(losses.values()).backward()
+        leaves = [m for lvl in pred["ghost_pcd_masks_pyramid"] for m in lvl]
+        for m, ref in zip(leaves, want["dmasks"]):
+            got = m.grad.cpu() if m.grad is not None else torch.zeros_like(ref)
+            assert (got - ref).abs().max() <= 1e-6 + 1e-4 * ref.abs().max()
+        assert rel(pred["rotation"].grad.cpu(), want["drotation"]) <= 1e-5
+        assert rel(pred["fine_ghost_pcd_offsets"].grad.cpu(), want["doffsets"]) <= 1e-5
+
+
+def test_act3d_training_gradients_match_reference_golden():
+    """End to end on the GPU: train-mode Act3D + keypose_loss + backward against the parameter gradients of the
+    unmodified reference (tests/golden/act3d_train_grads.pt; levels teacher-forced with its positions)."""
+    import os
+    from model import Act3D
+    from act3d_chained_diffuser_b200.losses import keypose_loss
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "act3d_train_grads.pt"), weights_only=False)
+    kw = dict(cases.ACT3D_KW, use_instruction=True, num_ghost_points=3 * 96)
+    m = Act3D(**kw).train()
+    cases.install_synth_trunk(m, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict())
+    m = m.cuda()
+    inp = cases.act3d_inputs(batch=2, ncam=1)
+    gt = cases.keypose_loss_case(batch=2)[1]
+    assert synth.checksum(gt, inp["curr_gripper"]) == g["check"]
+    sampler = synth.make_ghost_sampler(2, 96)
+    m._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor).to(device)
+    m._teacher_positions = [p.clone() for p in g["position_pyramid"]]
+    out = m(inp["visible_rgb"].cuda(), inp["visible_pcd"].cuda(), inp["instruction"].cuda(), inp["curr_gripper"].cuda(),
+            gt_action=gt.cuda())
+    losses = keypose_loss(out, gt.cuda())
+    for k, v in losses.items():
+        assert abs(v.item() - g["losses"][k].item()) <= 1e-4 * max(1.0, abs(g["losses"][k].item())), k
+    sum(losses.values()).backward()
+    params = dict(m.named_parameters())
+    checked = 0
+    for name, ref in g["grads"].items():
+        if ref.abs().max() == 0:
+            continue
+        got = params[name].grad
+        assert got is not None, name
+        assert rel(got.cpu(), ref) <= 1e-3, (name, rel(got.cpu(), ref))
+        checked += 1
+    assert checked >= 60, checked

@@ -190,3 +190,71 @@ def test_planner_100_steps():
     close(traj[..., :3], g["trajectory"][..., :3], 2e-4)
     # quaternion sign is determined; compare directly
     close(traj[..., 3:], g["trajectory"][..., 3:], 5e-4)
+
+
+# ------------------------------------------------------------------------------------------------ training objective
+def test_keypose_loss_and_its_gradients():
+    from oracle.losses import keypose_loss
+    g = load("keypose_loss")
+    for vi, variant in enumerate(cases.LOSS_VARIANTS):
+        want = g[f"v{vi}"]
+        pred, gt = cases.keypose_loss_case()
+        leaves = [m.requires_grad_(True) for lvl in pred["ghost_pcd_masks_pyramid"] for m in lvl]
+        assert synth.checksum(gt, *[m.detach() for m in leaves]) == want["check"]
+        for k in ("rotation", "gripper", "fine_ghost_pcd_offsets"):
+            pred[k].requires_grad_(True)
+        losses = keypose_loss(pred, gt, **variant)
+        assert set(losses) == set(want["losses"])
+        for k, v in losses.items():
+            close(v.detach(), want["losses"][k], 1e-6, 1e-6)
+        sum(losses.values()).backward()
+        for m, ref in zip(leaves, want["dmasks"]):
+            close(m.grad if m.grad is not None else torch.zeros_like(m), ref, 1e-7, 1e-5)
+        close(pred["rotation"].grad, want["drotation"], 1e-7, 1e-5)
+        close(pred["gripper"].grad, want["dgripper"], 1e-7, 1e-5)
+        close(pred["fine_ghost_pcd_offsets"].grad, want["doffsets"], 1e-7, 1e-5)
+
+
+def leaf_state_dict(module):
+    leaves, sd = {}, {}
+    for k, v in module.state_dict().items():
+        if v.data_ptr() not in leaves:
+            leaves[v.data_ptr()] = v.detach().clone().requires_grad_(v.is_floating_point())
+        sd[k] = leaves[v.data_ptr()]
+    return sd
+
+
+def test_act3d_training_gradients_of_the_oracle_match_the_reference():
+    """Autograd through the oracle restatement + oracle loss == autograd through the unmodified reference
+    + its own LossAndMetrics (train mode, gt_action given, 96 ghost points / level)."""
+    from model import Act3D
+    from oracle.losses import keypose_loss
+    g = load("act3d_train_grads")
+    kw = dict(cases.ACT3D_KW, use_instruction=True, num_ghost_points=3 * 96)
+    m = Act3D(**kw).train()
+    cases.install_synth_trunk(m, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict())
+    inp = cases.act3d_inputs(batch=2, ncam=1)
+    gt = cases.keypose_loss_case(batch=2)[1]
+    assert synth.checksum(gt, inp["curr_gripper"]) == g["check"]
+    sampler = synth.make_ghost_sampler(2, 96)
+    cfg = act3d_ref.Act3DConfig(gripper_loc_bounds=synth.BOUNDS, use_instruction=True, ghost_points_per_level=96)
+    sd = leaf_state_dict(m)
+    out = act3d_ref.act3d_forward(sd, cfg, act3d_ref.trunk_from_module(m), inp["visible_rgb"], inp["visible_pcd"],
+                                  inp["instruction"], inp["curr_gripper"], gt_action=gt, ghost_sampler=sampler)
+    for a, b in zip(out["position_pyramid"], g["position_pyramid"]):
+        assert torch.equal(a, b)
+    losses = keypose_loss(out, gt)
+    for k, v in losses.items():
+        close(v.detach(), g["losses"][k], 1e-5, 1e-5)
+    sum(losses.values()).backward()
+    checked = 0
+    for name, ref in g["grads"].items():
+        got = sd[name].grad
+        if ref.abs().max() == 0:
+            continue
+        assert got is not None, name
+        err = ((got - ref).norm() / ref.norm()).item()
+        assert err <= 1e-4, (name, err)
+        checked += 1
+    assert checked >= 60, checked
