@@ -216,7 +216,7 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = t.item()
     return {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
-            "final_loss": round(float(loss), 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
+            "final_loss": round(float(loss.detach()), 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
             "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
                         "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
 

@@ -396,11 +396,15 @@ def test_act3d_training_gradients_match_reference_golden():
     sum(losses.values()).backward()
     params = dict(m.named_parameters())
     checked = 0
+    # gradients that vanish analytically (the last LayerNorm bias of the ghost stack under softmax-CE: the logit
+    # gradients sum to zero) are fp32 noise ~1e-8 on both sides: absolute floor relative to the largest gradient
+    floor = 1e-6 * max(r.norm().item() for r in g["grads"].values())
     for name, ref in g["grads"].items():
         if ref.abs().max() == 0:
             continue
         got = params[name].grad
         assert got is not None, name
-        assert rel(got.cpu(), ref) <= 1e-3, (name, rel(got.cpu(), ref))
+        err = (got.cpu() - ref).norm().item()
+        assert err <= 1e-3 * ref.norm().item() + floor, (name, err, ref.norm().item())
         checked += 1
     assert checked >= 60, checked
