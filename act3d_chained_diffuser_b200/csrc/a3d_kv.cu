@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) ctx_kv_kernel(const float* __restrict__ t
                     } else {            // padded embed dims E..EP-1 own the pad slot (d = 15) of head dim-E
                         h = dim - E;
                         d = 15;
-                        val = (is_v && valid) ? 1.f : 0.f;
+                        val = valid ? 1.f : 0.f;      // V: softmax denominator; K: carries the shift of a3d_xattn4.cu
                     }
                     const int off = h * 2048 + row * 32 + (((d >> 3) ^ swz) << 4) + (d & 7) * 2;
                     *reinterpret_cast<__half*>(base + off) = __float2half_rn(val);

@@ -349,6 +349,7 @@ using namespace a3d;
 
 int g_xattn_core = 2;   // 2: mma.sync core (a3d_xattn2.cu), 3: tcgen05 / TMEM core (a3d_xattn3.cu)
 int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream);
+int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" size_t a3d_xattn_layer_words(int embed, int ffn) {
@@ -394,6 +395,7 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.logits = logits;
     dim3 grid((nq + Xa2::ROWS - 1) / Xa2::ROWS, batch);
     if (g_xattn_core == 3) return a3d_launch_xattn3(a, grid, (cudaStream_t)stream);
+    if (g_xattn_core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \
         static bool once = false;                                                                                      \

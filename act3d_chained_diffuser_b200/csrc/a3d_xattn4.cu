@@ -1,31 +1,32 @@
-// Fused cross-attention stack, tcgen05 / TMEM generation (same contract and packed weights as a3d_xattn2.cu).
+// Fused cross-attention stack, tcgen05 / TMEM generation, SINGLE PASS (same contract and packed weights as
+// a3d_xattn2.cu; supersedes the two-pass a3d_xattn3.cu).
 //
-// CTA = 128 query rows of one sample, 160 threads:
+// CTA = 128 query rows of one sample, 160 threads, 2 CTAs / SM:
 //   warps 0-3  "row warps": thread i owns query row i == TMEM lane i.  They run the projections / LayerNorm /
 //              FFN (register-chained split-fp16 mma.sync GEMMs shared with a3d_xattn2.cu) and the softmax:
 //              scores are read from tensor memory with tcgen05.ld one full row per thread, so row max /
 //              exp2 / packing need no shuffles at all, and P goes back to tensor memory with tcgen05.st.
 //   warp 4     one elected lane issues the K/V tile loads (1-D bulk async copies on an mbarrier ring) and all
-//              tcgen05.mma instructions:  S_h = Q_h K_h^T (M=128, N=64, K=16, operands straight from shared memory
-//              through SWIZZLE_32B K-major descriptors -- the K/V tile images are already in that canonical
-//              layout) and O_h += P_h V_h (A = P from tensor memory, B = V MN-major).  Completion is signalled
-//              with tcgen05.commit on mbarriers.
-// Two passes over the keys per layer: pass 1 finds the exact row maxima (S only), pass 2 recomputes S, forms
-// P = 2^(S - m) and accumulates O in tensor memory -- no running-max correction of O is ever needed, and the
-// extra QK^T pass is free on a tensor pipe that the MUFU-bound softmax leaves mostly idle.
-// Status (round 1): parity-green on every kernel / end-to-end test, 3.6 ms per C2 launch vs 2.8 ms for the mma.sync core,
-// so it is opt-in (a3d_set_option("xattn_core", 3) / A3D_XATTN_CORE=3).  ncu (profiles/r1_xattn_ghost_v3_ncu.txt): only
-// ~10 resident warps/SM, 21 % of stall samples in mbarrier spin loops, XU 58 %: the single issuing lane (several
-// ~100-cycle try_waits + 5 UMMAs per 8192-score unit) and 4 row warps per CTA are the limiters, not TMEM bandwidth
-// (21 %).  Next: single pass with conditional O correction, S and PV issue on separate warps, 8 row warps per CTA.
+//              tcgen05.mma instructions:  S_h = Q_h K_h^T (M=128, N=64, K=16, SS form, SWIZZLE_32B K-major
+//              descriptors -- the K/V tile images are already in that canonical layout) and O_h += P_h V_h
+//              (TS form: A = P from tensor memory, B = V MN-major).  Completion: tcgen05.commit on mbarriers.
+// One pass over the keys with a STALE shift per (row, head) that rides in the pad slot of the head dimension
+// (Q[15] = -shift, K[15] = 1): S = s - shift comes straight out of the tensor core, P = 2^S.  The shift is the
+// maximum of the first tile + 6 and is refreshed only when some P reaches 2.0 (overshoot by 2^7; detected with
+// an OR over the packed fp16 pairs); the denominator is accumulated in fp32 by the PV product through the ones
+// in V slot 15.  A refresh rescales the row of O_h in tensor memory (tcgen05.ld / st) after waiting for the PV
+// product of the previous tile of that head (pv_done[h]); after the first tiles this path is essentially never taken.
+// A fraction of the exponentials can run as a degree-3 polynomial on the FMA pipe (exp2_poly) next to the MUFU
+// unit, which is the binding unit at head_dim 15 (one exp per 30 useful FLOPs): template parameter PM = bit
+// mask over every 8 scores.
 // Tensor-memory map (256 columns): O = 4 heads x 16 columns at 0..63 (slot 15 = softmax denominator),
-// S/P buffer i (i = unit & 1) at 64 + 64 i (P overwrites the first 32 columns of S as packed fp16 pairs).
+// S/P buffer i (i = unit % 3) at 64 + 64 i (P overwrites the first 32 columns of S as packed fp16 pairs).
 #include "a3d_tcgen05.cuh"
 #include "a3d_xattn_common.cuh"
 
 namespace a3d {
 
-struct Xa3 {
+struct Xa4 {
     static constexpr int E = 60, H = 4, ROWS = 128, THREADS = 160;
     static constexpr int XP = Xa2::XP;
     static constexpr int TILE_BYTES = Xa2::TILE_BYTES, STAGES = 3;
@@ -33,25 +34,32 @@ struct Xa3 {
     static constexpr size_t Q_BYTES = (size_t)H * ROWS * 32;          // Q_h tiles [128][16] fp16, SWIZZLE_32B
     static constexpr size_t RING_BYTES = (size_t)STAGES * TILE_BYTES; // K/V ring; the O tile aliases it in the epilogue
     static constexpr size_t SMEM = X_BYTES + Q_BYTES + RING_BYTES + 256;
-    static constexpr int TMEM_COLS = 256, O_COL = 0, S_COL = 64;
+    static constexpr int TMEM_COLS = 256, O_COL = 0, S_COL = 64, NBUF = 3;   // O + 3 S/P buffers = 256 columns
 };
 
-struct Xa3Bars {
-    uint64_t kv_full[Xa3::STAGES], kv_empty[Xa3::STAGES];
-    uint64_t s_full[2], p_full[2], sfree1[2], sfree2[2];
+// element idx of every 8 goes to the FMA-pipe polynomial when bit idx of PM is set (folds under full unrolling)
+template <int PM>
+__device__ __forceinline__ float exp2_m(int idx, float x) {
+    return ((PM >> (idx & 7)) & 1) ? exp2_poly(x) : exp2_fast(x);
+}
+
+struct Xa4Bars {
+    uint64_t kv_full[Xa4::STAGES], kv_empty[Xa4::STAGES];
+    uint64_t s_full[Xa4::NBUF], p_full[Xa4::NBUF], pv_done[Xa4::H];
     uint64_t q_ready, o_full;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a) {
-    using C = Xa3;
+template <int PM>
+__global__ void __launch_bounds__(Xa4::THREADS, 2) xattn4_kernel(const Xa2Args a) {
+    using C = Xa4;
     constexpr int E = C::E, H = C::H;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* xpark = reinterpret_cast<float*>(smem);                                // [128][XP] residual stream
     unsigned char* qs = smem + C::X_BYTES;                                        // [H][128][32 B] fp16, SW32
     unsigned char* kvs = smem + C::X_BYTES + C::Q_BYTES;                          // STAGES x TILE_BYTES
     float* opark = reinterpret_cast<float*>(kvs);                                 // [128][XP] attention output (epilogue)
-    Xa3Bars* bars = reinterpret_cast<Xa3Bars*>(kvs + C::RING_BYTES);
+    Xa4Bars* bars = reinterpret_cast<Xa4Bars*>(kvs + C::RING_BYTES);
     __shared__ float freq[E / 6];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -63,12 +71,11 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
             mbar_init(bars->kv_full + s, 1);
             mbar_init(bars->kv_empty + s, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < C::NBUF; ++i) {
             mbar_init(bars->s_full + i, 1);
             mbar_init(bars->p_full + i, 128);
-            mbar_init(bars->sfree1 + i, 128);
-            mbar_init(bars->sfree2 + i, 1);
         }
+        for (int h = 0; h < C::H; ++h) mbar_init(bars->pv_done + h, 1);
         mbar_init(&bars->q_ready, 128);
         mbar_init(&bars->o_full, 1);
         mbar_fence_init();
@@ -86,60 +93,46 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
     if (warp == 4) {
         // =========================================================== producer: TMA loads + all tensor-core issue
         if (lane == 0) {
-            uint32_t gt_load = 0;               // tiles requested so far (2 * nt per layer: pass 1 then pass 2)
+            uint32_t gt_load = 0;               // tiles requested so far (nt per layer)
             for (int layer = 0; layer < a.nlayers; ++layer) {
                 const unsigned char* kv_layer = kv_sample + (size_t)layer * a.kv_layer_stride;
-                const uint32_t base1 = (uint32_t)layer * 2 * nt, base2 = base1 + nt, lim = base1 + 2 * nt;
+                const uint32_t base = (uint32_t)layer * nt, lim = base + nt;
                 auto load_next = [&]() {
                     if (gt_load >= lim) return;
                     const uint32_t s = gt_load % C::STAGES, use = gt_load / C::STAGES;
                     if (use >= 1) mbar_wait(bars->kv_empty + s, (use - 1) & 1);
-                    const uint32_t tile = (gt_load - base1) % nt;
                     mbar_expect_tx(bars->kv_full + s, C::TILE_BYTES);
-                    bulk_g2s(kvs + s * C::TILE_BYTES, kv_layer + (size_t)tile * C::TILE_BYTES, C::TILE_BYTES, bars->kv_full + s);
+                    bulk_g2s(kvs + s * C::TILE_BYTES, kv_layer + (size_t)(gt_load - base) * C::TILE_BYTES, C::TILE_BYTES,
+                             bars->kv_full + s);
                     ++gt_load;
                 };
                 mbar_wait(&bars->q_ready, layer & 1);       // Q of this layer is in shared memory; O tile no longer read
                 tc_fence_after();
                 for (int i = 0; i < C::STAGES - 1; ++i) load_next();
                 const uint32_t q_addr = smem_u32(qs);
-                // ---------------- pass 1: S only
-                for (int t = 0; t < nt; ++t) {
-                    const uint32_t tau = base1 + t, s = tau % C::STAGES;
-                    mbar_wait(bars->kv_full + s, (tau / C::STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t k_addr = smem_u32(kvs + s * C::TILE_BYTES);
-                    for (int h = 0; h < H; ++h) {
-                        const int u = t * H + h, i = u & 1, k = u >> 1;
-                        if (k >= 1) mbar_wait(bars->sfree1 + i, (k - 1) & 1);
-                        tc_fence_after();
-                        umma_ss(tmem + C::S_COL + 64 * i, sw32_desc(q_addr + h * 4096), sw32_desc(k_addr + h * 2048), kIdescS, 0);
-                        tc_commit(bars->s_full + i);
-                    }
-                    tc_commit(bars->kv_empty + s);
-                    load_next();                // reuses the stage of tile tau-1, whose release was committed one iteration ago
-                }
-                // both S buffers must have been read by the row warps before pass 2 overwrites them
-                {
-                    const int last_k = (nt * H) / 2 - 1;
-                    mbar_wait(bars->sfree1 + 0, last_k & 1);
-                    mbar_wait(bars->sfree1 + 1, last_k & 1);
-                }
-                // ---------------- pass 2: S -> (row warps: P) -> O += P V; the PV of unit u-1 is issued after S of unit u
-                for (int u = 0; u <= nt * H; ++u) {
+                // Software pipeline over units (tile t, head h): S(u) is issued two units ahead of the PV product that
+                // consumes P(u-2), so the row warps always find a finished S while the tensor pipe drains the previous
+                // products.  Buffer i = U % 3 (U counts units across layers); S(u) may overwrite the buffer of unit u-3
+                // without an explicit wait: its PV product was issued earlier by this same thread and tcgen05.mma
+                // instructions execute in issue order.
+                const uint32_t ubase = (uint32_t)layer * nt * H;
+                for (int u = 0; u < nt * H + 2; ++u) {
                     if (u < nt * H) {
-                        const int t = u / H, h = u % H, i = u & 1, k = u >> 1;
-                        const uint32_t tau = base2 + t, s = tau % C::STAGES;
-                        if (h == 0) mbar_wait(bars->kv_full + s, (tau / C::STAGES) & 1);
-                        if (k >= 1) mbar_wait(bars->sfree2 + i, (k - 1) & 1);
-                        tc_fence_after();
+                        const int t = u / H, h = u % H;
+                        const uint32_t U = ubase + u, i = U % C::NBUF;
+                        const uint32_t tau = base + t, s = tau % C::STAGES;
+                        if (h == 0) {
+                            mbar_wait(bars->kv_full + s, (tau / C::STAGES) & 1);
+                            tc_fence_after();
+                        }
                         const uint32_t k_addr = smem_u32(kvs + s * C::TILE_BYTES);
                         umma_ss(tmem + C::S_COL + 64 * i, sw32_desc(q_addr + h * 4096), sw32_desc(k_addr + h * 2048), kIdescS, 0);
                         tc_commit(bars->s_full + i);
                     }
-                    if (u >= 1) {
-                        const int v = u - 1, t = v / H, h = v % H, j = v & 1, k = v >> 1;
-                        const uint32_t s = (base2 + t) % C::STAGES;
+                    if (u >= 2) {
+                        const int v = u - 2, t = v / H, h = v % H;
+                        const uint32_t V = ubase + v, j = V % C::NBUF, k = V / C::NBUF;
+                        const uint32_t s = (base + t) % C::STAGES;
                         mbar_wait(bars->p_full + j, k & 1);
                         tc_fence_after();
                         const uint32_t v_addr = smem_u32(kvs + s * C::TILE_BYTES) + H * 2048 + h * 2048;
@@ -147,7 +140,7 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
                         for (int ks = 0; ks < 4; ++ks)
                             umma_ts(tmem + C::O_COL + 16 * h, tmem + C::S_COL + 64 * j + 8 * ks, sw32_desc(v_addr + ks * 512),
                                     kIdescPV, (t > 0 || ks > 0) ? 1u : 0u);
-                        tc_commit(bars->sfree2 + j);
+                        tc_commit(bars->pv_done + h);
                         if (h == H - 1) {
                             tc_commit(bars->kv_empty + s);
                             load_next();
@@ -239,71 +232,143 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
             tc_fence_before();
             mbar_arrive(&bars->q_ready);
 
-            // ---------------------------------------------------------------- pass 1: exact row maxima
-            float m[H];
+            // ---------------------------------------------------------------- softmax, single pass, shift folded into the MMA
+            // The pad slot of the head dimension carries the shift: Q_h[row][15] = -shift and K[key][15] = 1, so S
+            // leaves the tensor core as s - shift and the common case is ld -> exp2 -> pack -> st with no other
+            // arithmetic.  shift = max of the first tile + kMargin (P <= 2^-kMargin there); it is refreshed only when
+            // some P reaches 2.0 (bit 14 of an fp16 is set exactly for values >= 2), i.e. a score overshoots the
+            // stale maximum by 2^(kMargin+1).  The shift is rounded to fp16 and the same rounded value is used for
+            // every key of the row and for the rescaling of O, so softmax's shift invariance keeps the result exact.
+            constexpr float kMargin = 6.0f;
+            float sh[H];
 #pragma unroll
-            for (int h = 0; h < H; ++h) m[h] = -INFINITY;
-            for (int t = 0; t < nt; ++t) {
-                const int valid = min(kTileKeys, a.nk - t * kTileKeys);
+            for (int h = 0; h < H; ++h) sh[h] = 0.f;
+            const int q_swz = (lrow >> 2) & 1;
+            unsigned char* q_pad = qs + lrow * 32 + ((1 ^ q_swz) << 4) + 14;      // slot 15 of this row in head 0's tile
+
+            // explicit path of one unit: row maximum, new shift, rescale of O_h (t > 0), P with masking.
+            // r0 / r1 = the 64 scores of this row (unshifted on the first tile, shifted by sh[h] afterwards).
+            auto slow_unit = [&](int t, int h, int valid, const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t (&p)[32]) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c < valid) mx = fmaxf(mx, __uint_as_float(r0[c]));
+                    if (c + 32 < valid) mx = fmaxf(mx, __uint_as_float(r1[c]));
+                }
+                float shift_new, delta;
+                if (t == 0) {
+                    shift_new = -__half2float(__float2half_rn(-(mx + kMargin)));
+                    delta = shift_new;                                 // S of the first tile is unshifted
+                } else {
+                    shift_new = (mx >= 1.0f) ? -__half2float(__float2half_rn(-(sh[h] + mx + kMargin))) : sh[h];
+                    delta = shift_new - sh[h];                         // exact: both are fp16 values
+                    // O_h holds sums relative to the old shift: rescale this row once the PV product of the
+                    // previous tile of this head has landed (completion number layer*nt + t of pv_done[h])
+                    mbar_wait(bars->pv_done + h, (uint32_t)(layer * nt + t - 1) & 1);
+                    tc_fence_after();
+                    uint32_t o[16];
+                    tmem_ld16(lane_addr + C::O_COL + 16 * h, o);
+                    tmem_wait_ld();
+                    const float sc = exp2_fast(-delta);               // 1 for rows that keep their shift
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * sc);
+                    tmem_st16(lane_addr + C::O_COL + 16 * h, o);
+                }
+                sh[h] = shift_new;
+                *reinterpret_cast<__half*>(q_pad + h * 4096) = __float2half_rn(-shift_new);
+                fence_async_smem();                                    // visible to the S products of later tiles
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float e0 = (2 * c < valid) ? exp2_fast(__uint_as_float(r0[2 * c]) - delta) : 0.f;
+                    const float e1 = (2 * c + 1 < valid) ? exp2_fast(__uint_as_float(r0[2 * c + 1]) - delta) : 0.f;
+                    const float e2 = (2 * c + 32 < valid) ? exp2_fast(__uint_as_float(r1[2 * c]) - delta) : 0.f;
+                    const float e3 = (2 * c + 33 < valid) ? exp2_fast(__uint_as_float(r1[2 * c + 1]) - delta) : 0.f;
+                    p[c] = pack_h2(e0, e1);
+                    p[16 + c] = pack_h2(e2, e3);
+                }
+            };
+            auto publish = [&](uint32_t sb, uint32_t i, const uint32_t (&p)[32]) {
+                tmem_st32(sb, p);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bars->p_full + i);
+            };
+
+            // ---- first tile: always the explicit path (fixes the shift of every row)
+            {
+                const int valid = min(kTileKeys, a.nk);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
-                    const int u = t * H + h, i = u & 1, k = u >> 1;
+                    const uint32_t U = (uint32_t)layer * nt * H + h, i = U % C::NBUF, k = U / C::NBUF;
+                    const uint32_t sb = lane_addr + C::S_COL + 64 * i;
                     mbar_wait(bars->s_full + i, k & 1);
                     tc_fence_after();
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(lane_addr + C::S_COL + 64 * i, r0);
-                    tmem_ld32(lane_addr + C::S_COL + 64 * i + 32, r1);
+                    uint32_t r0[32], r1[32], p[32];
+                    tmem_ld32(sb, r0);
+                    tmem_ld32(sb + 32, r1);
                     tmem_wait_ld();
-                    tc_fence_before();
-                    mbar_arrive(bars->sfree1 + i);
-                    float mx = m[h];
-                    if (valid == kTileKeys) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            if (c < valid) mx = fmaxf(mx, __uint_as_float(r0[c]));
-                            if (c + 32 < valid) mx = fmaxf(mx, __uint_as_float(r1[c]));
-                        }
-                    }
-                    m[h] = mx;
+                    slow_unit(0, h, valid, r0, r1, p);
+                    publish(sb, i, p);
                 }
             }
-            // ---------------------------------------------------------------- pass 2: P = 2^(S - m) -> tensor memory
-            for (int t = 0; t < nt; ++t) {
-                const int valid = min(kTileKeys, a.nk - t * kTileKeys);
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const int u = t * H + h, i = u & 1, k = u >> 1;
-                    mbar_wait(bars->s_full + i, k & 1);      // pass-2 uses follow 2*nt pass-1 uses: same parity pattern
+            // ---- remaining tiles: software-pipelined halves.  `cur` = columns 0..31 of the current unit (already
+            //      in registers); columns 32..63 are fetched while the first half is exponentiated, and the first
+            //      half of the NEXT unit while the second half is.
+            if (nt > 1) {
+                uint32_t cur[32], nxt[32], p[32];
+                {
+                    const uint32_t U = ((uint32_t)layer * nt + 1) * H, i = U % C::NBUF, k = U / C::NBUF;
+                    mbar_wait(bars->s_full + i, k & 1);
                     tc_fence_after();
-                    uint32_t r0[32], r1[32], p[32];
-                    tmem_ld32(lane_addr + C::S_COL + 64 * i, r0);
-                    tmem_ld32(lane_addr + C::S_COL + 64 * i + 32, r1);
+                    tmem_ld32(lane_addr + C::S_COL + 64 * i, cur);
                     tmem_wait_ld();
-                    const float mh = m[h];
-                    if (valid == kTileKeys) {      // full tile: no per-element masking code at all
+                }
+                for (int t = 1; t < nt; ++t) {
+                    const int valid = min(kTileKeys, a.nk - t * kTileKeys);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const uint32_t U = ((uint32_t)layer * nt + t) * H + h, i = U % C::NBUF;
+                        const uint32_t sb = lane_addr + C::S_COL + 64 * i;
+                        tmem_ld32(sb + 32, nxt);
+                        uint32_t any = 0;
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            p[c] = pack_h2(exp2_fast(__uint_as_float(r0[2 * c]) - mh), exp2_fast(__uint_as_float(r0[2 * c + 1]) - mh));
-                            p[16 + c] = pack_h2(exp2_fast(__uint_as_float(r1[2 * c]) - mh), exp2_fast(__uint_as_float(r1[2 * c + 1]) - mh));
+                            p[c] = pack_h2(exp2_m<PM>(2 * c, __uint_as_float(cur[2 * c])), exp2_m<PM>(2 * c + 1, __uint_as_float(cur[2 * c + 1])));
+                            any |= p[c];
                         }
-                    } else {
+                        tmem_wait_ld();
+                        const bool has_next = !(t == nt - 1 && h == H - 1);
+                        const uint32_t Un = U + 1, in = Un % C::NBUF, kn = Un / C::NBUF;
+                        bool pre = false;
+                        if (has_next) {
+                            pre = __all_sync(0xffffffffu, mbar_test(bars->s_full + in, kn & 1));
+                            if (pre) {
+                                tc_fence_after();
+                                tmem_ld32(lane_addr + C::S_COL + 64 * in, cur);
+                            }
+                        }
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            const float e0 = (2 * c < valid) ? exp2_fast(__uint_as_float(r0[2 * c]) - mh) : 0.f;
-                            const float e1 = (2 * c + 1 < valid) ? exp2_fast(__uint_as_float(r0[2 * c + 1]) - mh) : 0.f;
-                            const float e2 = (2 * c + 32 < valid) ? exp2_fast(__uint_as_float(r1[2 * c]) - mh) : 0.f;
-                            const float e3 = (2 * c + 33 < valid) ? exp2_fast(__uint_as_float(r1[2 * c + 1]) - mh) : 0.f;
-                            p[c] = pack_h2(e0, e1);
-                            p[16 + c] = pack_h2(e2, e3);
+                            p[16 + c] = pack_h2(exp2_m<PM>(2 * c, __uint_as_float(nxt[2 * c])), exp2_m<PM>(2 * c + 1, __uint_as_float(nxt[2 * c + 1])));
+                            any |= p[16 + c];
+                        }
+                        if (__any_sync(0xffffffffu, (any & 0x40004000u) != 0u)) {
+                            // rare: some score overshot the stale shift -> redo this unit on the explicit path
+                            uint32_t r0[32];
+                            tmem_ld32(sb, r0);
+                            tmem_wait_ld();
+                            slow_unit(t, h, valid, r0, nxt, p);
+                        }
+                        publish(sb, i, p);
+                        if (has_next) {
+                            if (!pre) {
+                                mbar_wait(bars->s_full + in, kn & 1);
+                                tc_fence_after();
+                                tmem_ld32(lane_addr + C::S_COL + 64 * in, cur);
+                            }
+                            tmem_wait_ld();
                         }
                     }
-                    tmem_st32(lane_addr + C::S_COL + 64 * i, p);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(bars->p_full + i);
                 }
             }
             // ---------------------------------------------------------------- O -> normalise -> opark (aliases the idle K/V ring)
@@ -448,17 +513,27 @@ __global__ void __launch_bounds__(Xa3::THREADS, 2) xattn3_kernel(const Xa2Args a
 
 using namespace a3d;
 
-// launched by a3d_xattn_stack (a3d_xattn2.cu) when the "xattn_core" option selects the tcgen05 kernel
-int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
+// launched by a3d_xattn_stack (a3d_xattn2.cu) when the "xattn_core" option selects this kernel
+template <int PM>
+static int launch_pm(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
     static bool once = false;
     if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(xattn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Xa3::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(xattn4_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Xa4::SMEM);
         if (e != cudaSuccess) {
-            set_error("a3d_xattn_stack(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            set_error("a3d_xattn_stack(tcgen05 v4): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return A3D_ECUDA;
         }
         once = true;
     }
-    xattn3_kernel<<<grid, Xa3::THREADS, Xa3::SMEM, stream>>>(a);
-    return check_launch("a3d_xattn_stack(tcgen05)");
+    xattn4_kernel<PM><<<grid, Xa4::THREADS, Xa4::SMEM, stream>>>(a);
+    return check_launch("a3d_xattn_stack(tcgen05 v4)");
+}
+
+int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly) {
+    switch (poly) {   // bit i set: element i of every 8 goes through the FMA-pipe polynomial
+        case 2: return launch_pm<0x11>(a, grid, stream);
+        case 3: return launch_pm<0x49>(a, grid, stream);
+        case 4: return launch_pm<0x55>(a, grid, stream);
+        default: return launch_pm<0>(a, grid, stream);
+    }
 }

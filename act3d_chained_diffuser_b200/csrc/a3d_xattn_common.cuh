@@ -51,7 +51,7 @@ __device__ __forceinline__ void mma_16816_c(float (&d)[4], const uint32_t (&a)[4
 // error 7.5e-5 -- well below the fp16 rounding of P): used for a fraction of the scores so that the MUFU
 // unit (16 results / clk / SM, the measured ceiling of this kernel) and the FMA pipe work in parallel.
 __device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -126.0f);
+    x = fminf(fmaxf(x, -126.0f), 126.0f);       // outside: the exponent insertion below would wrap
     const float t = __fadd_rn(x, 12582912.0f);               // 1.5 * 2^23: rint(x) lands in the low mantissa bits
     const float f = __fsub_rn(x, __fsub_rn(t, 12582912.0f));  // x - rint(x) in [-0.5, 0.5]
     float p = fmaf(0.055170901f, f, 0.24260952f);

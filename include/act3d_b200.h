@@ -111,8 +111,9 @@ int a3d_trunk_fpn_topdown(const float* lat, const float* bias, const float* top,
  * (rows 0..E-1 = W_k, rows EP..EP+E-1 = W_v, EP = 16*H), bkv [nsets][2*EP],
  * rope_host[nsets] (1: rotate K of that set).  Output: K/V "tile images", fp16:
  *   kv [nsets][B][ntiles][2][H][64][16],  ntiles = ceil(nk/64),
- * slot 15 of every V row holds 1.0 for valid keys (the PV product then carries the
- * softmax denominator), padded keys are all-zero; inside a 32-byte row the two 16-byte
+ * slot 15 of every K and V row holds 1.0 for valid keys (V: the PV product then carries the
+ * softmax denominator; K: a query whose slot 15 holds -shift gets shifted scores straight out of the
+ * QK^T product -- queries that leave it 0 are unaffected), padded keys are all-zero; inside a 32-byte row the two 16-byte
  * halves are swapped when (key>>2)&1 (bank-conflict-free ldmatrix).
  * (embed, heads) in {(60,4), (120,8)}.
  */

@@ -162,7 +162,7 @@ def test_ctx_kv_matches_oracle(lib, embed, heads):
         for got, want in ((k[s][:, :, :nk, :15], kk), (v[s][:, :, :nk, :15], vv)):
             tol = want.abs() * 2 ** -10 + 2e-5
             assert ((got - want).abs() <= tol).all(), (got - want).abs().max()
-        assert (k[s][:, :, :nk, 15] == 0).all() and (v[s][:, :, :nk, 15] == 1).all()
+        assert (k[s][:, :, :nk, 15] == 1).all() and (v[s][:, :, :nk, 15] == 1).all()
         assert (k[s][:, :, nk:] == 0).all() and (v[s][:, :, nk:] == 0).all()
 
 

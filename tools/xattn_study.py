@@ -59,7 +59,8 @@ def run(b, nq, nk, tensors, iters=1):
 
 def main():
     lib.load()
-    for gain, tag in ((1.0, "unit-gain"), (4.0, "peaky x4")):
+    variants = [(2, 0), (3, 0), (4, 0), (4, 2), (4, 3), (4, 4)]
+    for gain, tag in ((1.0, "unit-gain"), (4.0, "peaky x4"), (16.0, "peaky x16")):
         b, nq, nk = 2, 1024, 4097
         t = setup(b, nq, nk, gain)
         sd, x0, q_xyz, ctx, c_xyz, qvec = t[:6]
@@ -69,24 +70,27 @@ def main():
                                            rope3d_table(q_xyz.double(), E), rope3d_table(c_xyz.double(), E))[-1].transpose(0, 1)
         lg64 = torch.einsum("jbc,bnc->jbn", qvec.double(), want64)
         rel = lambda a, r: ((a.double() - r).norm() / r.norm()).item()
-        for core in (2, 3):
+        for core, poly in variants:
             lib.set_option("xattn_core", core)
+            lib.set_option("xattn_poly", poly)
             feat, logits, _ = run(b, nq, nk, t)
-            print(json.dumps({"case": tag, "core": core, "feat_rel_l2": rel(feat[0], want64), "logit_rel_l2": rel(logits, lg64)}))
-        lib.set_option("xattn_core", 2)
-        feat, logits, _ = run(b, nq, nk, t)
-        print(json.dumps({"case": tag, "feat_rel_l2": rel(feat[0], want64), "logit_rel_l2": rel(logits, lg64),
-                          "feat_maxabs_over_max": ((feat[0].double() - want64).abs().max() / want64.abs().max()).item()}))
+            print(json.dumps({"case": tag, "core": core, "poly": poly, "feat_rel_l2": rel(feat[0], want64),
+                              "logit_rel_l2": rel(logits, lg64),
+                              "feat_maxabs_over_max": ((feat[0].double() - want64).abs().max() / want64.abs().max()).item()}),
+                  flush=True)
     b, nq, nk = 16, 16384, 4150
     t = setup(b, nq, nk, 1.0)
     flops = 4.0 * nq * nk * E * 2 * b
-    for core in (2, 3):
+    for core, poly in variants:
         lib.set_option("xattn_core", core)
+        lib.set_option("xattn_poly", poly)
         run(b, nq, nk, t, iters=2)
         _, _, ms = run(b, nq, nk, t, iters=5)
-        print(json.dumps({"shape": [b, nq, nk], "core": core, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
-                          "score_elems_per_clk_per_sm@1.965GHz": b * nq * nk * H * 2 / (ms * 1e-3) / 148 / 1.965e9}))
+        print(json.dumps({"shape": [b, nq, nk], "core": core, "poly": poly, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
+                          "score_elems_per_clk_per_sm@1.965GHz": b * nq * nk * H * 2 / (ms * 1e-3) / 148 / 1.965e9}),
+              flush=True)
     lib.set_option("xattn_core", 2)
+    lib.set_option("xattn_poly", 0)
 
 
 if __name__ == "__main__":
