@@ -347,7 +347,10 @@ __global__ void __launch_bounds__(256, 2) xattn2_kernel(const Xa2Args a) {
 
 using namespace a3d;
 
-int g_xattn_core = 2;   // 2: mma.sync core (a3d_xattn2.cu), 3: tcgen05 / TMEM core (a3d_xattn3.cu)
+// 0 (default): pick per launch -- the single-pass tcgen05 / TMEM core (a3d_xattn4.cu) for launches that fill the GPU,
+// the mma.sync core (this file) for the small ones (the 1-token query stack: 16 CTAs, runs on a side stream next to a
+// ghost-point launch whose CTAs own all of an SM's tensor memory); 2 / 3 / 4 force mma.sync / tcgen05 two-pass / single pass
+int g_xattn_core = 0;
 int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
@@ -394,8 +397,9 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.nqv = nqv;
     a.logits = logits;
     dim3 grid((nq + Xa2::ROWS - 1) / Xa2::ROWS, batch);
-    if (g_xattn_core == 3) return a3d_launch_xattn3(a, grid, (cudaStream_t)stream);
-    if (g_xattn_core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
+    const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 4 : 2);
+    if (core == 3) return a3d_launch_xattn3(a, grid, (cudaStream_t)stream);
+    if (core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \
         static bool once = false;                                                                                      \

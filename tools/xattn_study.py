@@ -89,7 +89,7 @@ def main():
         print(json.dumps({"shape": [b, nq, nk], "core": core, "poly": poly, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
                           "score_elems_per_clk_per_sm@1.965GHz": b * nq * nk * H * 2 / (ms * 1e-3) / 148 / 1.965e9}),
               flush=True)
-    lib.set_option("xattn_core", 2)
+    lib.set_option("xattn_core", 0)
     lib.set_option("xattn_poly", 0)
 
 
