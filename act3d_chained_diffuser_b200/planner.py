@@ -100,6 +100,14 @@ class DiffusionHead(nn.Module):
         self._packs = PackCache()
         self.fold_trunk = True
         self._eval_trunk = EvalTrunk()
+        self.parallel_heads = False         # position / rotation heads on two streams: measured SLOWER at C3 (16.9k vs 25.0k steps/s)
+        self._side_stream_obj = None
+
+    @property
+    def _side_stream(self):
+        if self._side_stream_obj is None:
+            self._side_stream_obj = torch.cuda.Stream()
+        return self._side_stream_obj
 
     # ------------------------------------------------------------------ packed weights / tables
     def _ada_layers(self):
@@ -205,7 +213,15 @@ class DiffusionHead(nn.Module):
     # ------------------------------------------------------------------ one denoiser evaluation
     def denoise(self, ctx, trajectory, trajectory_mask, t_idx, work, update=None):
         """One forward of the denoiser on (B, L, 9); returns (pos_upd (B,L,3), rot (B,L,6)) or, with
-        ``update`` (DDPM step arguments), writes the next trajectory in place of returning."""
+        ``update`` (DDPM step arguments), writes the next trajectory in place of returning.
+
+        The position and rotation heads (2 adaLN layers each, diffusion_head.py:344-356) both start from the
+        output of the shared trajectory stack and do not depend on each other, and a cd_post launch is only one
+        CTA per sample (32 of 148 SMs at C3): with ``parallel_heads`` the rotation branch runs on a side stream
+        next to the position branch (fork after the last shared cross-attention, join before the final launch,
+        which needs the position update for the DDPM step).  Bit-identical, but measured slower on B200 (the
+        226 KB-smem cd_post CTAs need whole SMs and wait behind the other branch's 1024-CTA cd_cross), so it
+        is off by default."""
         w = ctx["w"]
         b, length, _ = trajectory.shape
         n_traj = len(self.traj_attention[0].layers)
@@ -214,24 +230,58 @@ class DiffusionHead(nn.Module):
         xb, att, qb = work["x"], work["att"], work["q"]
         enc1, enc2, enc2_b = w["traj_enc"]
         lang_w, lang_v = w["lang"] if self.use_instruction else (None, None)
+        mask = work["mask_u8"]
+        kv, sb, nk = ctx["kv"], ctx["set_bytes"], ctx["nk"]
+
+        def post(li, x_in, att_buf, x_out, **kw):
+            lib.cd_post(trajectory, mask, work["wp_pe"], t_idx, ada, nl, li, x_in, att_buf, w["ada_w"][li], w["ada_v"][li],
+                        x_out, **kw)
+
+        def next_q(li, q_out):
+            return dict(next_wq=w["ada_w"][li], next_bq=w["ada_v"][li], next_ada_layer=li, q_out=q_out)
+
         lib.cd_step_begin(trajectory, work["wp_pe"], t_idx, ada, nl, enc1, enc2, enc2_b, lang_w, lang_v, ctx["lang_k"],
                           ctx["lang_v"], xb[0], w["ada_w"][0], w["ada_v"][0], 0, qb)
-        mask = work["mask_u8"]
-        for li in range(nl):
-            lib.cd_cross(qb, ctx["kv"], li * ctx["set_bytes"], b, ctx["nk"], att)
-            kw = {}
-            x_in = xb[li]
-            if li in (n_traj, n_traj + 2):        # first pos layer and first rot layer both start from the traj stack output
-                x_in = xb[n_traj]
-            if li == n_traj + 1:                  # last pos layer: position regressor; next Q comes from the traj output
-                kw.update(reg_w=w["pos_reg"][0], reg_v=w["pos_reg"][1], reg_out=work["pos_upd"], reg_dim=3,
-                          next_src=xb[n_traj])
-            if li == nl - 1:                      # last rot layer: rotation regressor (+ DDPM update)
-                kw.update(reg_w=w["rot_reg"][0], reg_v=w["rot_reg"][1], reg_out=work["rot_out"], reg_dim=6, update=update)
-            if li + 1 < nl:
-                kw.update(next_wq=w["ada_w"][li + 1], next_bq=w["ada_v"][li + 1], next_ada_layer=li + 1, q_out=qb)
-            lib.cd_post(trajectory, mask, work["wp_pe"], t_idx, ada, nl, li, x_in, att, w["ada_w"][li], w["ada_v"][li],
-                        xb[li + 1], **kw)
+        # ---- shared trajectory stack
+        for li in range(n_traj - 1):
+            lib.cd_cross(qb, kv, li * sb, b, nk, att)
+            post(li, xb[li], att, xb[li + 1], **next_q(li + 1, qb))
+        last = n_traj - 1
+        p0, p1, r0, r1 = n_traj, n_traj + 1, n_traj + 2, n_traj + 3        # the two position / rotation layers
+        pos_reg = dict(reg_w=w["pos_reg"][0], reg_v=w["pos_reg"][1], reg_out=work["pos_upd"], reg_dim=3)
+        rot_reg = dict(reg_w=w["rot_reg"][0], reg_v=w["rot_reg"][1], reg_out=work["rot_out"], reg_dim=6, update=update)
+        lib.cd_cross(qb, kv, last * sb, b, nk, att)
+        if not self.parallel_heads:
+            post(last, xb[last], att, xb[p0], **next_q(p0, qb))
+            lib.cd_cross(qb, kv, p0 * sb, b, nk, att)
+            post(p0, xb[p0], att, xb[p0 + 1], **next_q(p1, qb))
+            lib.cd_cross(qb, kv, p1 * sb, b, nk, att)
+            post(p1, xb[p1], att, xb[p1 + 1], next_src=xb[p0], **pos_reg, **next_q(r0, qb))
+            lib.cd_cross(qb, kv, r0 * sb, b, nk, att)
+            post(r0, xb[p0], att, xb[r0 + 1], **next_q(r1, qb))
+            lib.cd_cross(qb, kv, r1 * sb, b, nk, att)
+            post(r1, xb[r1], att, xb[r1 + 1], **rot_reg)
+            return work["pos_upd"], work["rot_out"]
+
+        main = torch.cuda.current_stream()
+        side = self._side_stream
+        att_p, att_r, q_r, x_r = work["att_pos"], work["att_rot"], work["q_rot"], work["x_rot"]
+        side.wait_stream(main)
+        # last shared layer, evaluated on both streams: each copy also emits the rotary Q of its own branch's first layer
+        post(last, xb[last], att, xb[p0], **next_q(p0, qb))
+        with torch.cuda.stream(side):
+            post(last, xb[last], att, x_r, **next_q(r0, q_r))
+            lib.cd_cross(q_r, kv, r0 * sb, b, nk, att_r)
+            post(r0, x_r, att_r, xb[r0 + 1], **next_q(r1, q_r))
+            lib.cd_cross(q_r, kv, r1 * sb, b, nk, att_r)
+        lib.cd_cross(qb, kv, p0 * sb, b, nk, att_p)
+        post(p0, xb[p0], att_p, xb[p0 + 1], **next_q(p1, qb))
+        lib.cd_cross(qb, kv, p1 * sb, b, nk, att_p)
+        post(p1, xb[p1], att_p, xb[p1 + 1], **pos_reg)
+        side.wait_stream(main)                 # the DDPM update needs the position head and rewrites the trajectory
+        with torch.cuda.stream(side):
+            post(r1, xb[r1], att_r, xb[r1 + 1], **rot_reg)
+        main.wait_stream(side)
         return work["pos_upd"], work["rot_out"]
 
     def make_work(self, b, length, trajectory_mask, device):
@@ -243,7 +293,9 @@ class DiffusionHead(nn.Module):
         return dict(
             x=torch.empty(nl + 1, b, 64, e, device=device),
             att=torch.empty(lib.cd_cross_part_floats(b), device=device),      # partial cross-attention results (cd_cross -> cd_post)
+            att_pos=torch.empty(lib.cd_cross_part_floats(b), device=device), att_rot=torch.empty(lib.cd_cross_part_floats(b), device=device),
             q=torch.empty(b, 8, 64, 16, device=device, dtype=torch.float16),
+            q_rot=torch.empty(b, 8, 64, 16, device=device, dtype=torch.float16), x_rot=torch.empty(b, 64, e, device=device),
             pos_upd=torch.empty(b, length, 3, device=device), rot_out=torch.empty(b, length, 6, device=device),
             wp_pe=sinusoidal(torch.arange(length, device=device), e).float().contiguous(), mask_u8=mask_u8)
 

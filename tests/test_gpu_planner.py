@@ -103,3 +103,24 @@ def test_training_loss_fused_and_differentiable_paths_agree():
     diff = m(*args)
     assert fused.dim() == 0 and torch.isfinite(fused) and diff.requires_grad
     assert abs(fused.item() - diff.item()) <= 1e-3 * abs(diff.item())
+
+
+def test_parallel_heads_are_bit_identical_to_the_sequential_order():
+    """Position / rotation heads on two streams (and inside the captured CUDA graph) == sequential launches."""
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    outs = []
+    for parallel, graph in ((False, False), (True, False), (True, True)):
+        m, _ = build()
+        m = m.cuda()
+        m.prediction_head.parallel_heads = parallel
+        m.use_cuda_graph = graph
+        m._noise_fn = synth.NoiseStream("cd")
+        outs.append(m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                                   "curr_gripper", "goal_gripper")]).cpu())
+        if graph:       # replay of the captured graph on a second call
+            m._noise_fn = synth.NoiseStream("cd")
+            again = m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                                   "curr_gripper", "goal_gripper")]).cpu()
+            assert torch.equal(again, outs[-1])
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])
