@@ -286,13 +286,20 @@ def run_ours(args, rank, world, device, local=0):
     if kern_ms:
         avg = sum(kern_ms) / len(kern_ms)
         ach = flops_launch / (avg * 1e-3) / 1e12
-        roof = {"kernel": "xattn2_kernel (fused ghost-point cross-attention stack)", "bound": "tensor", "achieved": round(ach, 2),
+        # dram__bytes_read + write of one launch from profiles/r1_xattn_ghost_v4_ncu.txt (37.6 MB + 19.6 MB): the K/V
+        # tile images stay in L2, the DRAM traffic is the first touch of K/V plus the part of the ghost features that
+        # spills past L2 -- nowhere near the HBM roofline (0.26 % of peak).
+        roof = {"kernel": "xattn4_kernel (fused ghost-point cross-attention stack, tcgen05/TMEM single pass)",
+                "bound": "tensor", "achieved": round(ach, 2),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
-                "traffic": None, "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
+                "traffic": 57.1e6, "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
                 "share_of_step": round(sum(kern_ms) / ms_res, 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
-                "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample; at head_dim 15 the kernel is bound by the MUFU "
-                        "exp unit (16/clk/SM): ncu XU pipe 76 %, HMMA 40 % (profiles/r1_xattn_ghost_v2_ncu.txt)"}
+                "mufu_floor_ms": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3, 3),
+                "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample.  head_dim 15 means one exp per 30 useful FLOPs: "
+                        "the binding unit is MUFU (16 ex2/clk/SM, measured with tools/micro/mufu_bench.cu), not the tensor pipe; "
+                        "mufu_floor_ms is the launch time at 100 % XU.  ncu: XU pipe 79 %, tensor pipe 13 % "
+                        "(profiles/r1_xattn_ghost_v4_ncu.txt)"}
 
     kf = w["batch"] * world * args.steps
     line = {
