@@ -57,8 +57,12 @@ class DiffusionHead(nn.Module):
         if rotation_parametrization != "6D":
             # traj_encoder is Linear(9, E) in the reference: only '6D' can run
             raise NotImplementedError("only rotation_parametrization='6D' is runnable (as in the reference)")
-        if feat_scales_to_use != 1 or attn_rounds != 1:
-            raise NotImplementedError("feat_scales_to_use > 1 / attn_rounds > 1 are not built yet (DESIGN.md 'next')")
+        if feat_scales_to_use not in (1, 2, 3) or attn_rounds < 1:
+            raise AssertionError("feat_scales_to_use must be 1, 2 or 3 and attn_rounds >= 1")
+        if feat_scales_to_use > 1 and not use_goal:
+            # without a goal the reference attends to the WHOLE fine map (65536 points per camera) at scales > 0
+            # (diffusion_head.py:253-259); only the local-refinement form (find_traj_nn) is built
+            raise NotImplementedError("feat_scales_to_use > 1 needs use_goal=True (local refinement around the trajectory)")
         if use_sigma:
             raise NotImplementedError("use_sigma is never enabled by the reference's entry points")
         if embedding_dim != 120 or num_attn_heads != 8:
@@ -110,16 +114,21 @@ class DiffusionHead(nn.Module):
         return self._side_stream_obj
 
     # ------------------------------------------------------------------ packed weights / tables
-    def _ada_layers(self):
-        return (list(self.traj_attention[0].layers) + list(self.pos_attention[0].layers)
-                + list(self.rot_attention[0].layers))
+    @property
+    def num_offsets(self):
+        """(attention round, feature scale) pairs, each with its own stacks unless weight_tying (diffusion_head.py:56-198)."""
+        return self.attn_rounds * self.feat_scales
 
-    def _weights(self, num_timesteps, device):
+    def _ada_layers(self, off=0):
+        return (list(self.traj_attention[off].layers) + list(self.pos_attention[off].layers)
+                + list(self.rot_attention[off].layers))
+
+    def _weights(self, num_timesteps, device, off=0):
         params = [p for n_, p in self.named_parameters() if not n_.startswith(("backbone.", "feature_pyramid."))]
         e, h = self.embedding_dim, self.num_attn_heads
 
         def build():
-            layers = self._ada_layers()
+            layers = self._ada_layers(off)
             ada = [pack_ada_layer(l, e, h) for l in layers]
             kv = [pack_kv_set(l.cross_12, e, h) for l in layers]
             # adaLN modulation of every (timestep, layer): Linear(SiLU(time_emb))   (layers.py:282-290, encoder.py:199)
@@ -137,78 +146,138 @@ class DiffusionHead(nn.Module):
                 wkv=torch.stack([k[0] for k in kv]).contiguous(), bkv=torch.stack([k[1] for k in kv]).contiguous(),
                 ada=torch.stack(rows, dim=1).contiguous(),                                            # (T, nl, 3, 2, EP)
                 traj_enc=pack_traj_encoder(self.traj_encoder, e),
-                pos_reg=pack_mlp(self.pos_regressor[0], e), rot_reg=pack_mlp(self.rot_regressor[0], e),
-                lang=pack_lang_layer(self.traj_lang_attention[0].layers[0], e, h),
+                pos_reg=pack_mlp(self.pos_regressor[off], e), rot_reg=pack_mlp(self.rot_regressor[off], e),
+                lang=pack_lang_layer(self.traj_lang_attention[off].layers[0], e, h),
             )
             if self.use_instruction:
-                vl = [pack_lang_layer(l, e, h) for l in self.vl_attention[0].layers]
+                vl = [pack_lang_layer(l, e, h) for l in self.vl_attention[off].layers]
                 out["vl_w"] = torch.cat([x[0] for x in vl]).contiguous()
                 out["vl_v"] = torch.cat([x[1] for x in vl]).contiguous()
             return out
-        return self._packs.get(("planner", num_timesteps, str(device)), params, build)
+        return self._packs.get(("planner", num_timesteps, str(device), off), params, build)
 
     # ------------------------------------------------------------------ step-invariant context
     def encode_context(self, visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, num_timesteps,
-                       static=None):
+                       static=None, length=None):
         """Everything of DiffusionHead.forward that does not depend on the trajectory or the timestep
-        (diffusion_head.py:221-247, 289-323).  ``static``: dict of persistent buffers (kv, lang_k, lang_v) to
-        write into, so that a captured CUDA graph of the sampling loop can be replayed on new inputs."""
+        (diffusion_head.py:221-247, 289-323).  Returns one context record per (round, scale) offset in
+        ``ctx["offs"]``: for scale 0 the finished K/V cache of the whole coarse map; for scales > 0 (local
+        refinement, needs ``length``) the buffers that ``refresh_local`` fills from the current trajectory.
+        ``static``: dict of persistent buffers (kv, lang_k, lang_v) to write into, so that a captured CUDA graph
+        of the single-offset sampling loop can be replayed on new inputs."""
         lib.load()
         e, h = self.embedding_dim, self.num_attn_heads
         b, ncam = visible_rgb.shape[:2]
         dev = visible_rgb.device
-        w = self._weights(num_timesteps, dev)
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:])
+        needed = tuple(dict.fromkeys(self.feature_map_pyramid[s] for s in range(self.feat_scales)))
         if self.training or not self.fold_trunk or isinstance(self.backbone, torch.nn.Identity):
             fpn, fpn_bias = self.feature_pyramid(self.backbone(self.normalize(rgb))), {}
         else:
-            fpn, fpn_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=("res3",),
+            fpn, fpn_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=needed,
                                              defer_bias=True)
-        fm = fpn["res3"].float()                                  # NCHW or channels-last: the gather reads either in place
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
-        pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
-        nctx = pts.shape[1]
-        rows = nctx + 1 + int(self.use_goal)
-        tok = torch.empty(b, rows, e, device=dev)
-        pos = torch.empty(b, rows, 3, device=dev)
-        lib.gather_tokens(fm, pts, None, b, ncam, tok, pos, bias=fpn_bias.get("res3"))
+        levels, pts_cache = [], {}
+        for s in range(self.feat_scales):
+            f = self.downscaling_factor_pyramid[s]
+            if f not in pts_cache:
+                pts_cache[f] = lib.pcd_pyramid(pcd, f).view(b, -1, 3)
+            name = self.feature_map_pyramid[s]
+            levels.append(dict(fm=fpn[name].float(), bias=fpn_bias.get(name), pts=pts_cache[f]))
+        n_goal = int(self.use_goal)
+        cur_tok = self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight[0]
+        goal_tok = (self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight[0]) if self.use_goal else None
+        instr = F.linear(instruction.float(), self.instruction_encoder.weight, self.instruction_encoder.bias) \
+            if self.use_instruction else None
 
-        ctx = dict(nk=rows, batch=b)
-        if self.use_instruction:
-            instr = F.linear(instruction.float(), self.instruction_encoder.weight, self.instruction_encoder.bias)
+        def instr_kv(attn):
+            wi, bi = attn.in_proj_weight, attn.in_proj_bias
+            return (F.linear(instr, wi[e:2 * e], bi[e:2 * e]).contiguous(),
+                    F.linear(instr, wi[2 * e:], bi[2 * e:]).contiguous())
 
-            def instr_kv(attn):
-                wi, bi = attn.in_proj_weight, attn.in_proj_bias
-                return (F.linear(instr, wi[e:2 * e], bi[e:2 * e]).contiguous(),
-                        F.linear(instr, wi[2 * e:], bi[2 * e:]).contiguous())
-            vl_layers = self.vl_attention[0].layers
-            kvs = [instr_kv(l.cross_12) for l in vl_layers]
-            lib.cd_ctx_lang(tok, nctx, torch.stack([k for k, _ in kvs]), torch.stack([v for _, v in kvs]),
-                            w["vl_w"], w["vl_v"], len(vl_layers))
-            lk, lv = instr_kv(self.traj_lang_attention[0].layers[0].cross_12)
-            if static is not None and static.get("lang_k") is not None:
-                static["lang_k"].copy_(lk)
-                static["lang_v"].copy_(lv)
-                lk, lv = static["lang_k"], static["lang_v"]
-            elif static is not None:
-                static["lang_k"], static["lang_v"] = lk, lv
-            ctx["lang_k"], ctx["lang_v"] = lk, lv
-        else:
-            ctx["lang_k"] = ctx["lang_v"] = None
-
-        tok[:, nctx] = self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight[0]
-        pos[:, nctx] = curr_gripper[:, :3].float()
-        if self.use_goal:
-            tok[:, nctx + 1] = self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight[0]
-            pos[:, nctx + 1] = goal_gripper[:, :3].float()
-        nl = len(w["ada_w"])
-        ctx["kv"] = lib.ctx_kv(tok, pos, rows, h, w["wkv"], w["bkv"], [1] * nl,
-                               out=static.get("kv") if static is not None else None)
-        if static is not None:
-            static["kv"] = ctx["kv"]
-        ctx["set_bytes"] = lib.kv_bytes(1, b, rows, h)
-        ctx["w"] = w
+        ctx = dict(batch=b, ncam=ncam, levels=levels, offs=[], cur_tok=cur_tok, goal_tok=goal_tok,
+                   cur_xyz=curr_gripper[:, :3].float(), goal_xyz=goal_gripper[:, :3].float() if self.use_goal else None)
+        for off in range(self.num_offsets):
+            scale = off % self.feat_scales
+            w = self._weights(num_timesteps, dev, off)
+            nl = len(w["ada_w"])
+            oc = dict(w=w, scale=scale, batch=b)
+            if self.use_instruction:
+                kvs = [instr_kv(l.cross_12) for l in self.vl_attention[off].layers]
+                oc["vl_k"], oc["vl_v"] = torch.stack([k for k, _ in kvs]), torch.stack([v for _, v in kvs])
+                lk, lv = instr_kv(self.traj_lang_attention[off].layers[0].cross_12)
+                if static is not None and off == 0:
+                    if static.get("lang_k") is not None:
+                        static["lang_k"].copy_(lk)
+                        static["lang_v"].copy_(lv)
+                        lk, lv = static["lang_k"], static["lang_v"]
+                    else:
+                        static["lang_k"], static["lang_v"] = lk, lv
+                oc["lang_k"], oc["lang_v"] = lk, lv
+            else:
+                oc["lang_k"] = oc["lang_v"] = None
+            lvl = levels[scale]
+            if scale == 0:
+                nvis = lvl["pts"].shape[1]
+            else:
+                if length is None:
+                    raise ValueError("encode_context: local refinement scales need the trajectory length")
+                nvis = (64 if scale == 1 else 16) * length            # find_traj_nn, diffusion_head.py:253-259
+            rows = nvis + 1 + n_goal
+            oc.update(nvis=nvis, nk=rows, set_bytes=lib.kv_bytes(1, b, rows, h),
+                      tok=torch.empty(b, rows, e, device=dev), pos=torch.empty(b, rows, 3, device=dev))
+            if scale == 0:
+                lib.gather_tokens(lvl["fm"], lvl["pts"], None, b, ncam, oc["tok"], oc["pos"], bias=lvl["bias"])
+                self._finish_context(ctx, oc, static.get("kv") if (static is not None and off == 0) else None)
+                if static is not None and off == 0:
+                    static["kv"] = oc["kv"]
+            else:
+                oc["kv"] = torch.empty(lib.kv_bytes(nl, b, rows, h), device=dev, dtype=torch.uint8)
+            ctx["offs"].append(oc)
+        # single-offset accessors used by the captured sampling loop
+        first = ctx["offs"][0]
+        ctx.update(kv=first["kv"], nk=first["nk"], set_bytes=first["set_bytes"], w=first["w"],
+                   lang_k=first["lang_k"], lang_v=first["lang_v"])
         return ctx
+
+    def _finish_context(self, ctx, oc, kv_out=None):
+        """Visual tokens already gathered into oc["tok"][:, :nvis]: vision->language attention, gripper / goal
+        tokens, rotary K/V cache of the 8 cross-attention layers of this offset (diffusion_head.py:305-323)."""
+        h = self.num_attn_heads
+        w, nvis = oc["w"], oc["nvis"]
+        if self.use_instruction:
+            lib.cd_ctx_lang(oc["tok"], nvis, oc["vl_k"], oc["vl_v"], w["vl_w"], w["vl_v"], oc["vl_k"].shape[0])
+        oc["tok"][:, nvis] = ctx["cur_tok"]
+        oc["pos"][:, nvis] = ctx["cur_xyz"]
+        if self.use_goal:
+            oc["tok"][:, nvis + 1] = ctx["goal_tok"]
+            oc["pos"][:, nvis + 1] = ctx["goal_xyz"]
+        nl = len(w["ada_w"])
+        oc["kv"] = lib.ctx_kv(oc["tok"], oc["pos"], oc["nk"], h, w["wkv"], w["bkv"], [1] * nl,
+                              out=kv_out if kv_out is not None else oc.get("kv"))
+
+    def refresh_local(self, ctx, off, traj_xyz):
+        """Local refinement context of offset ``off`` (scale > 0): the 64*L / 16*L fine points nearest the current
+        trajectory estimate (find_traj_nn, utils.py:38-48 -> a3d_traj_topk), their features, and the K/V cache."""
+        oc = ctx["offs"][off]
+        lvl = ctx["levels"][oc["scale"]]
+        idx = lib.traj_topk(traj_xyz.contiguous().float(), lvl["pts"], oc["nvis"])
+        lib.gather_tokens(lvl["fm"], lvl["pts"], idx, ctx["batch"], ctx["ncam"], oc["tok"], oc["pos"], bias=lvl["bias"])
+        self._finish_context(ctx, oc)
+        return idx
+
+    def denoise_offsets(self, ctx, trajectory, trajectory_mask, t_idx, work):
+        """All (round, scale) refinements of one denoiser evaluation: list of (B, L, 9) trajectories
+        (diffusion_head.py:249-277).  Token features and rotary positions always come from the INPUT trajectory;
+        each offset refines the previous offset's estimate."""
+        outs, base = [], trajectory
+        for off, oc in enumerate(ctx["offs"]):
+            if oc["scale"] > 0:
+                self.refresh_local(ctx, off, base[..., :3])
+            pos_upd, rot = self.denoise(oc, trajectory, trajectory_mask, t_idx, work)
+            base = torch.cat((base[..., :3] + pos_upd, rot), -1)
+            outs.append(base)
+        return outs
 
     # ------------------------------------------------------------------ one denoiser evaluation
     def denoise(self, ctx, trajectory, trajectory_mask, t_idx, work, update=None):
@@ -222,7 +291,7 @@ class DiffusionHead(nn.Module):
         which needs the position update for the DDPM step).  Bit-identical, but measured slower on B200 (the
         226 KB-smem cd_post CTAs need whole SMs and wait behind the other branch's 1024-CTA cd_cross), so it
         is off by default."""
-        w = ctx["w"]
+        w = ctx["w"]                               # ctx: the record of ONE offset (or the single-offset context)
         b, length, _ = trajectory.shape
         n_traj = len(self.traj_attention[0].layers)
         nl = len(w["ada_w"])
@@ -309,59 +378,78 @@ class DiffusionHead(nn.Module):
             return self._forward_train(trajectory, trajectory_mask, timestep, visible_rgb, visible_pcd, curr_gripper,
                                        goal_gripper, instruction)
         n_t = int(timestep.max().item()) + 1
-        ctx = self.encode_context(visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, max(n_t, 100))
         b, length, _ = trajectory.shape
+        ctx = self.encode_context(visible_rgb, visible_pcd, instruction, curr_gripper, goal_gripper, max(n_t, 100),
+                                  length=length)
         work = self.make_work(b, length, trajectory_mask, trajectory.device)
         traj = trajectory.float().contiguous()
-        pos_upd, rot = self.denoise(ctx, traj, trajectory_mask, timestep.to(torch.int32).contiguous(), work)
-        return [torch.cat((traj[..., :3] + pos_upd, rot), -1)]
+        return self.denoise_offsets(ctx, traj, trajectory_mask, timestep.to(torch.int32).contiguous(), work)
 
 
     # ------------------------------------------------------------------ differentiable forward (training)
     def _forward_train(self, trajectory, trajectory_mask, timestep, visible_rgb, visible_pcd, curr_gripper,
                        goal_gripper, instruction):
         """One denoiser evaluation with an autograd graph to every trainable parameter
-        (diffusion_head.py:200-363, encoder.py:81-203).  Attention cores (with the reference's 0.1 dropout on
-        the attention weights in train mode), rotary embedding and token gather are the kernels of
-        csrc/a3d_train.cu; projections, adaLN, LayerNorm, FFN and the regressors are torch.nn ops."""
+        (diffusion_head.py:200-363, encoder.py:81-203); returns the list of refinements (one per offset).
+        Attention cores (with the reference's 0.1 dropout on the attention weights in train mode), rotary
+        embedding and token gather are the kernels of csrc/a3d_train.cu; projections, adaLN, LayerNorm, FFN and
+        the regressors are torch.nn ops."""
         lib.load()
         e = self.embedding_dim
         b, ncam = visible_rgb.shape[:2]
         dev = trajectory.device
         training = self.training
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:]).float()
-        fm = self.feature_pyramid(self.backbone(self.normalize(rgb)))["res3"].float()
+        fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
-        pts = lib.pcd_pyramid(pcd, 8).view(b, -1, 3)
-        ctx, ctx_pos = gather_tokens(fm, pts, None, b, ncam)                          # (B, ncam*1024, E)
-        instr = None
-        if self.use_instruction:
-            instr = self.instruction_encoder(instruction.float())
-            ctx = train_layers.parallel_stack(self.vl_attention[0], ctx, None, instr, training=training)
-        cur = self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight
-        ctx = torch.cat([ctx, cur.unsqueeze(1)], dim=1)
-        ctx_pos = torch.cat([ctx_pos, curr_gripper[:, None, :3].float()], dim=1)
+        pts_cache = {}
+        for s_ in range(self.feat_scales):
+            f = self.downscaling_factor_pyramid[s_]
+            if f not in pts_cache:
+                pts_cache[f] = lib.pcd_pyramid(pcd, f).view(b, -1, 3)
+        instr = self.instruction_encoder(instruction.float()) if self.use_instruction else None
+        cur = (self.curr_gripper_encoder(curr_gripper.float()) + self.curr_gripper_embed.weight).unsqueeze(1)
+        cur_xyz = curr_gripper[:, None, :3].float()
         if self.use_goal:
-            goal = self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight
-            ctx = torch.cat([ctx, goal.unsqueeze(1)], dim=1)
-            ctx_pos = torch.cat([ctx_pos, goal_gripper[:, None, :3].float()], dim=1)
+            goal = (self.goal_gripper_encoder(goal_gripper.float()) + self.goal_gripper_embed.weight).unsqueeze(1)
+            goal_xyz = goal_gripper[:, None, :3].float()
 
         traj = trajectory.float()
-        x = self.traj_encoder(traj)
+        x0 = self.traj_encoder(traj)                                                  # once, from the input trajectory
         traj_pos = traj[..., :3].detach().contiguous()
         t_emb = sinusoidal(timestep.to(dev), e).float()                               # encoder.py:199
         wp_pe = sinusoidal(torch.arange(traj.shape[1], device=dev), e).float()[None]  # diffusion_head.py:326-328
         mask = trajectory_mask if trajectory_mask is not None and bool(trajectory_mask.any()) else None
-        if self.use_instruction:                                                      # diffusion_head.py:330-336
-            x = train_layers.parallel_stack(self.traj_lang_attention[0], x, mask, instr, sem_pos=wp_pe,
-                                            training=training)
-        common = dict(x_mask=mask, ctx=ctx, x_pos=traj_pos, ctx_pos=ctx_pos, sem_pos=wp_pe, t_emb=t_emb,
-                      training=training)
-        x = train_layers.parallel_stack(self.traj_attention[0], x, **common)
-        pos_f = train_layers.parallel_stack(self.pos_attention[0], x, **common)
-        rot_f = train_layers.parallel_stack(self.rot_attention[0], x, **common)
-        upd = torch.cat((self.pos_regressor[0](pos_f), self.rot_regressor[0](rot_f)), -1)
-        return [torch.cat((traj[..., :3] + upd[..., :3], upd[..., 3:]), -1)]          # diffusion_head.py:271-274
+        outs, base = [], traj
+        for off in range(self.num_offsets):
+            scale = off % self.feat_scales
+            fm = fpn[self.feature_map_pyramid[scale]].float()
+            pts = pts_cache[self.downscaling_factor_pyramid[scale]]
+            idx = None
+            if scale > 0:                                                             # diffusion_head.py:253-259
+                with torch.no_grad():
+                    idx = lib.traj_topk(base[..., :3].detach().contiguous(), pts, (64 if scale == 1 else 16) * traj.shape[1])
+            ctx, ctx_pos = gather_tokens(fm, pts, idx, b, ncam)
+            if self.use_instruction:
+                ctx = train_layers.parallel_stack(self.vl_attention[off], ctx, None, instr, training=training)
+            ctx = torch.cat([ctx, cur], dim=1)
+            ctx_pos = torch.cat([ctx_pos, cur_xyz], dim=1)
+            if self.use_goal:
+                ctx = torch.cat([ctx, goal], dim=1)
+                ctx_pos = torch.cat([ctx_pos, goal_xyz], dim=1)
+            x = x0
+            if self.use_instruction:                                                  # diffusion_head.py:330-336
+                x = train_layers.parallel_stack(self.traj_lang_attention[off], x, mask, instr, sem_pos=wp_pe,
+                                                training=training)
+            common = dict(x_mask=mask, ctx=ctx, x_pos=traj_pos, ctx_pos=ctx_pos, sem_pos=wp_pe, t_emb=t_emb,
+                          training=training)
+            x = train_layers.parallel_stack(self.traj_attention[off], x, **common)
+            pos_f = train_layers.parallel_stack(self.pos_attention[off], x, **common)
+            rot_f = train_layers.parallel_stack(self.rot_attention[off], x, **common)
+            upd = torch.cat((self.pos_regressor[off](pos_f), self.rot_regressor[off](rot_f)), -1)
+            base = torch.cat((base[..., :3] + upd[..., :3], upd[..., 3:]), -1)        # diffusion_head.py:271-274
+            outs.append(base)
+        return outs
 
 
 class DiffusionPlanner(nn.Module):
@@ -443,6 +531,23 @@ class DiffusionPlanner(nn.Module):
                        noise_pos=st["noise_pos"][k], noise_rot=st["noise_rot"][k])
             head.denoise(ctx, st["traj"], trajectory_mask, t_all[k], work, update=upd)
 
+    def _run_steps_multi(self, ctx, st, work, trajectory_mask, timesteps, t_all):
+        """Sampling loop with several refinements per step (diffusion_model.py:98-117 over diffusion_head.py:249-277)."""
+        head = self.prediction_head
+        pc, rc = self.position_noise_scheduler.coef, self.rotation_noise_scheduler.coef
+        cmask = st["cmask"].bool()
+        for k, t in enumerate(timesteps):
+            traj = st["traj"]
+            out = head.denoise_offsets(ctx, traj, trajectory_mask, t_all[k], work)[-1]
+            out = torch.where(cmask, st["cond"], out)
+            if k == len(timesteps) - 1:
+                nxt = out
+            else:
+                pos = pc[t, 0] * out[..., :3].clamp(-1, 1) + pc[t, 1] * traj[..., :3] + pc[t, 2] * st["noise_pos"][k]
+                rot = rc[t, 0] * out[..., 3:9].clamp(-1, 1) + rc[t, 1] * traj[..., 3:9] + rc[t, 2] * st["noise_rot"][k]
+                nxt = torch.cat((pos, rot), -1)
+            st["traj"].copy_(nxt)
+
     @torch.no_grad()
     def conditional_sample(self, condition_data, condition_mask, fixed_inputs):
         """100-step DDPM ancestral sampling with inpainting of the conditioned waypoints
@@ -459,8 +564,9 @@ class DiffusionPlanner(nn.Module):
         timesteps = self.position_noise_scheduler.timesteps
         has_mask = trajectory_mask is not None and bool(trajectory_mask.any())
         st = self._sampler_state(b, length, (rgb_obs.shape[1], has_mask), dev)
+        multi = head.num_offsets > 1
         ctx = head.encode_context(rgb_obs, pcd_obs, instruction, curr_gripper, goal_gripper, self.n_steps,
-                                  static=st["static"])
+                                  static=None if multi else st["static"], length=length)
         if "work" not in st:
             st["work"] = head.make_work(b, length, trajectory_mask, dev)
             st["t_all"] = torch.tensor(timesteps, device=dev, dtype=torch.int32)[:, None].repeat(1, b).contiguous()
@@ -479,6 +585,11 @@ class DiffusionPlanner(nn.Module):
             st["noise_pos"].normal_()
             st["noise_rot"].normal_()
 
+        if multi:
+            # coarse-to-fine refinement (feat_scales_to_use > 1 / attn_rounds > 1): the local context is rebuilt from
+            # the running estimate inside every step; launched eagerly (no graph), DDPM update as elementwise torch ops
+            self._run_steps_multi(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
+            return st["traj"].clone()
         if not self.use_cuda_graph:
             self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
             return st["traj"].clone()
@@ -543,6 +654,8 @@ class DiffusionPlanner(nn.Module):
         t = torch.randint(0, self.n_steps, (len(noise),), device=dev).long()
         noisy = torch.cat((self.position_noise_scheduler.add_noise(gt[..., :3], noise[..., :3], t),
                            self.rotation_noise_scheduler.add_noise(gt[..., 3:9], noise[..., 3:9], t)), -1)
-        pred = self.prediction_head(noisy, trajectory_mask, t, rgb_obs, pcd_n, cur, goal, instruction)[-1]
-        return (100 * F.l1_loss(pred[..., :3], gt[..., :3], reduction="mean")
-                + 10 * F.l1_loss(pred[..., 3:9], gt[..., 3:9], reduction="mean"))
+        total = 0
+        for pred in self.prediction_head(noisy, trajectory_mask, t, rgb_obs, pcd_n, cur, goal, instruction):
+            total = total + (100 * F.l1_loss(pred[..., :3], gt[..., :3], reduction="mean")      # diffusion_model.py:315-324
+                             + 10 * F.l1_loss(pred[..., 3:9], gt[..., 3:9], reduction="mean"))
+        return total

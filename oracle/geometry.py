@@ -52,6 +52,13 @@ def local_topk_exact(center: np.ndarray, points: np.ndarray, k: int) -> np.ndarr
     return order[:, :k].astype(np.int64), d
 
 
+def find_traj_nn(trajectory: torch.Tensor, points: torch.Tensor, nn_: int) -> torch.Tensor:
+    """Indices of the nn_ * L points closest to ANY waypoint (squared distance to the nearest waypoint,
+    ascending).  trajectory (B, L, 3), points (B, P, 3) -> (B, nn_ * L).  Reference: utils.py:38-48."""
+    d = ((trajectory[:, :, None] - points[:, None]) ** 2).sum(-1)
+    return d.min(1).values.topk(k=nn_ * trajectory.shape[1], dim=-1, largest=False).indices
+
+
 def normalise_quat(x: torch.Tensor) -> torch.Tensor:
     """Reference: model/utils/utils.py:51-52."""
     return x / torch.clamp(x.square().sum(dim=-1).sqrt().unsqueeze(-1), min=1e-10)

@@ -4,8 +4,8 @@ Functional CPU restatement of
   model/trajectory_optimization/diffusion_head.py:200-363   (DiffusionHead.forward / _one_attention_round)
   model/utils/encoder.py:81-203                              (token encoders)
   model/trajectory_optimization/diffusion_model.py:64-324    (DiffusionPlanner)
-for the shipped configuration family: rotation_parametrization='6D', feat_scales_to_use=1,
-attn_rounds=1.  ``sd`` holds the keys under ``prediction_head.`` with that
+for rotation_parametrization='6D' (the only runnable one), any attn_rounds, and
+feat_scales_to_use in {1, 2, 3} (coarse-to-fine local refinement around the trajectory, find_traj_nn).  ``sd`` holds the keys under ``prediction_head.`` with that
 prefix stripped.
 """
 from dataclasses import dataclass
@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 from .attention import parallel_attention_stack
 from .ddpm import DDPMScheduler
-from .geometry import (matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix,
+from .geometry import (find_traj_nn, matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix,
                        pcd_level, quat_to_matrix)
 from .rope import rope3d_table, sinusoidal_embedding
 
@@ -32,6 +32,8 @@ class PlannerConfig:
     use_goal_at_test: bool = False
     gripper_loc_bounds: object = None
     diffusion_timesteps: int = 100
+    feat_scales_to_use: int = 1
+    attn_rounds: int = 1
 
 
 def _mlp2(sd, p, x, i0="0", i1="3"):
@@ -39,58 +41,103 @@ def _mlp2(sd, p, x, i0="0", i1="3"):
                     sd[f"{p}{i1}.weight"], sd[f"{p}{i1}.bias"])
 
 
+FEATURE_MAP_PYRAMID = ["res3", "res1", "res1", "res1"]        # encoder.py:52-53
+DOWNSCALING_PYRAMID = [8, 2, 2, 2]
+
+
 def encode_context(sd, cfg: PlannerConfig, trunk: Callable, rgb, pcd, instruction, curr_gripper, goal_gripper):
     """Everything in DiffusionHead.forward that does not depend on the trajectory or the
-    timestep: trunk features, context rotary table, vision->language
-    attention, gripper / goal tokens, instruction tokens."""
+    timestep: trunk features and point pyramid of every scale, instruction tokens,
+    gripper / goal tokens, and -- for the scale-0 offsets, whose context is the whole coarse map --
+    the context after the vision->language attention."""
     e, h = cfg.embedding_dim, cfg.num_attn_heads
     b, ncam = rgb.shape[:2]
     fpn = trunk(rgb.reshape(b * ncam, *rgb.shape[2:]))                       # encoder.py:133-139
-    fm = fpn["res3"]
-    ctx = fm.view(b, ncam, *fm.shape[1:]).permute(0, 1, 3, 4, 2).reshape(b, -1, e)   # diffusion_head.py:290-293
-    pts = pcd_level(pcd.reshape(b * ncam, *pcd.shape[2:]), 8, ncam)          # encoder.py:147-158
-    ctx_rope = rope3d_table(pts, e)
+    pcd_flat = pcd.reshape(b * ncam, *pcd.shape[2:])
+    feats, pts = [], []
+    for s in range(cfg.feat_scales_to_use):                                  # encoder.py:141-167
+        fm = fpn[FEATURE_MAP_PYRAMID[s]]
+        feats.append(fm.view(b, ncam, *fm.shape[1:]).permute(0, 1, 3, 4, 2).reshape(b, -1, e))   # diffusion_head.py:290-293
+        pts.append(pcd_level(pcd_flat, DOWNSCALING_PYRAMID[s], ncam))
 
     instr, instr_rope = None, None
     if cfg.use_instruction:                                                  # encoder.py:169-187
         instr = F.linear(instruction, sd["instruction_encoder.weight"], sd["instruction_encoder.bias"])
         instr_rope = rope3d_table(torch.zeros(b, instr.shape[1], 3), e)
-        ctx = parallel_attention_stack(sd, "vl_attention.0.", h, cfg.num_vis_ins_attn_layers,   # diffusion_head.py:305-314
-                                       ctx, None, instr)
 
     cur = F.linear(curr_gripper, sd["curr_gripper_encoder.weight"], sd["curr_gripper_encoder.bias"])[:, None]
     cur = cur + sd["curr_gripper_embed.weight"].repeat(b, 1).unsqueeze(1)    # diffusion_head.py:231-237
-    ctx = torch.cat([ctx, cur], dim=1)
-    ctx_rope = torch.cat([ctx_rope, rope3d_table(curr_gripper[:, :3][:, None], e)], dim=1)
-    if cfg.use_goal:                                                         # diffusion_head.py:239-247, 320-323
+    goal = None
+    if cfg.use_goal:                                                         # diffusion_head.py:239-247
         goal = F.linear(goal_gripper, sd["goal_gripper_encoder.weight"], sd["goal_gripper_encoder.bias"])[:, None]
         goal = goal + sd["goal_gripper_embed.weight"].repeat(b, 1).unsqueeze(1)
-        ctx = torch.cat([ctx, goal], dim=1)
-        ctx_rope = torch.cat([ctx_rope, rope3d_table(goal_gripper[:, :3][:, None], e)], dim=1)
-    return {"ctx": ctx, "ctx_rope": ctx_rope, "instr": instr, "instr_rope": instr_rope, "pcd": pts}
+    out = {"feats": feats, "pts": pts, "instr": instr, "instr_rope": instr_rope, "cur": cur, "goal": goal,
+           "cur_xyz": curr_gripper[:, :3], "goal_xyz": goal_gripper[:, :3], "pcd": pts[0], "static": {}}
+    for off in range(cfg.attn_rounds * cfg.feat_scales_to_use):
+        if off % cfg.feat_scales_to_use == 0:
+            out["static"][off] = _offset_context(sd, cfg, out, off, None)
+    out["ctx"], out["ctx_rope"] = out["static"][0]
+    return out
 
 
-def denoise_once(sd, cfg: PlannerConfig, context, trajectory, trajectory_mask, timestep):
-    """One DiffusionHead.forward given the step-invariant context.  Returns (B, L, 9).
-    diffusion_head.py:215-277 (token prep) and :325-363 (attention + regressors)."""
+def _offset_context(sd, cfg: PlannerConfig, context, off, p_inds):
+    """Context tokens + rotary table of one (round, scale) offset: visual tokens (all of them, or the
+    p_inds subset), vision->language attention, current / goal gripper tokens.  diffusion_head.py:289-323."""
+    e, h = cfg.embedding_dim, cfg.num_attn_heads
+    scale = off % cfg.feat_scales_to_use
+    feats, pts = context["feats"][scale], context["pts"][scale]
+    if p_inds is not None:                                                   # diffusion_head.py:295-302
+        feats = torch.stack([f[i] for f, i in zip(feats, p_inds)])
+        pts = torch.stack([f[i] for f, i in zip(pts, p_inds)])
+    rope = rope3d_table(pts, e)
+    if cfg.use_instruction:                                                  # diffusion_head.py:305-314
+        feats = parallel_attention_stack(sd, f"vl_attention.{off}.", h, cfg.num_vis_ins_attn_layers,
+                                         feats, None, context["instr"])
+    feats = torch.cat([feats, context["cur"]], dim=1)
+    rope = torch.cat([rope, rope3d_table(context["cur_xyz"][:, None], e)], dim=1)
+    if cfg.use_goal:                                                         # diffusion_head.py:320-323
+        feats = torch.cat([feats, context["goal"]], dim=1)
+        rope = torch.cat([rope, rope3d_table(context["goal_xyz"][:, None], e)], dim=1)
+    return feats, rope
+
+
+def denoise_all(sd, cfg: PlannerConfig, context, trajectory, trajectory_mask, timestep):
+    """One DiffusionHead.forward given the step-invariant context: the list of refined trajectories, one per
+    (attention round, feature scale) offset.  diffusion_head.py:215-277 (token prep, loop) and :325-363."""
     e, h = cfg.embedding_dim, cfg.num_attn_heads
     b, length, _ = trajectory.shape
-    x = _mlp2(sd, "traj_encoder.", trajectory)
+    x0 = _mlp2(sd, "traj_encoder.", trajectory)                              # computed once from the input trajectory
     traj_rope = rope3d_table(trajectory[..., :3], e)
     t_emb = sinusoidal_embedding(timestep, e)                                # encoder.py:199
     wp_pe = sinusoidal_embedding(torch.arange(0, length), e)[None].repeat(b, 1, 1)   # diffusion_head.py:326-328
+    outs = []
+    for off in range(cfg.attn_rounds * cfg.feat_scales_to_use):
+        scale = off % cfg.feat_scales_to_use
+        if cfg.use_goal and scale > 0:                                       # diffusion_head.py:253-259
+            p_inds = find_traj_nn(outs[-1][..., :3], context["pts"][scale], 64 if scale == 1 else 16)
+            ctx, ctx_rope = _offset_context(sd, cfg, context, off, p_inds)
+        elif off in context["static"]:
+            ctx, ctx_rope = context["static"][off]
+        else:
+            ctx, ctx_rope = _offset_context(sd, cfg, context, off, None)
+        x = x0
+        if cfg.use_instruction:                                              # diffusion_head.py:330-336
+            x = parallel_attention_stack(sd, f"traj_lang_attention.{off}.", h, 1, x, trajectory_mask, context["instr"],
+                                         seq1_sem_pos=wp_pe, apply_ffn=False)
+        common = dict(seq1_mask=trajectory_mask, seq2=ctx, seq1_rope=traj_rope, seq2_rope=ctx_rope,
+                      seq1_sem_pos=wp_pe, ada_signal=t_emb, self_attention=True, rotary=True, use_adaln=True)
+        x = parallel_attention_stack(sd, f"traj_attention.{off}.", h, cfg.num_query_cross_attn_layers - 2, x, **common)
+        pos_f = parallel_attention_stack(sd, f"pos_attention.{off}.", h, 2, x, **common)
+        rot_f = parallel_attention_stack(sd, f"rot_attention.{off}.", h, 2, x, **common)
+        upd = torch.cat((_mlp2(sd, f"pos_regressor.{off}.", pos_f), _mlp2(sd, f"rot_regressor.{off}.", rot_f)), -1)
+        base = trajectory if not outs else outs[-1]
+        outs.append(torch.cat((base[..., :3] + upd[..., :3], upd[..., 3:]), -1))   # diffusion_head.py:271-274
+    return outs
 
-    if cfg.use_instruction:                                                  # diffusion_head.py:330-336
-        x = parallel_attention_stack(sd, "traj_lang_attention.0.", h, 1, x, trajectory_mask, context["instr"],
-                                     seq1_sem_pos=wp_pe, apply_ffn=False)
-    common = dict(seq1_mask=trajectory_mask, seq2=context["ctx"], seq1_rope=traj_rope,
-                  seq2_rope=context["ctx_rope"], seq1_sem_pos=wp_pe, ada_signal=t_emb,
-                  self_attention=True, rotary=True, use_adaln=True)
-    x = parallel_attention_stack(sd, "traj_attention.0.", h, cfg.num_query_cross_attn_layers - 2, x, **common)
-    pos_f = parallel_attention_stack(sd, "pos_attention.0.", h, 2, x, **common)
-    rot_f = parallel_attention_stack(sd, "rot_attention.0.", h, 2, x, **common)
-    upd = torch.cat((_mlp2(sd, "pos_regressor.0.", pos_f), _mlp2(sd, "rot_regressor.0.", rot_f)), -1)
-    return torch.cat((trajectory[..., :3] + upd[..., :3], upd[..., 3:]), -1)   # diffusion_head.py:271-274
+
+def denoise_once(sd, cfg: PlannerConfig, context, trajectory, trajectory_mask, timestep):
+    """Last refinement of denoise_all (what the sampling loop keeps, diffusion_model.py:104)."""
+    return denoise_all(sd, cfg, context, trajectory, trajectory_mask, timestep)[-1]
 
 
 # ---------------------------------------------------------------- planner wrapper
@@ -169,7 +216,7 @@ def compute_trajectory(sd, cfg: PlannerConfig, trunk, trajectory_mask, rgb, pcd,
     for t in pos_s.timesteps:
         if not hoist_context:
             ctx = encode_context(sd, cfg, trunk, rgb, pcd_n, instruction, cur, goal)
-        out = denoise_once(sd, cfg, ctx, traj, trajectory_mask, t * torch.ones(b).long())
+        out = denoise_once(sd, cfg, ctx, traj, trajectory_mask, t * torch.ones(b).long()).clone()
         out[cmask] = cond[cmask]
         if t == last:
             traj = out

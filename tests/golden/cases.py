@@ -21,6 +21,11 @@ PLANNER_KW = dict(
 )
 
 
+# multi-scale refinement (feat_scales_to_use=3: coarse map, then the 64*L / 16*L fine points nearest the trajectory),
+# untied weights so that every (round, scale) offset has its own parameters; short schedule for the sampling fixture
+PLANNER_MS_KW = dict(PLANNER_KW, feat_scales_to_use=3, weight_tying=False, diffusion_timesteps=8)
+
+
 def act3d_inputs(batch=2, ncam=1, seed=0):
     rgb, pcd = synth.rgbd("a3d", batch, ncam, 256, seed)
     return dict(

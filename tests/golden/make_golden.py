@@ -131,6 +131,34 @@ def gen_planner(ref):
     save("planner_100step", dict(trajectory=traj, check=synth.checksum(inp["curr_gripper"], inp["goal_gripper"])))
 
 
+def build_planner_ms(ref):
+    torch.manual_seed(0)
+    model = ref.DiffusionPlanner(**cases.PLANNER_MS_KW).eval()
+    cases.install_synth_trunk(model.prediction_head, cases.PLANNER_MS_KW["embedding_dim"])
+    synth.fill_state_dict(model.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    return model
+
+
+@torch.no_grad()
+def gen_planner_multiscale(ref):
+    """feat_scales_to_use=3: one DiffusionHead.forward (all three refinements) and an 8-step sampling loop."""
+    model = build_planner_ms(ref)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.4)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    pcd_n = model.normalize_pos(inp["pcd_obs"].permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
+    t = torch.tensor([5, 2])
+    outs = model.prediction_head(traj, inp["trajectory_mask"], t, visible_rgb=inp["rgb_obs"], visible_pcd=pcd_n,
+                                 curr_gripper=cur, goal_gripper=goal, instruction=inp["instruction"])
+    with synth.patched_randn(synth.NoiseStream("cdms")):
+        sampled = model.compute_trajectory(inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"],
+                                           inp["instruction"], inp["curr_gripper"], inp["goal_gripper"])
+    save("planner_multiscale", dict(head_outs=[o.clone() for o in outs], trajectory=sampled,
+                                    check=synth.checksum(traj, cur, goal, t, inp["curr_gripper"])))
+
+
 def reference_loss_class():
     """LossAndMetrics straight from the reference's main_keypose.py source (the module itself cannot be
     imported here: tap / blosc / datasets are missing).  Only the class statement is executed."""
@@ -205,6 +233,7 @@ def main():
     gen_planner(ref)
     gen_keypose_loss(ref)
     gen_act3d_train_grads(ref)
+    gen_planner_multiscale(ref)
 
 
 if __name__ == "__main__":

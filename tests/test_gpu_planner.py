@@ -124,3 +124,49 @@ def test_parallel_heads_are_bit_identical_to_the_sequential_order():
             assert torch.equal(again, outs[-1])
     assert torch.equal(outs[0], outs[1])
     assert torch.equal(outs[0], outs[2])
+
+
+# ------------------------------------------------------------------------------------------------ multi-scale (a17)
+def build_ms():
+    from model import DiffusionPlanner
+    kw = cases.PLANNER_MS_KW
+    m = DiffusionPlanner(**kw).eval()
+    cases.install_synth_trunk(m.prediction_head, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    return m
+
+
+def test_multiscale_head_matches_golden():
+    """feat_scales_to_use=3: coarse map, then the 64*L and 16*L fine points nearest the running estimate
+    (find_traj_nn -> a3d_traj_topk), untied weights per offset.  All three refinements vs the reference."""
+    g = torch.load(os.path.join(G, "planner_multiscale.pt"), weights_only=False)
+    m = build_ms().cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.4)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    t = torch.tensor([5, 2])
+    assert synth.checksum(traj, cur, goal, t, inp["curr_gripper"]) == g["check"]
+    pcd_n = m.normalize_pos(inp["pcd_obs"].cuda().permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+    with torch.no_grad():
+        outs = m.prediction_head(traj.cuda(), inp["trajectory_mask"].cuda(), t.cuda(), inp["rgb_obs"].cuda(), pcd_n,
+                                 cur.cuda(), goal.cuda(), inp["instruction"].cuda())
+    assert len(outs) == 3
+    for i, (got, want) in enumerate(zip(outs, g["head_outs"])):
+        got = got.cpu()
+        assert torch.isfinite(got).all()
+        assert rel(got, want) <= 1e-3, (i, rel(got, want))
+
+
+def test_multiscale_sampling_matches_golden():
+    g = torch.load(os.path.join(G, "planner_multiscale.pt"), weights_only=False)
+    m = build_ms().cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    m._noise_fn = synth.NoiseStream("cdms")
+    traj = m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                         "curr_gripper", "goal_gripper")]).cpu()
+    want = g["trajectory"]
+    assert (traj[..., :3] - want[..., :3]).abs().max() <= 2e-3
+    qd = torch.minimum((traj[..., 3:] - want[..., 3:]).abs().amax(-1), (traj[..., 3:] + want[..., 3:]).abs().amax(-1))
+    assert qd.max() <= 4e-3

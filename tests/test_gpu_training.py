@@ -408,3 +408,48 @@ def test_act3d_training_gradients_match_reference_golden():
         assert err <= 1e-3 * ref.norm().item() + floor, (name, err, ref.norm().item())
         checked += 1
     assert checked >= 60, checked
+
+
+def test_multiscale_denoiser_training_gradients_match_oracle():
+    """feat_scales_to_use=3 through the differentiable path: every refinement and the parameter gradients of the
+    summed objective (diffusion_model.py:315-324) against the oracle's autograd."""
+    from model import DiffusionPlanner
+    kw = cases.PLANNER_MS_KW
+    m = DiffusionPlanner(**kw).eval()
+    cases.install_synth_trunk(m.prediction_head, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    head = m.prediction_head
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.4)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    t = torch.tensor([5, 2])
+    gws = [synth.normal(f"cd.gw{i}", (b, length, 9), 1.0) for i in range(3)]
+    cfg = planner_ref.PlannerConfig(gripper_loc_bounds=synth.BOUNDS, feat_scales_to_use=3, diffusion_timesteps=8)
+    pcd_n = m.normalize_pos(inp["pcd_obs"].permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3).contiguous()
+    sd = leaf_state_dict(head)
+    ctx = planner_ref.encode_context(sd, cfg, act3d_ref.trunk_from_module(head), inp["rgb_obs"], pcd_n, inp["instruction"],
+                                     cur, goal)
+    want = planner_ref.denoise_all(sd, cfg, ctx, traj, inp["trajectory_mask"], t)
+    sum((w_ * g_).sum() for w_, g_ in zip(want, gws)).backward()
+
+    m = m.cuda()
+    got = m.prediction_head(traj.cuda(), inp["trajectory_mask"].cuda(), t.cuda(), inp["rgb_obs"].cuda(), pcd_n.cuda(),
+                            cur.cuda(), goal.cuda(), inp["instruction"].cuda())
+    assert len(got) == 3
+    for a_, w_ in zip(got, want):
+        assert rel(a_.detach().cpu(), w_.detach()) <= 1e-4
+    sum((a_ * g_.cuda()).sum() for a_, g_ in zip(got, gws)).backward()
+    torch.cuda.synchronize()
+    checked = 0
+    floor = 1e-6 * max(v.grad.norm().item() for v in sd.values() if v.grad is not None)
+    for name, p in m.prediction_head.named_parameters():
+        ref = sd[name].grad
+        if ref is None or ref.abs().max() == 0:
+            continue
+        assert p.grad is not None, f"{name}: no gradient reached this parameter"
+        err = (p.grad.cpu() - ref).norm().item()
+        assert err <= 1e-3 * ref.norm().item() + floor, (name, err, ref.norm().item())
+        checked += 1
+    assert checked >= 300, checked

@@ -258,3 +258,37 @@ def test_act3d_training_gradients_of_the_oracle_match_the_reference():
         assert err <= 1e-4, (name, err)
         checked += 1
     assert checked >= 60, checked
+
+
+# ------------------------------------------------------------------------------------------------ multi-scale planner
+def test_planner_multiscale_head_and_sampling():
+    """feat_scales_to_use=3 (find_traj_nn local refinement, untied weights per offset): all three refinements of one
+    DiffusionHead.forward and an 8-step sampling loop against the reference."""
+    from model import DiffusionPlanner
+    g = load("planner_multiscale")
+    kw = cases.PLANNER_MS_KW
+    m = DiffusionPlanner(**kw).eval()
+    cases.install_synth_trunk(m.prediction_head, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    sd = {k[len("prediction_head."):]: v for k, v in m.state_dict().items() if k.startswith("prediction_head.")}
+    cfg = planner_ref.PlannerConfig(gripper_loc_bounds=synth.BOUNDS, feat_scales_to_use=3, diffusion_timesteps=8)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    b, length = inp["trajectory_mask"].shape
+    traj = synth.normal("cd.traj", (b, length, 9), 0.4)
+    cur = synth.normal("cd.cur9", (b, 9), 0.5)
+    goal = synth.normal("cd.goal9", (b, 9), 0.5)
+    t = torch.tensor([5, 2])
+    assert synth.checksum(traj, cur, goal, t, inp["curr_gripper"]) == g["check"]
+    trunk = act3d_ref.trunk_from_module(m.prediction_head)
+    pcd_n = planner_ref.normalize_pos(cfg, inp["pcd_obs"].permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
+    with torch.no_grad():
+        ctx = planner_ref.encode_context(sd, cfg, trunk, inp["rgb_obs"], pcd_n, inp["instruction"], cur, goal)
+        outs = planner_ref.denoise_all(sd, cfg, ctx, traj, inp["trajectory_mask"], t)
+        assert len(outs) == 3
+        for got, want in zip(outs, g["head_outs"]):
+            close(got, want, 1e-5, 1e-5)
+        sampled = planner_ref.compute_trajectory(sd, cfg, trunk, inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"],
+                                                 inp["instruction"], inp["curr_gripper"], inp["goal_gripper"],
+                                                 noise_fn=synth.NoiseStream("cdms"))
+    close(sampled[..., :3], g["trajectory"][..., :3], 1e-4)
+    close(sampled[..., 3:], g["trajectory"][..., 3:], 1e-4)
