@@ -419,8 +419,9 @@ extern int g_xattn_poly;
 extern int g_xattn_core;
 extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "xattn_core") == 0) {
-        A3D_REQUIRE(value == 0 || (value >= 2 && value <= 4),
-                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 3 (tcgen05, two-pass) or 4 (tcgen05, single pass)");
+        A3D_REQUIRE(value == 0 || (value >= 2 && value <= 5),
+                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 3 (tcgen05, two-pass), 4 (tcgen05, single pass) "
+                    "or 5 (tcgen05, single pass, warp-specialised exponentials)");
         g_xattn_core = value;
         return A3D_OK;
     }

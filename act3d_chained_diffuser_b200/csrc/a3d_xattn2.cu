@@ -353,6 +353,7 @@ using namespace a3d;
 int g_xattn_core = 0;
 int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
+int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" size_t a3d_xattn_layer_words(int embed, int ffn) {
@@ -400,6 +401,7 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 4 : 2);
     if (core == 3) return a3d_launch_xattn3(a, grid, (cudaStream_t)stream);
     if (core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
+    if (core == 5) return a3d_launch_xattn5(a, grid, (cudaStream_t)stream);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \
         static bool once = false;                                                                                      \

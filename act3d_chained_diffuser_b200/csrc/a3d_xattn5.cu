@@ -1,0 +1,640 @@
+// Fused cross-attention stack, tcgen05 / TMEM generation with WARP-SPECIALISED EXPONENTIALS (same contract and
+// packed weights as a3d_xattn2.cu; the single-pass design of a3d_xattn4.cu plus a second group of row warps).
+//
+// At head_dim 15 the binding unit of this kernel is MUFU (one ex2 per 30 useful FLOPs, 16 ex2/clk/SM), not the
+// tensor pipe.  An exp2 polynomial on the FMA pipe can take part of the load, but inside ONE warp ptxas clusters
+// the polynomial and the MUFU stream apart (in-order issue then starves one pipe or the other).  Here the two
+// kinds of exponential live in DIFFERENT warps, so the SM's warp schedulers interleave them cycle by cycle:
+//   warps 0-3  "MUFU warps"  thread i owns query row i (TMEM lane i): projections / LayerNorm / FFN, the explicit
+//              (first-tile / safe-mode) softmax, and in the fast pass keys 16..63 of every tile with ex2.approx;
+//   warps 4-7  "poly warps"  thread i owns the same row i (lane quarter = warp % 4): keys 0..15 of every fast
+//              unit with the degree-3 polynomial (FMNMX / FADD / FFMA / LEA only);
+//   warp 8     one elected lane issues the K/V tile loads and the S = Q K^T products;
+//   warp 9     one elected lane issues the PV products (warps 10-11 only complete the third warpgroup).
+// setmaxnreg moves registers from the poly warps (48) and the issuing warpgroup (40) to the MUFU warps (152) so
+// that 2 CTAs of 384 threads (80 registers per thread at launch) fit an SM.  P of a unit is assembled in tensor memory by both groups without any cross-warp hand-shake: the poly
+// warps read S columns 0..15 and write their 8 packed columns over 0..7, the MUFU warps read S columns 16..63 and
+// write 24 packed columns over 40..63 -- each group only overwrites columns it has itself consumed -- and the PV
+// product takes its A operand per 16-key step from those two places.  Both groups arrive on p_full (256).
+// Everything else (shift folded into the MMA through the pad slot, unchecked fast pass with end-of-pass overflow
+// verdict and safe-mode replay, 3 S buffers with S issued two units ahead, pass counters) is a3d_xattn4.cu's.
+#include "a3d_tcgen05.cuh"
+#include "a3d_xattn_common.cuh"
+
+namespace a3d {
+
+struct Xa5 {
+    static constexpr int E = 60, H = 4, ROWS = 128, THREADS = 384, ISSUE_WARP = 8;
+    // setmaxnreg moves registers inside the CTA's own pool: 3 warpgroups x 128 threads x LAUNCH_REGS at launch must
+    // cover MUFU_REGS + POLY_REGS + ISSUE_REGS per thread triple (checked against cudaFuncGetAttributes at first launch)
+    static constexpr int LAUNCH_REGS = 80, MUFU_REGS = 152, POLY_REGS = 48, ISSUE_REGS = 40;
+    static_assert(MUFU_REGS + POLY_REGS + ISSUE_REGS <= 3 * LAUNCH_REGS, "register budget of the three warpgroups");
+    static constexpr int XP = Xa2::XP;
+    static constexpr int TILE_BYTES = Xa2::TILE_BYTES, STAGES = 3;
+    static constexpr size_t X_BYTES = (size_t)ROWS * XP * 4;          // parked residual stream
+    static constexpr size_t Q_BYTES = (size_t)H * ROWS * 32;          // Q_h tiles [128][16] fp16, SWIZZLE_32B
+    static constexpr size_t RING_BYTES = (size_t)STAGES * TILE_BYTES; // K/V ring; the O tile aliases it in the epilogue
+    static constexpr size_t SMEM = X_BYTES + Q_BYTES + RING_BYTES + 256;
+    static constexpr int TMEM_COLS = 256, O_COL = 0, S_COL = 64, NBUF = 3;   // O + 3 S/P buffers = 256 columns
+};
+
+struct Xa5Bars {
+    uint64_t kv_full[Xa5::STAGES], kv_empty[Xa5::STAGES];
+    uint64_t s_full[Xa5::NBUF], p_full[Xa5::NBUF], pv_free[Xa5::NBUF], pv_done[Xa5::H];
+    uint64_t q_ready, o_full, verdict;
+    uint32_t tmem_base;
+    uint32_t overflow_count;      // bumped by every row thread whose fast pass produced a non-finite denominator
+};
+
+__global__ void __launch_bounds__(Xa5::THREADS, 2) xattn5_kernel(const Xa2Args a) {
+    using C = Xa5;
+    constexpr int E = C::E, H = C::H;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* xpark = reinterpret_cast<float*>(smem);                                // [128][XP] residual stream
+    unsigned char* qs = smem + C::X_BYTES;                                        // [H][128][32 B] fp16, SW32
+    unsigned char* kvs = smem + C::X_BYTES + C::Q_BYTES;                          // STAGES x TILE_BYTES
+    float* opark = reinterpret_cast<float*>(kvs);                                 // [128][XP] attention output (epilogue)
+    Xa5Bars* bars = reinterpret_cast<Xa5Bars*>(kvs + C::RING_BYTES);
+    __shared__ float freq[E / 6];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, row0 = blockIdx.x * C::ROWS;
+    const int g = lane >> 2, q4 = lane & 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(bars->kv_full + s, 1);
+            mbar_init(bars->kv_empty + s, 1);
+        }
+        for (int i = 0; i < C::NBUF; ++i) {
+            mbar_init(bars->s_full + i, 1);
+            mbar_init(bars->p_full + i, 256);
+            mbar_init(bars->pv_free + i, 1);
+        }
+        for (int h = 0; h < C::H; ++h) mbar_init(bars->pv_done + h, 1);
+        mbar_init(&bars->q_ready, 128);
+        mbar_init(&bars->o_full, 1);
+        mbar_init(&bars->verdict, 128);
+        bars->overflow_count = 0;
+        mbar_fence_init();
+    }
+    if (tid < E / 6) freq[tid] = rope_freq<E>(tid);
+    if (warp == C::ISSUE_WARP) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    const int nt = a.ntiles;
+    const unsigned char* kv_sample = a.kv_base + (size_t)b * nt * C::TILE_BYTES;
+
+    if (warp >= C::ISSUE_WARP) {
+        // =========================================================== producer: TMA loads + all tensor-core issue
+        // (warpgroup 2 = the issuing warp + three idle warps that only exist so that setmaxnreg sees a full warpgroup)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" : : "n"(C::ISSUE_REGS));
+        // Two issuing threads: a tcgen05.mma / tcgen05.commit costs its issuing thread ~70-100 cycles at these tiny shapes
+        // (measured: 284 cycles per unit for S + commit, 428 for 4 PV k-steps + commits when one thread did both), so
+        // the S products (+ K/V tile loads) and the PV products are issued by different warps.  Instructions of
+        // different threads are not ordered with each other: S(u) may overwrite buffer u % 3 only after the PV
+        // product of unit u-3 has completed, which the PV thread signals through pv_free[].
+        if (warp == C::ISSUE_WARP && lane == 0) {
+            // ------------------------------------------------------- S thread: K/V tile loads + S_h = Q_h K_h^T
+            uint32_t gt_load = 0;               // tiles requested so far (nt per pass)
+            uint32_t ps = 0;                    // pass counter: one pass over the keys per layer, plus one per (rare) safe-mode replay
+            uint32_t seen_overflows = 0;
+            for (int layer = 0; layer < a.nlayers; ++layer) {
+                const unsigned char* kv_layer = kv_sample + (size_t)layer * a.kv_layer_stride;
+                mbar_wait(&bars->q_ready, layer & 1);       // Q of this layer is in shared memory; O tile no longer read
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(qs);
+                for (int attempt = 0; attempt < 2; ++attempt, ++ps) {
+                    const uint32_t base = ps * nt, lim = base + nt;
+                    auto load_next = [&]() {
+                        if (gt_load >= lim) return;
+                        const uint32_t s = gt_load % C::STAGES, use = gt_load / C::STAGES;
+                        if (use >= 1) mbar_wait(bars->kv_empty + s, (use - 1) & 1);
+                        mbar_expect_tx(bars->kv_full + s, C::TILE_BYTES);
+                        bulk_g2s(kvs + s * C::TILE_BYTES, kv_layer + (size_t)(gt_load - base) * C::TILE_BYTES, C::TILE_BYTES,
+                                 bars->kv_full + s);
+                        ++gt_load;
+                    };
+                    for (int i = 0; i < C::STAGES - 1; ++i) load_next();
+                    const uint32_t ubase = ps * nt * H;
+                    for (int u = 0; u < nt * H; ++u) {
+                        const int t = u / H, h = u % H;
+                        const uint32_t U = ubase + u, i = U % C::NBUF, k = U / C::NBUF;
+                        const uint32_t tau = base + t, s = tau % C::STAGES;
+                        if (h == 0) {
+                            mbar_wait(bars->kv_full + s, (tau / C::STAGES) & 1);
+                            tc_fence_after();
+                        }
+                        if (k >= 1) {                              // PV of the previous user of this buffer (unit U-3) is done
+                            mbar_wait(bars->pv_free + i, (k - 1) & 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t k_addr = smem_u32(kvs + s * C::TILE_BYTES);
+                        umma_ss(tmem + C::S_COL + 64 * i, sw32_desc(q_addr + h * 4096), sw32_desc(k_addr + h * 2048), kIdescS, 0);
+                        tc_commit(bars->s_full + i);
+                        if (h == 2) load_next();                   // refills the stage of tile t-1 (released by the PV thread)
+                    }
+                    if (attempt == 1) continue;
+                    mbar_wait(&bars->verdict, layer & 1);          // replay this layer in safe mode if any row overflowed
+                    const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&bars->overflow_count);
+                    const bool redo = now != seen_overflows;
+                    seen_overflows = now;
+                    if (!redo) {
+                        ++ps;
+                        break;
+                    }
+                }
+            }
+        } else if (warp == C::ISSUE_WARP + 1 && lane == 0) {
+            // ------------------------------------------------------- PV thread: O_h += P_h V_h
+            uint32_t ps = 0, seen_overflows = 0;
+            for (int layer = 0; layer < a.nlayers; ++layer) {
+                for (int attempt = 0; attempt < 2; ++attempt, ++ps) {
+                    const uint32_t base = ps * nt, ubase = ps * nt * H;
+                    for (int v = 0; v < nt * H; ++v) {
+                        const int t = v / H, h = v % H;
+                        const uint32_t V = ubase + v, j = V % C::NBUF, k = V / C::NBUF;
+                        const uint32_t s = (base + t) % C::STAGES;
+                        mbar_wait(bars->p_full + j, k & 1);
+                        tc_fence_after();
+                        const uint32_t v_addr = smem_u32(kvs + s * C::TILE_BYTES) + H * 2048 + h * 2048;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_ts(tmem + C::O_COL + 16 * h, tmem + C::S_COL + 64 * j + (ks ? 32 + 8 * ks : 0), sw32_desc(v_addr + ks * 512),
+                                    kIdescPV, (t > 0 || ks > 0) ? 1u : 0u);
+                        tc_commit(bars->pv_free + j);
+                        tc_commit(bars->pv_done + h);
+                        if (h == H - 1) tc_commit(bars->kv_empty + s);
+                    }
+                    tc_commit(&bars->o_full);
+                    if (attempt == 1) continue;
+                    mbar_wait(&bars->verdict, layer & 1);
+                    const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&bars->overflow_count);
+                    const bool redo = now != seen_overflows;
+                    seen_overflows = now;
+                    if (!redo) {
+                        ++ps;
+                        break;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================================================== poly warps: keys 0..15 of every fast unit
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" : : "n"(C::POLY_REGS));
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+        uint32_t ps = 0, seen_overflows = 0;
+        for (int layer = 0; layer < a.nlayers; ++layer) {
+            for (int attempt = 0; attempt < 2; ++attempt, ++ps) {
+                const int t_fast = attempt == 0 ? 1 : nt;          // first tile and safe mode: the MUFU warps do all 64 keys
+                for (int t = 0; t < nt; ++t) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const uint32_t U = (ps * nt + t) * H + h, i = U % C::NBUF, k = U / C::NBUF;
+                        const uint32_t sb = lane_addr + C::S_COL + 64 * i;
+                        mbar_wait(bars->s_full + i, k & 1);      // also orders this arrival after the previous use of p_full[i]
+                        if (t >= t_fast) {
+                            tc_fence_after();
+                            uint32_t r[16], p[8];
+                            tmem_ld16(sb, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                p[c] = pack_h2(exp2_poly(__uint_as_float(r[2 * c])), exp2_poly(__uint_as_float(r[2 * c + 1])));
+                            tmem_st8(sb, p);
+                            tmem_wait_st();
+                            tc_fence_before();
+                        }
+                        mbar_arrive(bars->p_full + i);
+                    }
+                }
+                if (attempt == 1) continue;
+                mbar_wait(&bars->verdict, layer & 1);
+                const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&bars->overflow_count);
+                const bool redo = now != seen_overflows;
+                seen_overflows = now;
+                if (!redo) {
+                    ++ps;
+                    break;
+                }
+            }
+        }
+    } else {
+        // =========================================================== MUFU row warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" : : "n"(C::MUFU_REGS));
+        const int lrow = warp * 32 + lane;                      // this thread's row == TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        // ---- residual stream -> xpark (row per thread)
+        {
+            const int row = row0 + lrow;
+            const float* xp = a.x0 + (long)b * a.x0_sb + (long)row * a.x0_sn;
+            for (int c = 0; c < 64; c += 2) {
+                float2 v = make_float2(0.f, 0.f);
+                if (row < a.nq && c < E) v = __ldg(reinterpret_cast<const float2*>(xp + c));
+                *reinterpret_cast<float2*>(xpark + lrow * C::XP + c) = v;
+            }
+        }
+        __syncwarp();
+
+        uint32_t ps = 0;                    // pass counter (see the issuing warp)
+        uint32_t seen_overflows = 0;
+        for (int layer = 0; layer < a.nlayers; ++layer) {
+            const uint4* w = a.w + (size_t)layer * Xa2::LAYER_W;
+            const float* vv = a.v + (size_t)layer * Xa2::LAYER_V;
+            // ---------------------------------------------------------------- Q = rotary(x Wq^T + bq) -> smem (SW32 tiles per head)
+            for (int mt = 0; mt < 2; ++mt) {
+                const int r0 = warp * 32 + 16 * mt + g, r1 = r0 + 8;
+                float xr[8][4], qa[8][4];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float2 v0 = *reinterpret_cast<const float2*>(xpark + r0 * C::XP + 8 * n + 2 * q4);
+                    const float2 v1 = *reinterpret_cast<const float2*>(xpark + r1 * C::XP + 8 * n + 2 * q4);
+                    xr[n][0] = v0.x;
+                    xr[n][1] = v0.y;
+                    xr[n][2] = v1.x;
+                    xr[n][3] = v1.y;
+                }
+                gemm_reg(xr, w + Xa2::W_Q, lane, qa);
+                float qxyz[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+                if (a.qpos) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int row = row0 + (r ? r1 : r0);
+                        if (row < a.nq)
+                            for (int ax = 0; ax < 3; ++ax) qxyz[r][ax] = __ldg(a.qpos + ((long)b * a.nq + row) * 3 + ax);
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const int c = 8 * n + 2 * q4;
+                    const float b0 = __ldg(vv + Xa2::B_Q + c), b1 = __ldg(vv + Xa2::B_Q + c + 1);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        float v0 = qa[n][2 * r] + b0, v1 = qa[n][2 * r + 1] + b1;
+                        if (a.qpos && c < E) {
+                            const int pi = c >> 1, axis = pi / (E / 6), j = pi - axis * (E / 6);
+                            const float ang = qxyz[r][axis] * freq[j];
+                            float sv, cv;
+                            if (fabsf(ang) < 3.0f) {
+                                __sincosf(ang, &sv, &cv);
+                            } else {
+                                sincosf(ang, &sv, &cv);
+                            }
+                            const float ev = v0, od = v1;
+                            v0 = ev * cv - od * sv;
+                            v1 = od * cv + ev * sv;
+                        }
+                        const int row = r ? r1 : r0;
+                        const int swz = (row >> 2) & 1;
+                        auto put = [&](int hh, int d, float val) {
+                            *reinterpret_cast<__half*>(qs + hh * 4096 + row * 32 + (((d >> 3) ^ swz) << 4) + (d & 7) * 2) =
+                                __float2half_rn(val);
+                        };
+                        if (c < E) {
+                            put(c / 15, c % 15, v0);
+                            put((c + 1) / 15, (c + 1) % 15, v1);
+                        } else {   // dims 60..63 own the pad slot (d = 15) of heads 0..3
+                            put(c - E, 15, 0.f);
+                            put(c + 1 - E, 15, 0.f);
+                        }
+                    }
+                }
+            }
+            fence_async_smem();                 // generic-proxy writes of Q -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            mbar_arrive(&bars->q_ready);
+
+            // ---------------------------------------------------------------- softmax, single pass, shift folded into the MMA
+            // The pad slot of the head dimension carries the shift: Q_h[row][15] = -shift and K[key][15] = 1, so S
+            // leaves the tensor core as s - shift and a unit is ld -> exp2 -> pack -> st with no other arithmetic.
+            // FAST pass: shift = maximum of the first tile + kMargin, never refreshed, nothing checked per unit:
+            // P = 2^(s - shift) may exceed 1 (fp16 holds up to 2^16, the sums are fp32), so only a score that overshoots
+            // the first tile's maximum by more than 2^(16 + kMargin) breaks it -- that shows up as a non-finite
+            // denominator at the end of the pass, and then the whole layer is replayed in SAFE mode (exact running
+            // maximum per unit, O rescaled on every refresh).  The shift is rounded to fp16 and the same rounded value
+            // is used for every key of the row, so softmax's shift invariance keeps the result exact.
+            constexpr float kMargin = 6.0f;
+            float sh[H];
+            const int q_swz = (lrow >> 2) & 1;
+            unsigned char* q_pad = qs + lrow * 32 + ((1 ^ q_swz) << 4) + 14;      // slot 15 of this row in head 0's tile
+
+            // explicit path of one unit: row maximum, new shift, rescale of O_h (t > 0), P with masking.
+            // r0 / r1 = the 64 scores of this row (unshifted on the first tile, shifted by sh[h] afterwards).
+            auto slow_unit = [&](int t, int h, int valid, const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t (&p)[32]) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (c < valid) mx = fmaxf(mx, __uint_as_float(r0[c]));
+                    if (c + 32 < valid) mx = fmaxf(mx, __uint_as_float(r1[c]));
+                }
+                float shift_new, delta;
+                if (t == 0) {
+                    shift_new = -__half2float(__float2half_rn(-(mx + kMargin)));
+                    delta = shift_new;                                 // S of the first tile is unshifted
+                } else {
+                    shift_new = (mx >= 1.0f) ? -__half2float(__float2half_rn(-(sh[h] + mx + kMargin))) : sh[h];
+                    delta = shift_new - sh[h];                         // exact: both are fp16 values
+                    if (__any_sync(0xffffffffu, delta != 0.f)) {
+                        // O_h holds sums relative to the old shift: rescale this row once the PV product of the
+                        // previous tile of this head has landed (completion number ps*nt + t of pv_done[h])
+                        mbar_wait(bars->pv_done + h, (ps * nt + t - 1) & 1);
+                        tc_fence_after();
+                        uint32_t o[16];
+                        tmem_ld16(lane_addr + C::O_COL + 16 * h, o);
+                        tmem_wait_ld();
+                        const float sc = exp2_fast(-delta);           // 1 for rows that keep their shift
+#pragma unroll
+                        for (int d = 0; d < 16; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * sc);
+                        tmem_st16(lane_addr + C::O_COL + 16 * h, o);
+                    }
+                }
+                sh[h] = shift_new;
+                *reinterpret_cast<__half*>(q_pad + h * 4096) = __float2half_rn(-shift_new);
+                fence_async_smem();                                    // visible to the S products of later tiles
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float e0 = (2 * c < valid) ? exp2_fast(__uint_as_float(r0[2 * c]) - delta) : 0.f;
+                    const float e1 = (2 * c + 1 < valid) ? exp2_fast(__uint_as_float(r0[2 * c + 1]) - delta) : 0.f;
+                    const float e2 = (2 * c + 32 < valid) ? exp2_fast(__uint_as_float(r1[2 * c]) - delta) : 0.f;
+                    const float e3 = (2 * c + 33 < valid) ? exp2_fast(__uint_as_float(r1[2 * c + 1]) - delta) : 0.f;
+                    p[c] = pack_h2(e0, e1);
+                    p[16 + c] = pack_h2(e2, e3);
+                }
+            };
+            // P (32 packed columns in key order) -> keys 0..15 over columns 0..7, keys 16..63 over columns 40..63
+            auto store_p_split = [&](uint32_t sb, const uint32_t (&p)[32]) {
+                tmem_st8(sb, *reinterpret_cast<const uint32_t(*)[8]>(&p[0]));
+                tmem_st16(sb + 40, *reinterpret_cast<const uint32_t(*)[16]>(&p[8]));
+                tmem_st8(sb + 56, *reinterpret_cast<const uint32_t(*)[8]>(&p[24]));
+            };
+            // tiles [t0, t1) on the explicit path
+            auto explicit_tiles = [&](int t0, int t1) {
+                for (int t = t0; t < t1; ++t) {
+                    const int valid = min(kTileKeys, a.nk - t * kTileKeys);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const uint32_t U = (ps * nt + t) * H + h, i = U % C::NBUF, k = U / C::NBUF;
+                        const uint32_t sb = lane_addr + C::S_COL + 64 * i;
+                        mbar_wait(bars->s_full + i, k & 1);
+                        tc_fence_after();
+                        uint32_t r0[32], r1[32], p[32];
+                        tmem_ld32(sb, r0);
+                        tmem_ld32(sb + 32, r1);
+                        tmem_wait_ld();
+                        slow_unit(t, h, valid, r0, r1, p);
+                        store_p_split(sb, p);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(bars->p_full + i);
+                    }
+                }
+            };
+
+            uint32_t o0[32], o1[32];           // O of this row (4 heads x 16 columns) after the pass
+            for (int attempt = 0; attempt < 2; ++attempt, ++ps) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) sh[h] = 0.f;
+                if (attempt == 1) {
+                    explicit_tiles(0, nt);             // safe mode: every unit tracks the exact running maximum
+                } else {
+                    explicit_tiles(0, 1);              // the first tile fixes the shift of every row
+                    // ---- remaining tiles: software-pipelined halves.  `cur` = columns 0..31 of the current unit (already
+                    //      in registers); columns 32..63 are fetched while the first half is exponentiated, the first half
+                    //      of the NEXT unit while the second half is, and the tcgen05.st of P(u) stays in flight until the
+                    //      first half of unit u+1 is done (`pend` = buffer whose hand-over to the issuing warp is still owed).
+                    if (nt > 1) {
+                        uint32_t cur[32], nxt[16], p[24];
+                        {
+                            const uint32_t U = (ps * nt + 1) * H, i = U % C::NBUF, k = U / C::NBUF;
+                            mbar_wait(bars->s_full + i, k & 1);
+                            tc_fence_after();
+                            tmem_ld32(lane_addr + C::S_COL + 64 * i + 16, cur);
+                            tmem_wait_ld();
+                        }
+                        int pend = -1;
+                        for (int t = 1; t < nt; ++t) {
+#pragma unroll
+                            for (int h = 0; h < H; ++h) {
+                                const uint32_t U = (ps * nt + t) * H + h, i = U % C::NBUF;
+                                const uint32_t sb = lane_addr + C::S_COL + 64 * i;
+                                tmem_ld16(sb + 48, nxt);
+#pragma unroll
+                                for (int c = 0; c < 16; ++c)
+                                    p[c] = pack_h2(exp2_fast(__uint_as_float(cur[2 * c])), exp2_fast(__uint_as_float(cur[2 * c + 1])));
+                                if (pend >= 0) {                   // P of the previous unit has landed by now
+                                    tmem_wait_st();
+                                    tc_fence_before();
+                                    mbar_arrive(bars->p_full + pend);
+                                    pend = -1;
+                                }
+                                tmem_wait_ld();
+                                const bool has_next = !(t == nt - 1 && h == H - 1);
+                                if (has_next) {                    // S of the next unit was issued two units ago: normally ready
+                                    const uint32_t Un = U + 1, in = Un % C::NBUF, kn = Un / C::NBUF;
+                                    mbar_wait(bars->s_full + in, kn & 1);
+                                    tc_fence_after();
+                                    tmem_ld32(lane_addr + C::S_COL + 64 * in + 16, cur);
+                                }
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    p[16 + c] = pack_h2(exp2_fast(__uint_as_float(nxt[2 * c])), exp2_fast(__uint_as_float(nxt[2 * c + 1])));
+                                tmem_st16(sb + 40, *reinterpret_cast<const uint32_t(*)[16]>(&p[0]));
+                                tmem_st8(sb + 56, *reinterpret_cast<const uint32_t(*)[8]>(&p[16]));
+                                pend = (int)i;
+                                if (has_next) tmem_wait_ld();
+                            }
+                        }
+                        if (pend >= 0) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                            mbar_arrive(bars->p_full + pend);
+                        }
+                    }
+                }
+                // the pad slots go back to 0 (an unshifted first tile) for a possible replay; harmless otherwise
+#pragma unroll
+                for (int h = 0; h < H; ++h) *reinterpret_cast<__half*>(q_pad + h * 4096) = __float2half_rn(0.f);
+                fence_async_smem();
+                // ---------------------------------------------------------------- O of this pass
+                mbar_wait(&bars->o_full, ps & 1);
+                tc_fence_after();
+                tmem_ld32(lane_addr + C::O_COL, o0);
+                tmem_ld32(lane_addr + C::O_COL + 32, o1);
+                tmem_wait_ld();
+                tc_fence_before();
+                if (attempt == 1) continue;
+                // verdict on the fast pass: a non-finite denominator anywhere in the CTA -> replay the layer in safe mode
+                const float l0 = __uint_as_float(o0[15]), l1 = __uint_as_float(o0[31]), l2 = __uint_as_float(o1[15]),
+                            l3 = __uint_as_float(o1[31]);
+                const bool bad = !(isfinite(l0) && isfinite(l1) && isfinite(l2) && isfinite(l3));
+                if (bad) atomicAdd(&bars->overflow_count, 1u);
+                __threadfence_block();
+                mbar_arrive(&bars->verdict);
+                mbar_wait(&bars->verdict, layer & 1);
+                const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&bars->overflow_count);
+                const bool redo = now != seen_overflows;
+                seen_overflows = now;
+                if (!redo) {
+                    ++ps;
+                    break;
+                }
+            }
+            // ---------------------------------------------------------------- normalise -> opark (aliases the idle K/V ring)
+            {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const uint32_t* src = (h < 2) ? (o0 + 16 * h) : (o1 + 16 * (h - 2));
+                    const float inv = 1.0f / __uint_as_float(src[15]);
+#pragma unroll
+                    for (int d = 0; d < 16; d += 2)
+                        *reinterpret_cast<float2*>(opark + lrow * C::XP + 16 * h + d) =
+                            make_float2(__uint_as_float(src[d]) * inv, __uint_as_float(src[d + 1]) * inv);
+                }
+            }
+            __syncwarp();
+            // ---------------------------------------------------------------- out-proj + LN, FFN + LN (two 16-row tiles per warp)
+            const bool last = (layer == a.nlayers - 1);
+            for (int mt = 0; mt < 2; ++mt) {
+                const int r0 = warp * 32 + 16 * mt + g, r1 = r0 + 8;
+                float xr[8][4];
+                {
+                    float of[8][4], y[8][4];
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const float2 v0 = *reinterpret_cast<const float2*>(opark + r0 * C::XP + 8 * n + 2 * q4);
+                        const float2 v1 = *reinterpret_cast<const float2*>(opark + r1 * C::XP + 8 * n + 2 * q4);
+                        of[n][0] = v0.x;
+                        of[n][1] = v0.y;
+                        of[n][2] = v1.x;
+                        of[n][3] = v1.y;
+                    }
+                    gemm_reg(of, w + Xa2::W_O, lane, y);
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const int c = 8 * n + 2 * q4;
+                        const float b0 = __ldg(vv + Xa2::B_O + c), b1 = __ldg(vv + Xa2::B_O + c + 1);
+                        const float2 x0v = *reinterpret_cast<const float2*>(xpark + r0 * C::XP + c);
+                        const float2 x1v = *reinterpret_cast<const float2*>(xpark + r1 * C::XP + c);
+                        xr[n][0] = y[n][0] + b0 + x0v.x;
+                        xr[n][1] = y[n][1] + b1 + x0v.y;
+                        xr[n][2] = y[n][2] + b0 + x1v.x;
+                        xr[n][3] = y[n][3] + b1 + x1v.y;
+                    }
+                    layernorm_frag(xr, q4, vv + Xa2::G_1, vv + Xa2::BE_1);
+                }
+                {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        *reinterpret_cast<float2*>(xpark + r0 * C::XP + 8 * n + 2 * q4) = make_float2(xr[n][0], xr[n][1]);
+                        *reinterpret_cast<float2*>(xpark + r1 * C::XP + 8 * n + 2 * q4) = make_float2(xr[n][2], xr[n][3]);
+                    }
+                    float hid[8][4];
+                    gemm_reg(xr, w + Xa2::W_1, lane, hid);
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const int c = 8 * n + 2 * q4;
+                        const float b0 = __ldg(vv + Xa2::B_1 + c), b1 = __ldg(vv + Xa2::B_1 + c + 1);
+                        hid[n][0] = fmaxf(hid[n][0] + b0, 0.f);
+                        hid[n][1] = fmaxf(hid[n][1] + b1, 0.f);
+                        hid[n][2] = fmaxf(hid[n][2] + b0, 0.f);
+                        hid[n][3] = fmaxf(hid[n][3] + b1, 0.f);
+                    }
+                    gemm_reg(hid, w + Xa2::W_2, lane, xr);
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const int c = 8 * n + 2 * q4;
+                        const float b0 = __ldg(vv + Xa2::B_2 + c), b1 = __ldg(vv + Xa2::B_2 + c + 1);
+                        const float2 x0v = *reinterpret_cast<const float2*>(xpark + r0 * C::XP + c);
+                        const float2 x1v = *reinterpret_cast<const float2*>(xpark + r1 * C::XP + c);
+                        xr[n][0] += b0 + x0v.x;
+                        xr[n][1] += b1 + x0v.y;
+                        xr[n][2] += b0 + x1v.x;
+                        xr[n][3] += b1 + x1v.y;
+                    }
+                    layernorm_frag(xr, q4, vv + Xa2::G_2, vv + Xa2::BE_2);
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {   // x of the next layer
+                        *reinterpret_cast<float2*>(xpark + r0 * C::XP + 8 * n + 2 * q4) = make_float2(xr[n][0], xr[n][1]);
+                        *reinterpret_cast<float2*>(xpark + r1 * C::XP + 8 * n + 2 * q4) = make_float2(xr[n][2], xr[n][3]);
+                    }
+                }
+                // ---- outputs of this layer
+                if (a.feat_out && (a.feat_all || last)) {
+                    float* fo = a.feat_out + ((size_t)(a.feat_all ? layer : 0) * a.batch + b) * (size_t)a.feat_rows * E;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int row = row0 + (r ? r1 : r0);
+                        if (row < a.nq) {
+#pragma unroll
+                            for (int n = 0; n < 8; ++n) {
+                                const int c = 8 * n + 2 * q4;
+                                if (c < E) *reinterpret_cast<float2*>(fo + (size_t)row * E + c) = make_float2(xr[n][2 * r], xr[n][2 * r + 1]);
+                            }
+                        }
+                    }
+                }
+                if (last && a.logits) {
+                    for (int j = 0; j < a.nqv; ++j) {
+                        const float* qv = a.qvec + ((size_t)j * a.batch + b) * E;
+                        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            const int c = 8 * n + 2 * q4;
+                            if (c < E) {
+                                const float2 qc = __ldg(reinterpret_cast<const float2*>(qv + c));
+                                p0 = fmaf(xr[n][0], qc.x, p0);
+                                p0 = fmaf(xr[n][1], qc.y, p0);
+                                p1 = fmaf(xr[n][2], qc.x, p1);
+                                p1 = fmaf(xr[n][3], qc.y, p1);
+                            }
+                        }
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+                        p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+                        p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+                        if (q4 == 0) {
+                            float* lo = a.logits + ((size_t)j * a.batch + b) * a.nq;
+                            if (row0 + r0 < a.nq) lo[row0 + r0] = p0;
+                            if (row0 + r1 < a.nq) lo[row0 + r1] = p1;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == C::ISSUE_WARP) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+}  // namespace a3d
+
+using namespace a3d;
+
+// launched by a3d_xattn_stack (a3d_xattn2.cu) when the "xattn_core" option selects this kernel
+int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
+    static bool once = false;
+    if (!once) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, xattn5_kernel) != cudaSuccess || fa.numRegs < Xa5::LAUNCH_REGS) {
+            // setmaxnreg.inc would block forever: the CTA's register pool is too small for the warpgroup budgets
+            set_error("a3d_xattn_stack(tcgen05 v5): kernel was compiled with %d registers per thread, needs %d", fa.numRegs,
+                      Xa5::LAUNCH_REGS);
+            return A3D_ENOSUPPORT;
+        }
+        cudaError_t e = cudaFuncSetAttribute(xattn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Xa5::SMEM);
+        if (e != cudaSuccess) {
+            set_error("a3d_xattn_stack(tcgen05 v5): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return A3D_ECUDA;
+        }
+        once = true;
+    }
+    xattn5_kernel<<<grid, Xa5::THREADS, Xa5::SMEM, stream>>>(a);
+    return check_launch("a3d_xattn_stack(tcgen05 v5)");
+}
