@@ -17,7 +17,10 @@ struct Norm3 {
     float mean[3], stdv[3];
 };
 
-// one thread per pixel: three coalesced plane reads, one 12-byte row write
+// one thread per pixel: three coalesced plane reads, one 12-byte row write -- or, with PAD4, one 16-byte write of
+// (r, g, b, 0): a 4-channel NHWC input lets cuDNN run the 7x7 stem on its vectorised tensor-core kernels instead of
+// the indexed 3-channel fallback (the zero channel meets zero weights: same sums)
+template <bool PAD4>
 __global__ void __launch_bounds__(256) trunk_normalize_kernel(const float* __restrict__ in, Norm3 nm, int hw, long total,
                                                               float* __restrict__ out) {
     const long stride = (long)gridDim.x * blockDim.x;
@@ -25,8 +28,15 @@ __global__ void __launch_bounds__(256) trunk_normalize_kernel(const float* __res
         const long n = i / hw;
         const int p = (int)(i - n * hw);
         const float* src = in + n * 3 * hw + p;
+        float v[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) out[i * 3 + c] = __fdiv_rn(__fsub_rn(__ldg(src + (long)c * hw), nm.mean[c]), nm.stdv[c]);
+        for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(__ldg(src + (long)c * hw), nm.mean[c]), nm.stdv[c]);
+        if (PAD4) {
+            reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], 0.f);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out[i * 3 + c] = v[c];
+        }
     }
 }
 
@@ -99,15 +109,20 @@ static inline int grid_for(long total) {
 using namespace a3d;
 
 extern "C" int a3d_trunk_normalize(const float* rgb, const float* mean_host, const float* std_host, int images, int hw,
-                                   float* out, void* stream) {
+                                   float* out, int out_channels, void* stream) {
     A3D_REQUIRE(rgb && mean_host && std_host && out && images > 0 && hw > 0, "a3d_trunk_normalize: bad arguments");
+    A3D_REQUIRE(out_channels == 3 || out_channels == 4, "a3d_trunk_normalize: out_channels must be 3 or 4 (got %d)", out_channels);
+    A3D_REQUIRE(out_channels == 3 || ((uintptr_t)out & 15) == 0, "a3d_trunk_normalize: 16-byte aligned output required");
     Norm3 nm;
     for (int c = 0; c < 3; ++c) {
         nm.mean[c] = mean_host[c];
         nm.stdv[c] = std_host[c];
     }
     const long total = (long)images * hw;
-    trunk_normalize_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(rgb, nm, hw, total, out);
+    if (out_channels == 4)
+        trunk_normalize_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(rgb, nm, hw, total, out);
+    else
+        trunk_normalize_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(rgb, nm, hw, total, out);
     return check_launch("a3d_trunk_normalize");
 }
 

@@ -24,7 +24,7 @@ EXPORTS = {
     "a3d_gather_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "a3d_trunk_normalize": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), c_int, c_int,
-                                    c_void_p, c_void_p]),
+                                    c_void_p, c_int, c_void_p]),
     "a3d_trunk_maxpool": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a3d_trunk_fpn_topdown": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p]),
@@ -186,14 +186,16 @@ def _nhwc_like(images, channels, h, w, device):
     return torch.empty(images, h, w, channels, device=device, dtype=torch.float32).permute(0, 3, 1, 2)
 
 
-def trunk_normalize(rgb, mean, std):
-    """(N,3,H,W) NCHW fp32 -> (x - mean) / std as a channels-last tensor (transforms.Normalize + layout change)."""
+def trunk_normalize(rgb, mean, std, out_channels=3):
+    """(N,3,H,W) NCHW fp32 -> (x - mean) / std as a channels-last tensor (transforms.Normalize + layout change);
+    out_channels=4 appends a zero channel (16-byte pixels for the stem convolution)."""
     assert rgb.is_cuda and rgb.dim() == 4 and rgb.shape[1] == 3
     rgb = _f32(rgb)
     n, _, h, w = rgb.shape
-    out = _nhwc_like(n, 3, h, w, rgb.device)
+    out = _nhwc_like(n, out_channels, h, w, rgb.device)
     m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
-    _check(load().a3d_trunk_normalize(_ptr(rgb), m3, s3, n, h * w, out.data_ptr(), _stream()), "a3d_trunk_normalize")
+    _check(load().a3d_trunk_normalize(_ptr(rgb), m3, s3, n, h * w, out.data_ptr(), int(out_channels), _stream()),
+           "a3d_trunk_normalize")
     return out
 
 

@@ -21,8 +21,11 @@ def mha(attn, heads, query, key, value, q_pos=None, k_pos=None, key_padding_mask
     e = query.shape[-1]
     w, b = attn.in_proj_weight, attn.in_proj_bias
     q = F.linear(query, w[:e], b[:e]) * (float(e // heads) ** -0.5)
-    k = F.linear(key, w[e:2 * e], b[e:2 * e])
-    v = F.linear(value, w[2 * e:], b[2 * e:])
+    if key is value:        # one (2E x E) projection like the reference's kv_same branch (:268-275): half the GEMM launches
+        k, v = F.linear(key, w[e:], b[e:]).chunk(2, dim=-1)
+    else:
+        k = F.linear(key, w[e:2 * e], b[e:2 * e])
+        v = F.linear(value, w[2 * e:], b[2 * e:])
     if q_pos is not None:
         q = rope_apply(q, q_pos)
         k = rope_apply(k, k_pos)

@@ -82,6 +82,7 @@ class EvalTrunk:
         self._fused = None
         self._plan = None
         self._fused_ok = True
+        self.pad_stem = True        # 4-channel (r, g, b, 0) stem input + zero-padded 7x7 weight: vectorised cuDNN kernel
 
     @staticmethod
     def _signature(backbone):
@@ -114,7 +115,9 @@ class EvalTrunk:
 
     def _resnet_plan(self, folded):
         """Flatten a folded torchvision ResNet into (stem, [blocks]) of cuDNN fused-call arguments."""
-        plan = dict(stem=self._conv_args(folded.conv1), pool=folded.maxpool, stages=[])
+        stem = self._conv_args(folded.conv1)
+        w4 = torch.nn.functional.pad(folded.conv1.weight.detach(), (0, 0, 0, 0, 0, 1)).contiguous(memory_format=torch.channels_last)
+        plan = dict(stem=stem, stem4=(w4,) + stem[1:], pool=folded.maxpool, stages=[])
         for stage in (folded.layer1, folded.layer2, folded.layer3, folded.layer4):
             blocks = []
             for blk in stage:
@@ -129,7 +132,7 @@ class EvalTrunk:
     @staticmethod
     def _run_resnet(plan, x):
         cr, car = torch.cudnn_convolution_relu, torch.cudnn_convolution_add_relu
-        stem = cr(x, *plan["stem"])
+        stem = cr(x, *(plan["stem4"] if x.shape[1] == 4 else plan["stem"]))
         feats = {"res1": stem}
         pool = plan["pool"]
         if (_pair(pool.kernel_size), _pair(pool.stride), _pair(pool.padding), _pair(pool.dilation), pool.ceil_mode) == \
@@ -190,7 +193,8 @@ class EvalTrunk:
             self._fused, self._sig = self._fold_modules(backbone), sig
             self._plan = self._resnet_plan(self._fused) if isinstance(backbone, ResNet) else None
         if rgb.is_cuda and isinstance(normalize, transforms.Normalize) and rgb.shape[1] == 3 and len(normalize.mean) == 3:
-            x = lib.trunk_normalize(rgb.float().contiguous(), normalize.mean, normalize.std)
+            pad = self.pad_stem and self._plan is not None and self._fused_ok
+            x = lib.trunk_normalize(rgb.float().contiguous(), normalize.mean, normalize.std, 4 if pad else 3)
         else:
             x = normalize(rgb).contiguous(memory_format=torch.channels_last)
         if self._plan is not None and self._fused_ok and x.is_cuda:
@@ -200,5 +204,7 @@ class EvalTrunk:
                 if "libact3d_b200" in str(exc) or "a3d_" in str(exc):
                     raise
                 self._fused_ok = False
+        if x.shape[1] == 4:
+            x = x[:, :3].contiguous(memory_format=torch.channels_last)
         out = fpn(self._fused(x))
         return (out, {}) if defer_bias else out

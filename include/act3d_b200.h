@@ -91,7 +91,9 @@ int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, i
  *
  * a3d_trunk_normalize: out[n][p][c] = (rgb[n][c][p] - mean[c]) / std[c] for the 3 colour planes
  *   (NCHW in, NHWC out).  Replaces transforms.Normalize (act3d.py:62, diffusion_head.py:40) and the
- *   channels-last conversion.  mean / std are HOST arrays of 3 floats.
+ *   channels-last conversion.  mean / std are HOST arrays of 3 floats.  out_channels = 3, or 4 to append a zero
+ *   channel (rows of 16 bytes: the 7x7 stem convolution then runs on cuDNN's vectorised NHWC kernels with a
+ *   weight padded by a zero input channel).
  * a3d_trunk_maxpool: 3x3, stride 2, padding 1 (the ResNet stem pool, utils/resnet.py:44);
  *   out [images][(h-1)/2+1][(w-1)/2+1][channels]; channels % 4 == 0.
  * a3d_trunk_fpn_topdown: out = (lat + bias) + nearest_upsample(top) -- the top-down merge of
@@ -99,7 +101,7 @@ int a3d_gather_tokens(const float* feat, const float* pcd, const int32_t* idx, i
  *   (bias may be NULL); lat/out [images][h][w][channels] (out may alias lat), top
  *   [images][top_h][top_w][channels]; channels % 4 == 0. */
 int a3d_trunk_normalize(const float* rgb, const float* mean_host, const float* std_host, int images, int hw,
-                        float* out, void* stream);
+                        float* out, int out_channels, void* stream);
 int a3d_trunk_maxpool(const float* in, int images, int h, int w, int channels, float* out, void* stream);
 int a3d_trunk_fpn_topdown(const float* lat, const float* bias, const float* top, int images, int h, int w,
                           int top_h, int top_w, int channels, float* out, void* stream);

@@ -351,6 +351,9 @@ def test_trunk_normalize_bit_exact(lib):
     assert got.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(got.cpu(), norm(x))
     assert torch.equal(got.cpu(), norm(dev(x)).cpu())
+    padded = lib.trunk_normalize(dev(x), norm.mean, norm.std, out_channels=4)      # (r, g, b, 0) pixels for the stem
+    assert padded.shape == (5, 4, 37, 41) and padded.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(padded[:, :3].cpu(), norm(x)) and (padded[:, 3] == 0).all()
 
 
 @pytest.mark.parametrize("shape", [(3, 64, 32, 32), (2, 8, 17, 23), (1, 4, 1, 5)])
