@@ -94,3 +94,31 @@ def gather_tokens(feat, pcd, idx, batch, ncam):
     tok (B, K, E) differentiable w.r.t. feat, pos (B, K, 3)   (act3d.py:236-254)."""
     k = idx.shape[1] if idx is not None else ncam * feat.shape[2] * feat.shape[3]
     return _GatherTokens.apply(feat, pcd, idx, batch, ncam, k)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b with the weight / bias gradient from a3d_linear_wgrad (row-split reduction at HBM speed)
+    instead of autograd's single-CTA SIMT GEMM + separate bias reduction; dx stays a library GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight = ctx.saved_tensors
+        g2 = grad.reshape(-1, grad.shape[-1]).contiguous()
+        dx = (g2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = lib.linear_wgrad(g2, x.reshape(-1, x.shape[-1]).contiguous(), want_bias=ctx.has_bias)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """torch.nn.functional.linear for the training path; rows = every leading dimension of x."""
+    if x.numel() // x.shape[-1] < 2048:          # few rows: autograd's own GEMM is as good
+        return torch.nn.functional.linear(x, weight, bias)
+    return _Linear.apply(x, weight, bias)

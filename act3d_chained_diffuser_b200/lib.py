@@ -47,6 +47,7 @@ EXPORTS = {
     "a3d_rope_apply": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
     "a3d_gather_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                       c_void_p]),
+    "a3d_linear_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_soft_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
     "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -329,6 +330,17 @@ def gather_tokens_bwd(dtok, idx, batch, ncam, k, feat_shape, channels_last):
     _check(load().a3d_gather_tokens_bwd(_ptr(_f32(dtok)), _ptr(idx), batch, ncam, e, h * w, k, dtok.shape[1],
                                         int(channels_last), dfeat.data_ptr(), _stream()), "a3d_gather_tokens_bwd")
     return dfeat
+
+
+def linear_wgrad(dy, x, want_bias=True):
+    """dy (rows, O), x (rows, I) -> dW (O, I), db (O,) or None."""
+    rows, o = dy.shape
+    i = x.shape[1]
+    dw = torch.zeros(o, i, device=dy.device, dtype=torch.float32)
+    db = torch.zeros(o, device=dy.device, dtype=torch.float32) if want_bias else None
+    _check(load().a3d_linear_wgrad(_ptr(_f32(dy)), _ptr(_f32(x)), rows, o, i, _ptr(dw), _ptr(db), _stream()),
+           "a3d_linear_wgrad")
+    return dw, db
 
 
 def soft_ce(logits, ghost, gt, spread, label_smoothing=0.0, want_grad=True):

@@ -11,7 +11,7 @@ MultiheadCustomAttention (model/utils/multihead_custom_attention.py:157-462).
 """
 import torch.nn.functional as F
 
-from .autograd_ops import attention_core, rope_apply
+from .autograd_ops import attention_core, linear, rope_apply
 
 
 def mha(attn, heads, query, key, value, q_pos=None, k_pos=None, key_padding_mask=None, dropout_p=0.0):
@@ -20,17 +20,17 @@ def mha(attn, heads, query, key, value, q_pos=None, k_pos=None, key_padding_mask
     (multihead_custom_attention.py:247-303); q scaled by head_dim^-1/2 before the rotation (:325, :348-353)."""
     e = query.shape[-1]
     w, b = attn.in_proj_weight, attn.in_proj_bias
-    q = F.linear(query, w[:e], b[:e]) * (float(e // heads) ** -0.5)
+    q = linear(query, w[:e], b[:e]) * (float(e // heads) ** -0.5)
     if key is value:        # one (2E x E) projection like the reference's kv_same branch (:268-275): half the GEMM launches
-        k, v = F.linear(key, w[e:], b[e:]).chunk(2, dim=-1)
+        k, v = linear(key, w[e:], b[e:]).chunk(2, dim=-1)
     else:
-        k = F.linear(key, w[e:2 * e], b[e:2 * e])
-        v = F.linear(value, w[2 * e:], b[2 * e:])
+        k = linear(key, w[e:2 * e], b[e:2 * e])
+        v = linear(value, w[2 * e:], b[2 * e:])
     if q_pos is not None:
         q = rope_apply(q, q_pos)
         k = rope_apply(k, k_pos)
     o = attention_core(q, k, v, heads, key_padding_mask, dropout_p)
-    return attn.out_proj(o)
+    return linear(o, attn.out_proj.weight, attn.out_proj.bias)
 
 
 def xattn_stack(stack, x, ctx, q_pos=None, k_pos=None):
@@ -43,7 +43,7 @@ def xattn_stack(stack, x, ctx, q_pos=None, k_pos=None):
         rot = q_pos is not None
         att = mha(al.multihead_attn, stack.num_heads, x, ctx, ctx, q_pos if rot else None, k_pos if rot else None)
         x = al.norm(x + att)
-        x = fl.norm(x + fl.linear2(F.relu(fl.linear1(x))))
+        x = fl.norm(x + linear(F.relu(linear(x, fl.linear1.weight, fl.linear1.bias)), fl.linear2.weight, fl.linear2.bias))
         outs.append(x)
     return outs
 
@@ -85,5 +85,7 @@ def parallel_stack(stack, x, x_mask, ctx, x_pos=None, ctx_pos=None, sem_pos=None
         # ---- FFN-1 (layers.py:205-209); ffn_12 holds its own Dropout modules
         if stack.apply_ffn:
             y = ada_ln(layer.adaln_ff1, x, t_emb) if ada else x
-            x = layer.norm_122(y + layer.ffn_12(y))
+            ffn = layer.ffn_12                      # Linear, ReLU, Dropout, Linear, Dropout (layers.py:76-82)
+            hid = F.dropout(F.relu(linear(y, ffn[0].weight, ffn[0].bias)), ffn[2].p, training)
+            x = layer.norm_122(y + F.dropout(linear(hid, ffn[3].weight, ffn[3].bias), ffn[4].p, training))
     return x

@@ -156,6 +156,26 @@ def test_gather_tokens_backward(channels_last):
     assert torch.equal(fc2.grad.cpu(), want2)
 
 
+@pytest.mark.parametrize("rows,o,i", [(70000, 60, 60), (5000, 120, 60), (3000, 480, 120), (33, 7, 5), (513, 64, 64)])
+def test_linear_weight_gradient_kernel(rows, o, i):
+    from act3d_chained_diffuser_b200 import lib
+    from act3d_chained_diffuser_b200.autograd_ops import _Linear
+    dy = synth.normal("wg.dy", (rows, o), 1.0)
+    x = synth.normal("wg.x", (rows, i), 1.0)
+    dw, db = lib.linear_wgrad(dy.cuda(), x.cuda())
+    want_w, want_b = dy.double().t() @ x.double(), dy.double().sum(0)
+    assert rel(dw.cpu().double(), want_w) <= 1e-5 and rel(db.cpu().double(), want_b) <= 1e-5
+    # through autograd, on a 3-D input, with and without bias
+    w = synth.normal("wg.w", (o, i), 0.1).cuda().requires_grad_(True)
+    b = synth.normal("wg.b", (o,), 0.1).cuda().requires_grad_(True)
+    xin = x.cuda().view(1, rows, i).requires_grad_(True)
+    y = _Linear.apply(xin, w, b)
+    y.backward(dy.cuda().view(1, rows, o))
+    assert rel(w.grad.cpu().double(), want_w) <= 1e-5 and rel(b.grad.cpu().double(), want_b) <= 1e-5
+    assert rel(xin.grad.cpu().double()[0], dy.double() @ w.detach().cpu().double()) <= 1e-4
+    assert rel(y.detach().cpu()[0], torch.nn.functional.linear(x, w.detach().cpu(), b.detach().cpu())) <= 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ Act3D
 def _act3d(use_instruction, **over):
     from model import Act3D
