@@ -43,5 +43,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_tools(verbose=False):
+    """Compile the standalone micro-benchmarks under tools/micro/ (one executable each, into build/)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    root = os.path.join(HERE, "..")
+    out_dir = os.path.join(root, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    built = []
+    for src in sorted(glob.glob(os.path.join(root, "tools", "micro", "*.cu"))):
+        exe = os.path.join(out_dir, os.path.splitext(os.path.basename(src))[0])
+        if os.path.exists(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
+            built.append(exe)
+            continue
+        res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", exe, src],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src + ":\n" + res.stdout + res.stderr)
+        built.append(exe)
+    return built
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

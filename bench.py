@@ -295,10 +295,12 @@ def run_ours(args, rank, world, device, local=0):
                 "traffic": 57.1e6, "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
                 "share_of_step": round(sum(kern_ms) / ms_res, 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
-                "mufu_floor_ms": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3, 3),
+                "binding_unit": {"unit": "MUFU ex2 (16 / clk / SM at 1.965 GHz, measured 15.9 with tools/micro/mufu_bench.cu)",
+                                 "floor_ms": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3, 3),
+                                 "frac": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3 / avg, 4)},
                 "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample.  head_dim 15 means one exp per 30 useful FLOPs: "
                         "the binding unit is MUFU (16 ex2/clk/SM, measured with tools/micro/mufu_bench.cu), not the tensor pipe; "
-                        "mufu_floor_ms is the launch time at 100 % XU.  ncu: XU pipe 79 %, tensor pipe 13 % "
+                        "binding_unit.floor_ms is the launch time at 100 % XU.  ncu: XU pipe 79 %, tensor pipe 13 % "
                         "(profiles/r1_xattn_ghost_v4_ncu.txt)"}
 
     kf = w["batch"] * world * args.steps
