@@ -37,11 +37,12 @@ def _inputs(batch, ncam, seed):
     return [t.cuda() for t in (rgb, pcd, instr, grip)]
 
 
-def test_act3d_c2_ghost_points_are_scored_independently():
+@pytest.mark.parametrize("ng", [16384, 5461])      # 5461 = the CLI's 16384 ghost points in total: ragged last 128-row tile
+def test_act3d_c2_ghost_points_are_scored_independently(ng):
     from act3d_chained_diffuser_b200 import lib
     m = _c2_model()
     ins = _inputs(16, 4, 7)
-    b, ng = 16, 16384
+    b = 16
     g = torch.Generator().manual_seed(3)
     lo, hi = torch.tensor(synth.WORKSPACE_LO), torch.tensor(synth.WORKSPACE_HI)
     base = [(lo + torch.rand(b, ng, 3, generator=g) * (hi - lo)).cuda() for _ in range(3)]
