@@ -1,47 +1,57 @@
 // Context K/V cache builder: k/v in-projection + 3-D rotary on K + head split + fp16 tile images.
-//
-// One CTA = one 64-key tile of one sample.  The 64 context tokens are staged once (K-major) in
-// shared memory together with their cos/sin table, then for every attention layer ("set") that
-// shares this context the CTA runs the [64 x E] x [E x 2E] projection as a register-tiled fp32
-// GEMM, rotates K, rounds to fp16 and assembles the tile image in shared memory in exactly the
-// byte layout the attention kernels ldmatrix from; the image leaves with 16-byte coalesced
-// stores.  HBM-bound: reads 64*(E+3)*4 B, writes nsets*2*H*2 KiB per CTA.
-#include "a3d_linear.cuh"
+// HBM-bound by design: reads 64*(E+3)*4 B, writes nsets*2*H*2 KiB per CTA (64-key tile).
+#include "a3d_mma_gemm.cuh"
 
 namespace a3d {
 
 template <int E, int H>
 struct KvCfg {
-    static constexpr int EP = 16 * H;          // padded embed (64 / 128)
-    static constexpr int NW = 2 * EP;          // packed weight width (K | V)
-    static constexpr int RP = 66;              // row pitch of the K-major token tile
-    static constexpr int PASSES = NW / 128;    // 128 output columns per GEMM pass
+    static constexpr int EP = 16 * H;          // padded embed (64 / 128) = padded K of the projection
+    static constexpr int NW = 2 * EP;          // packed output width (K | V)
+    static constexpr int KSTEPS = EP / 16;     // k16 steps
+    static constexpr int NTILES = NW / 8;      // n8 tiles of one set (K tiles first, then V tiles)
+    static constexpr int PITCH = EP + 8;       // halfs per row of an activation plane (conflict-free ldmatrix)
     static constexpr int IMG_HALF = H * 2048;  // bytes of the K (or V) image of one tile
-    static constexpr size_t SMEM = (size_t)E * RP * 4 + 2 * 64 * (E / 2) * 4 + 2 * IMG_HALF;
+    static constexpr int SET_UINT4 = KSTEPS * NTILES * 32;   // fragment-ordered weight of one set
+    static constexpr size_t SMEM = (size_t)2 * 64 * PITCH * 2 + 2 * 64 * (E / 2) * 4 + 2 * IMG_HALF;
 };
 
+// One CTA = one 64-key tile of one sample, 8 warps = 4 row tiles x {K half, V half}.  The 64 tokens are staged once as
+// fp16 (hi, lo) planes together with their cos/sin table; for every attention layer ("set") sharing this context the
+// [64 x E] x [E x 2E] projection runs on the tensor cores as the error-compensated split-fp16 GEMM of
+// a3d_mma_gemm.cuh (fp32-class accuracy: the cache must agree with an fp32 projection to 1 fp16 ulp), K is rotated in
+// the accumulator fragments (a rotary pair = the two columns a thread holds), rounded to fp16 and written into the
+// tile image in exactly the byte layout the attention kernels consume; the image leaves with 16-byte coalesced stores.
 template <int E, int H>
 __global__ void __launch_bounds__(256) ctx_kv_kernel(const float* __restrict__ tok, const float* __restrict__ pos,
-                                                     int tok_rows, int nk, const float* __restrict__ wkv,
+                                                     int tok_rows, int nk, const uint4* __restrict__ wkv,
                                                      const float* __restrict__ bkv, unsigned rope_mask, int nsets,
                                                      unsigned char* __restrict__ kv, int batch, int ntiles) {
     using C = KvCfg<E, H>;
     extern __shared__ __align__(16) unsigned char smem[];
-    float* xt = reinterpret_cast<float*>(smem);                       // [E][RP]
-    float* cs = xt + E * C::RP;                                       // [64][E/2] cos
-    float* sn = cs + 64 * (E / 2);                                    // [64][E/2] sin
+    __half* ah = reinterpret_cast<__half*>(smem);                      // [64][PITCH] hi plane
+    __half* al = ah + 64 * C::PITCH;                                   // [64][PITCH] lo plane
+    float* cs = reinterpret_cast<float*>(al + 64 * C::PITCH);          // [64][E/2] cos
+    float* sn = cs + 64 * (E / 2);                                     // [64][E/2] sin
     unsigned char* img = reinterpret_cast<unsigned char*>(sn + 64 * (E / 2));   // K image | V image
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, b = blockIdx.y;
     const int r0 = tile * 64;
 
-    // ---- stage tokens (K-major) and the rotary table
-    for (int i = tid; i < 64 * E; i += 256) {
-        const int r = i / E, c = i - r * E;
-        float v = 0.f;
-        if (r0 + r < nk) v = __ldg(tok + ((long)b * tok_rows + r0 + r) * E + c);
-        xt[c * C::RP + r] = v;
+    // ---- stage tokens as (hi, lo) fp16 planes (zero beyond nk and in the padded columns) and the rotary table
+    for (int i = tid; i < 64 * (C::EP / 2); i += 256) {
+        const int r = i / (C::EP / 2), c = 2 * (i - r * (C::EP / 2));
+        float v0 = 0.f, v1 = 0.f;
+        if (r0 + r < nk && c < E) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(tok + ((long)b * tok_rows + r0 + r) * E + c));
+            v0 = t.x;
+            v1 = t.y;
+        }
+        uint32_t hi, lo;
+        split_h2(v0, v1, hi, lo);
+        *reinterpret_cast<uint32_t*>(ah + r * C::PITCH + c) = hi;
+        *reinterpret_cast<uint32_t*>(al + r * C::PITCH + c) = lo;
     }
     for (int i = tid; i < 64 * (E / 2); i += 256) {
         const int r = i / (E / 2), p = i - r * (E / 2);
@@ -56,65 +66,54 @@ __global__ void __launch_bounds__(256) ctx_kv_kernel(const float* __restrict__ t
     }
     __syncthreads();
 
-    const int rg = (warp & 3) * 8 + (lane & 7);
-    const int cg = (warp >> 2) * 4 + (lane >> 3);
-    const int row_a = 2 * rg, row_b = 2 * rg + 1;
+    const int m0 = 16 * (warp & 3);
+    const bool is_v = (warp >> 2) != 0;
+    const int g = lane >> 2, q4 = lane & 3;
+    constexpr int NT = 8;                                   // n tiles per GEMM call (64 output columns)
 
     for (int s = 0; s < nsets; ++s) {
         const bool rope = (rope_mask >> s) & 1u;
-        const float* w_s = wkv + (size_t)s * E * C::NW;
-        const float* b_s = bkv + (size_t)s * C::NW;
+        const uint4* w_s = wkv + (size_t)s * C::SET_UINT4;
+        const float* b_s = bkv + (size_t)s * C::NW + (is_v ? C::EP : 0);
+        unsigned char* base = img + (is_v ? C::IMG_HALF : 0);
+#pragma unroll 1
+        for (int part = 0; part < C::EP / 64; ++part) {     // 64 columns of this warp's half per pass
+            float acc[NT][4];
+            const int nt0 = (is_v ? C::EP / 8 : 0) + part * NT;
+            mma_gemm_split<C::KSTEPS, NT, C::PITCH>(ah, al, m0, w_s, C::NTILES, nt0, lane, acc);
 #pragma unroll
-        for (int pass = 0; pass < C::PASSES; ++pass) {
-            float acc[2][16];
-            gemm_2x16<E, C::RP, C::NW>(xt, w_s + pass * 128, rg, cg, acc);
-            const int col0 = pass * 128 + 16 * cg;            // column in the packed [K | V] output
-            const bool is_v = col0 >= C::EP;
-            const int dim0 = col0 - (is_v ? C::EP : 0);       // first embed dim of this thread
+            for (int n = 0; n < NT; ++n) {
+                const int dim = part * 64 + 8 * n + 2 * q4;                 // even; this thread holds dims (dim, dim+1)
+                const float b0 = __ldg(b_s + dim), b1 = __ldg(b_s + dim + 1);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float bias = __ldg(b_s + col0 + c);
-                acc[0][c] += bias;
-                acc[1][c] += bias;
-            }
-            if (!is_v && rope) {
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int row = m0 + g + 8 * rr;
+                    const bool valid = (r0 + row) < nk;
+                    float v0 = acc[n][2 * rr] + b0, v1 = acc[n][2 * rr + 1] + b1;
+                    if (!is_v && rope && dim < E) {                          // rotary pair (2i, 2i+1), i = dim / 2
+                        const float c = cs[row * (E / 2) + (dim >> 1)], sv = sn[row * (E / 2) + (dim >> 1)];
+                        const float ev = v0, od = v1;
+                        v0 = ev * c - od * sv;
+                        v1 = od * c + ev * sv;
+                    }
+                    const int swz = (row >> 2) & 1;
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int pi = (dim0 >> 1) + p;
-                    if (2 * pi < E) {
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            const int row = (r == 0) ? row_a : row_b;
-                            const float c = cs[row * (E / 2) + pi], sv = sn[row * (E / 2) + pi];
-                            const float ev = acc[r][2 * p], od = acc[r][2 * p + 1];
-                            acc[r][2 * p] = ev * c - od * sv;
-                            acc[r][2 * p + 1] = od * c + ev * sv;
+                    for (int e = 0; e < 2; ++e) {
+                        const int dd = dim + e;
+                        int h, d;
+                        float val;
+                        if (dd < E) {
+                            h = dd / 15;
+                            d = dd - 15 * h;
+                            val = valid ? (e ? v1 : v0) : 0.f;
+                        } else {            // padded embed dims E..EP-1 own the pad slot (d = 15) of head dd-E
+                            h = dd - E;
+                            d = 15;
+                            val = valid ? 1.f : 0.f;      // V: softmax denominator; K: carries the shift of a3d_xattn4.cu
                         }
+                        const int off = h * 2048 + row * 32 + (((d >> 3) ^ swz) << 4) + (d & 7) * 2;
+                        *reinterpret_cast<__half*>(base + off) = __float2half_rn(val);
                     }
-                }
-            }
-            unsigned char* base = img + (is_v ? C::IMG_HALF : 0);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int row = (r == 0) ? row_a : row_b;
-                const bool valid = (r0 + row) < nk;
-                const int swz = (row >> 2) & 1;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int dim = dim0 + c;
-                    int h, d;
-                    float val;
-                    if (dim < E) {
-                        h = dim / 15;
-                        d = dim - 15 * h;
-                        val = valid ? acc[r][c] : 0.f;
-                    } else {            // padded embed dims E..EP-1 own the pad slot (d = 15) of head dim-E
-                        h = dim - E;
-                        d = 15;
-                        val = valid ? 1.f : 0.f;      // V: softmax denominator; K: carries the shift of a3d_xattn4.cu
-                    }
-                    const int off = h * 2048 + row * 32 + (((d >> 3) ^ swz) << 4) + (d & 7) * 2;
-                    *reinterpret_cast<__half*>(base + off) = __float2half_rn(val);
                 }
             }
         }
@@ -137,7 +136,7 @@ extern "C" size_t a3d_kv_bytes(int nsets, int batch, int nk, int heads) {
 }
 
 extern "C" int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok_rows, int nk, int embed, int heads,
-                          const float* wkv, const float* bkv, const int* rope_host, int nsets, void* kv,
+                          const void* wkv, const float* bkv, const int* rope_host, int nsets, void* kv,
                           void* stream) {
     A3D_REQUIRE(tok && pos && wkv && bkv && rope_host && kv, "a3d_ctx_kv: null pointer");
     A3D_REQUIRE(batch > 0 && nk > 0 && nk <= tok_rows, "a3d_ctx_kv: need 0 < nk <= tok_rows (nk=%d rows=%d)", nk, tok_rows);
@@ -149,12 +148,12 @@ extern "C" int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok
     if (embed == 60 && heads == 4) {
         using C = KvCfg<60, 4>;
         cudaFuncSetAttribute(ctx_kv_kernel<60, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        ctx_kv_kernel<60, 4><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(tok, pos, tok_rows, nk, wkv, bkv, mask, nsets,
+        ctx_kv_kernel<60, 4><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(tok, pos, tok_rows, nk, (const uint4*)wkv, bkv, mask, nsets,
                                                                          (unsigned char*)kv, batch, ntiles);
     } else if (embed == 120 && heads == 8) {
         using C = KvCfg<120, 8>;
         cudaFuncSetAttribute(ctx_kv_kernel<120, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        ctx_kv_kernel<120, 8><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(tok, pos, tok_rows, nk, wkv, bkv, mask, nsets,
+        ctx_kv_kernel<120, 8><<<grid, 256, C::SMEM, (cudaStream_t)stream>>>(tok, pos, tok_rows, nk, (const uint4*)wkv, bkv, mask, nsets,
                                                                           (unsigned char*)kv, batch, ntiles);
     } else {
         A3D_REQUIRE(false, "a3d_ctx_kv: (embed, heads) = (%d, %d) not supported; use (60,4) or (120,8)", embed, heads);

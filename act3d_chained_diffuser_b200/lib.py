@@ -236,7 +236,8 @@ def ctx_kv(tok, pos, nk, heads, wkv, bkv, rope_flags, out=None):
     if out is None or out.numel() < nbytes:
         out = torch.empty(nbytes, device=tok.device, dtype=torch.uint8)
     flags = (c_int * nsets)(*[int(f) for f in rope_flags])
-    _check(load().a3d_ctx_kv(_ptr(_f32(tok)), _ptr(_f32(pos)), b, rows, nk, e, heads, _ptr(_f32(wkv)), _ptr(_f32(bkv)),
+    assert wkv.dtype == torch.int32 and wkv.numel() == nsets * 2 * (16 * heads) ** 2, "wkv: packing.pack_kv_set layout expected"
+    _check(load().a3d_ctx_kv(_ptr(_f32(tok)), _ptr(_f32(pos)), b, rows, nk, e, heads, _raw(wkv), _ptr(_f32(bkv)),
                              flags, nsets, _ptr(out), _stream()), "a3d_ctx_kv")
     return out
 

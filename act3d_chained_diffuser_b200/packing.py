@@ -52,15 +52,17 @@ def pack_xattn_layer(attn, norm, ffw, embed, heads):
 
 
 def pack_kv_set(attn, embed, heads):
-    """K/V in-projection of one attention layer -> (wkv [E][2*EP], bkv [2*EP]):
-    columns [0,E) = W_k^T, [EP, EP+E) = W_v^T (slices W[E:2E], W[2E:3E],
-    multihead_custom_attention.py:268-303)."""
+    """K/V in-projection of one attention layer -> (wkv, bkv) for a3d_ctx_kv: wkv = the [2*EP] x [EP] matrix
+    (rows [0,E) = W_k, rows [EP, EP+E) = W_v: slices W[E:2E], W[2E:3E], multihead_custom_attention.py:268-303)
+    as fragment-ordered split-fp16 words (pack_mma_weight), bkv [2*EP] fp32."""
     ep = 16 * heads
     e = embed
     w_in, b_in = attn.in_proj_weight.detach().float(), attn.in_proj_bias.detach().float()
-    wkv = torch.cat([_kmajor(w_in[e:2 * e], ep), _kmajor(w_in[2 * e:], ep)], dim=1)
+    full = w_in.new_zeros(2 * ep, ep)
+    full[:e, :e] = w_in[e:2 * e]
+    full[ep:ep + e, :e] = w_in[2 * e:]
     bkv = torch.cat([_pad_vec(b_in[e:2 * e], ep), _pad_vec(b_in[2 * e:], ep)])
-    return wkv.contiguous(), bkv.contiguous()
+    return pack_mma_weight(full, ep, 2 * ep).contiguous(), bkv.contiguous()
 
 
 class PackCache:

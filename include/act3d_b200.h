@@ -112,8 +112,9 @@ int a3d_trunk_fpn_topdown(const float* lat, const float* bias, const float* top,
  *   k = embed_rotary(k, cos, sin)                  (:352-353, position_encodings.py:31-34,58-97)
  * and the head split (:356-359).  The rotary table is never materialised: angles are
  * evaluated from pos on the fly.
- * tok [B][tok_rows][E], pos [B][tok_rows][3] (first nk rows used), wkv [nsets][2*EP][E]
- * (rows 0..E-1 = W_k, rows EP..EP+E-1 = W_v, EP = 16*H), bkv [nsets][2*EP],
+ * tok [B][tok_rows][E], pos [B][tok_rows][3] (first nk rows used), wkv [nsets] fragment-ordered split-fp16
+ * weights of the [2*EP] x [EP] matrix (rows 0..E-1 = W_k, rows EP..EP+E-1 = W_v, EP = 16*H; layout of
+ * csrc/a3d_mma_gemm.cuh, produced by packing.pack_kv_set; 2*EP*EP*4 bytes per set), bkv [nsets][2*EP],
  * rope_host[nsets] (1: rotate K of that set).  Output: K/V "tile images", fp16:
  *   kv [nsets][B][ntiles][2][H][64][16],  ntiles = ceil(nk/64),
  * slot 15 of every K and V row holds 1.0 for valid keys (V: the PV product then carries the
@@ -124,7 +125,7 @@ int a3d_trunk_fpn_topdown(const float* lat, const float* bias, const float* top,
  */
 size_t a3d_kv_bytes(int nsets, int batch, int nk, int heads);
 int a3d_ctx_kv(const float* tok, const float* pos, int batch, int tok_rows, int nk, int embed, int heads,
-               const float* wkv, const float* bkv, const int* rope_host, int nsets, void* kv, void* stream);
+               const void* wkv, const float* bkv, const int* rope_host, int nsets, void* kv, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Fused cross-attention stack (the north-star kernel).  Replaces, per layer,
