@@ -113,7 +113,11 @@ class _Linear(torch.autograd.Function):
         dx = (g2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = lib.linear_wgrad(g2, x.reshape(-1, x.shape[-1]).contiguous(), want_bias=ctx.has_bias)
+            x2 = x.reshape(-1, x.shape[-1]).contiguous()
+            if weight.numel() <= 128 * 128:      # one to four 64 x 64 output tiles: the row-split kernel
+                dw, db = lib.linear_wgrad(g2, x2, want_bias=ctx.has_bias)
+            else:                                # wide FFN matrices give a library GEMM enough output tiles
+                dw, db = g2.t() @ x2, (g2.sum(0) if ctx.has_bias else None)
         return dx, dw, db
 
 

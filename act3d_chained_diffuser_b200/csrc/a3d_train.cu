@@ -409,16 +409,18 @@ __global__ void __launch_bounds__(256) soft_ce_kernel(const float* __restrict__ 
 }
 
 // ================================================================================ weight / bias gradient of a linear layer
-// dW[o][i] += sum_r dY[r][o] X[r][i],  db[o] += sum_r dY[r][o]   for y = x W^T + b with R rows (tokens) in the tens of
+// dW[o][i] = sum_r dY[r][o] X[r][i],  db[o] = sum_r dY[r][o]   for y = x W^T + b with R rows (tokens) in the tens of
 // thousands and O, I <= a few hundred: a GEMM whose output is one or a few 64 x 64 tiles and whose reduction
 // dimension is huge.  cuBLAS runs it as a single-CTA SIMT sgemm (0.1 ms per call at R = 66 k: 19 % of a training
-// step); here the rows are split over the grid, every CTA reduces its slice of 512 rows into a 64 x 64 register
-// tile and adds it to dW with fp32 atomics -- one pass over dY and X at HBM speed.
-constexpr int kWgRows = 512;      // rows per CTA
+// step).  Here the rows are split over the grid in slices of 128: every CTA reduces its slice into a 64 x 64 register
+// tile and writes it to a workspace, and a second small kernel sums the slices in a fixed order (deterministic, no
+// atomics) -- one pass over dY and X at HBM speed plus a few MB of partials.
+constexpr int kWgRows = 128;      // rows per CTA
 constexpr int kWgBlk = 32;        // rows per shared-memory block
 
-__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, long rows,
-                                                    int O, int I, float* __restrict__ dw, float* __restrict__ db) {
+__global__ void __launch_bounds__(256) wgrad_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            long rows, int O, int I, float* __restrict__ part_w,
+                                                            float* __restrict__ part_b) {
     __shared__ __align__(16) float ys[kWgBlk][64 + 4];
     __shared__ __align__(16) float xs[kWgBlk][64 + 4];
     const int o0 = blockIdx.y * 64, i0 = blockIdx.z * 64;
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy
             }
         }
     }
+    float* pw = part_w + (size_t)blockIdx.x * O * I;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int o = o0 + 4 * to + a;
@@ -460,10 +463,27 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dy
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int i = i0 + 4 * ti + c;
-            if (i < I) atomicAdd(dw + (long)o * I + i, acc[a][c]);
+            if (i < I) pw[(size_t)o * I + i] = acc[a][c];
         }
-        if (db && blockIdx.z == 0 && ti == 0) atomicAdd(db + o, bsum[a]);
+        if (part_b && blockIdx.z == 0 && ti == 0) part_b[(size_t)blockIdx.x * O + o] = bsum[a];
     }
+}
+
+// out[e] = sum over slices of part[slice][e], e < n  (n = O*I for the weight, O for the bias), fixed summation order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, long slices, long n,
+                                                           float* __restrict__ out) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    long k = 0;
+    for (; k + 4 <= slices; k += 4) {
+        s0 += __ldg(part + (k + 0) * n + e);
+        s1 += __ldg(part + (k + 1) * n + e);
+        s2 += __ldg(part + (k + 2) * n + e);
+        s3 += __ldg(part + (k + 3) * n + e);
+    }
+    for (; k < slices; ++k) s0 += __ldg(part + k * n + e);
+    out[e] = (s0 + s1) + (s2 + s3);
 }
 
 int drop_args(float p, uint32_t* thresh, float* scale) {
@@ -566,12 +586,23 @@ extern "C" int a3d_soft_ce(const float* logits, const float* ghost, const float*
     return check_launch("a3d_soft_ce");
 }
 
+extern "C" size_t a3d_linear_wgrad_workspace(long rows, int out_features, int in_features) {
+    const long slices = (rows + kWgRows - 1) / kWgRows;
+    return (size_t)slices * ((size_t)out_features * in_features + out_features) * sizeof(float);
+}
+
 extern "C" int a3d_linear_wgrad(const float* dy, const float* x, long rows, int out_features, int in_features, float* dw,
-                                float* db, void* stream) {
-    A3D_REQUIRE(dy && x && dw && rows > 0 && out_features > 0 && in_features > 0, "a3d_linear_wgrad: bad arguments");
-    const long chunks = (rows + kWgRows - 1) / kWgRows;
-    A3D_REQUIRE(chunks <= 2147483647L, "a3d_linear_wgrad: too many rows");
-    dim3 grid((unsigned)chunks, (out_features + 63) / 64, (in_features + 63) / 64);
-    wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, x, rows, out_features, in_features, dw, db);
+                                float* db, void* workspace, void* stream) {
+    A3D_REQUIRE(dy && x && dw && workspace && rows > 0 && out_features > 0 && in_features > 0, "a3d_linear_wgrad: bad arguments");
+    const long slices = (rows + kWgRows - 1) / kWgRows;
+    A3D_REQUIRE(slices <= 2147483647L, "a3d_linear_wgrad: too many rows");
+    float* part_w = (float*)workspace;
+    float* part_b = part_w + (size_t)slices * out_features * in_features;
+    dim3 grid((unsigned)slices, (out_features + 63) / 64, (in_features + 63) / 64);
+    cudaStream_t st = (cudaStream_t)stream;
+    wgrad_partial_kernel<<<grid, 256, 0, st>>>(dy, x, rows, out_features, in_features, part_w, db ? part_b : nullptr);
+    const long nw = (long)out_features * in_features;
+    wgrad_reduce_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(part_w, slices, nw, dw);
+    if (db) wgrad_reduce_kernel<<<(out_features + 255) / 256, 256, 0, st>>>(part_b, slices, out_features, db);
     return check_launch("a3d_linear_wgrad");
 }

@@ -47,7 +47,8 @@ EXPORTS = {
     "a3d_rope_apply": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p]),
     "a3d_gather_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                       c_void_p]),
-    "a3d_linear_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "a3d_linear_wgrad_workspace": (c_size_t, [c_long, c_int, c_int]),
+    "a3d_linear_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "a3d_soft_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
     "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -337,9 +338,10 @@ def linear_wgrad(dy, x, want_bias=True):
     """dy (rows, O), x (rows, I) -> dW (O, I), db (O,) or None."""
     rows, o = dy.shape
     i = x.shape[1]
-    dw = torch.zeros(o, i, device=dy.device, dtype=torch.float32)
-    db = torch.zeros(o, device=dy.device, dtype=torch.float32) if want_bias else None
-    _check(load().a3d_linear_wgrad(_ptr(_f32(dy)), _ptr(_f32(x)), rows, o, i, _ptr(dw), _ptr(db), _stream()),
+    dw = torch.empty(o, i, device=dy.device, dtype=torch.float32)
+    db = torch.empty(o, device=dy.device, dtype=torch.float32) if want_bias else None
+    ws = torch.empty(load().a3d_linear_wgrad_workspace(rows, o, i), device=dy.device, dtype=torch.uint8)
+    _check(load().a3d_linear_wgrad(_ptr(_f32(dy)), _ptr(_f32(x)), rows, o, i, _ptr(dw), _ptr(db), _ptr(ws), _stream()),
            "a3d_linear_wgrad")
     return dw, db
 

@@ -214,12 +214,14 @@ int a3d_rope_apply(const float* x, const float* pos, long rows, int embed, int t
 int a3d_gather_tokens_bwd(const float* dtok, const int32_t* idx, int batch, int ncam, int embed, int hw, int k,
                           int tok_rows, int channels_last, float* dfeat, void* stream);
 
-/* Weight / bias gradient of y = x W^T + b over `rows` tokens: dw [O][I] += dy^T x, db [O] += column sums of dy
- * (db may be NULL).  dy [rows][O], x [rows][I] row-major; dw / db are ACCUMULATED into (zero-fill them first).
+/* Weight / bias gradient of y = x W^T + b over `rows` tokens: dw [O][I] = dy^T x, db [O] = column sums of dy
+ * (db may be NULL).  dy [rows][O], x [rows][I] row-major.  Rows are reduced in slices of 128 into `workspace`
+ * (a3d_linear_wgrad_workspace bytes) and summed in a fixed order: deterministic, no atomics.
  * Replaces the single-CTA SIMT GEMMs + separate bias reductions autograd issues for the E x E projections of the
  * attention stacks when rows = batch * tokens is in the tens of thousands. */
+size_t a3d_linear_wgrad_workspace(long rows, int out_features, int in_features);
 int a3d_linear_wgrad(const float* dy, const float* x, long rows, int out_features, int in_features, float* dw,
-                     float* db, void* stream);
+                     float* db, void* workspace, void* stream);
 
 /* Position loss of the keypose trainer in one pass.  Replaces the label construction + F.cross_entropy with
  * probability targets of LossAndMetrics._compute_position_loss (main_keypose.py:387-403) for one pyramid level:
