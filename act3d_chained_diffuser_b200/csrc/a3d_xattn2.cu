@@ -15,6 +15,8 @@
 //       O += P V                   slot 15 of V is 1: the softmax denominator rides in the same MMA
 //   x = LN(x + (O / l) Wo^T + bo);  x = LN(x + W2 relu(W1 x + b1) + b2)  split MMAs chained in registers
 // After the last layer: mask logits <qvec, x> (act3d.py:493-494) and/or the features.
+#include <string.h>
+
 #include "a3d_xattn_common.cuh"
 
 namespace a3d {
@@ -355,6 +357,22 @@ int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
+
+extern "C" int a3d_set_option(const char* name, int value) {
+    if (name && strcmp(name, "xattn_core") == 0) {
+        A3D_REQUIRE(value == 0 || (value >= 2 && value <= 5),
+                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 3 (tcgen05, two-pass), 4 (tcgen05, single pass) "
+                    "or 5 (tcgen05, single pass, warp-specialised exponentials)");
+        g_xattn_core = value;
+        return A3D_OK;
+    }
+    if (name && strcmp(name, "xattn_poly") == 0) {
+        A3D_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4, "a3d_set_option: xattn_poly must be 0, 2, 3 or 4");
+        g_xattn_poly = value;
+        return A3D_OK;
+    }
+    A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");
+}
 
 extern "C" size_t a3d_xattn_layer_words(int embed, int ffn) {
     return (embed == 60 && ffn == 60) ? (size_t)Xa2::LAYER_W * 4 : 0;   // 32-bit words of fragment weights per layer
