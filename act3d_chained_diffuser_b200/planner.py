@@ -472,6 +472,7 @@ class DiffusionPlanner(nn.Module):
         self.n_steps = diffusion_timesteps
         self.gripper_loc_bounds = torch.tensor(gripper_loc_bounds)
         self._noise_fn = None          # test hook: callable(shape) -> CPU/GPU tensor, called in the reference's order
+        self._timestep_fn = None       # test hook: callable(batch) -> long tensor of training timesteps
         self.rng_compat = False        # True: draw Gaussian noise with the reference's torch.randn call sequence
         self.use_cuda_graph = True     # capture the 100-step loop once per shape and replay it
         self._samplers = {}
@@ -651,7 +652,10 @@ class DiffusionPlanner(nn.Module):
         goal[:, :3] = self.normalize_pos(goal[:, :3])
         gt, cur, goal = self.convert_rot(gt), self.convert_rot(cur), self.convert_rot(goal)
         noise = self._randn(gt.shape, dev)
-        t = torch.randint(0, self.n_steps, (len(noise),), device=dev).long()
+        if self._timestep_fn is not None:
+            t = self._timestep_fn(len(noise)).to(dev).long()
+        else:
+            t = torch.randint(0, self.n_steps, (len(noise),), device=dev).long()
         noisy = torch.cat((self.position_noise_scheduler.add_noise(gt[..., :3], noise[..., :3], t),
                            self.rotation_noise_scheduler.add_noise(gt[..., 3:9], noise[..., 3:9], t)), -1)
         total = 0

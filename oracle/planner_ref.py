@@ -234,3 +234,29 @@ def compute_trajectory(sd, cfg: PlannerConfig, trunk, trajectory_mask, rgb, pcd,
     traj = sixd_signal_to_quat(traj)
     traj[:, :, :3] = unnormalize_pos(cfg, traj[:, :, :3])
     return traj
+
+
+def training_loss(sd, cfg: PlannerConfig, trunk, gt_trajectory, trajectory_mask, rgb, pcd, instruction,
+                  curr_gripper, goal_gripper, noise_fn: Callable, timesteps: torch.Tensor):
+    """DiffusionPlanner.forward with run_inference=False (diffusion_model.py:253-324): normalise, 6-D rotations,
+    one random timestep per sample, noise added by the two schedulers, one denoiser evaluation, and
+    100 * L1(position) + 10 * L1(rotation) summed over the returned refinements.  ``noise_fn(shape)`` and
+    ``timesteps`` stand for the reference's torch.randn / torch.randint draws."""
+    pos_s = DDPMScheduler(cfg.diffusion_timesteps, "scaled_linear", "sample")
+    rot_s = DDPMScheduler(cfg.diffusion_timesteps, "squaredcos_cap_v2", "sample")
+    gt = gt_trajectory.clone()
+    gt[:, :, :3] = normalize_pos(cfg, gt[:, :, :3])
+    pcd_n = normalize_pos(cfg, pcd.permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
+    cur, goal = curr_gripper.clone(), goal_gripper.clone()
+    cur[:, :3] = normalize_pos(cfg, cur[:, :3])
+    goal[:, :3] = normalize_pos(cfg, goal[:, :3])
+    gt, cur, goal = quat_signal_to_6d(gt), quat_signal_to_6d(cur), quat_signal_to_6d(goal)
+    noise = noise_fn(gt.shape)
+    noisy = torch.cat((pos_s.add_noise(gt[..., :3], noise[..., :3], timesteps),
+                       rot_s.add_noise(gt[..., 3:9], noise[..., 3:9], timesteps)), -1)
+    ctx = encode_context(sd, cfg, trunk, rgb, pcd_n, instruction, cur, goal)
+    total = 0
+    for pred in denoise_all(sd, cfg, ctx, noisy, trajectory_mask, timesteps):
+        total = total + (100 * F.l1_loss(pred[..., :3], gt[..., :3], reduction="mean")
+                         + 10 * F.l1_loss(pred[..., 3:9], gt[..., 3:9], reduction="mean"))
+    return total

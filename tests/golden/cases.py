@@ -90,3 +90,9 @@ LOSS_VARIANTS = [
     dict(),
     dict(compute_loss_at_all_layers=True, label_smoothing=0.1, symmetric_rotation_loss=True, ground_truth_gaussian_spread=0.02),
 ]
+
+
+def planner_gt_trajectory(batch=2, length=12, seed=0):
+    """Ground-truth trajectory (B, L, 7): xyz in the workspace + unit quaternion (main_trajectory.py:177-199 input)."""
+    q = synth.normal("cd.gtq", (batch, length, 4), seed=seed)
+    return torch.cat([synth.points_in_bounds("cd.gt", (batch, length), seed), q / q.norm(dim=-1, keepdim=True)], -1)

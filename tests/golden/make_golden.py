@@ -159,6 +159,27 @@ def gen_planner_multiscale(ref):
                                     check=synth.checksum(traj, cur, goal, t, inp["curr_gripper"])))
 
 
+def gen_planner_train(ref):
+    """DiffusionPlanner.forward (training objective, diffusion_model.py:253-324) with autograd: loss value and
+    parameter gradients.  eval() mode so that dropout is off; torch.randn / torch.randint are pinned."""
+    model = build_planner(ref)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    gt = cases.planner_gt_trajectory(batch=2, length=12)
+    orig_randint = torch.randint
+    torch.randint = lambda *a, **k: torch.tensor([37, 5])
+    try:
+        with synth.patched_randn(synth.NoiseStream("cdtr")):
+            loss = model(gt, inp["trajectory_mask"], inp["rgb_obs"], inp["pcd_obs"], inp["instruction"],
+                         inp["curr_gripper"], inp["goal_gripper"])
+    finally:
+        torch.randint = orig_randint
+    loss.backward()
+    # 3 M gradient entries: keep (norm, projection on a name-keyed random direction) per tensor, full tensors if small
+    grads = {n: synth.grad_summary(n, p.grad) for n, p in model.named_parameters()
+             if p.grad is not None and p.grad.abs().max() > 0}
+    save("planner_train", dict(loss=loss.detach(), grads=grads, check=synth.checksum(gt, inp["curr_gripper"])))
+
+
 def reference_loss_class():
     """LossAndMetrics straight from the reference's main_keypose.py source (the module itself cannot be
     imported here: tap / blosc / datasets are missing).  Only the class statement is executed."""
@@ -234,6 +255,7 @@ def main():
     gen_keypose_loss(ref)
     gen_act3d_train_grads(ref)
     gen_planner_multiscale(ref)
+    gen_planner_train(ref)
 
 
 if __name__ == "__main__":

@@ -82,6 +82,15 @@ def fill_state_dict(sd: dict, seed=0, skip_prefixes=("backbone.",), gain=1.0) ->
     return sd
 
 
+def grad_summary(name, grad):
+    """Compact fingerprint of a gradient tensor: (l2 norm, <grad, r>, full tensor or None) with r ~ N(0,1) keyed on
+    the parameter name; small tensors (<= 2048 entries) are kept in full."""
+    g = grad.detach().float().cpu()
+    r = normal("proj:" + name, tuple(g.shape))
+    return dict(norm=g.norm().item(), proj=(g * r).sum().item(), rnorm=r.norm().item(),
+                full=g.clone() if g.numel() <= 2048 else None)
+
+
 def checksum(*tensors) -> str:
     h = hashlib.sha256()
     for t in tensors:

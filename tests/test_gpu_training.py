@@ -473,3 +473,25 @@ def test_multiscale_denoiser_training_gradients_match_oracle():
         assert err <= 1e-3 * ref.norm().item() + floor, (name, err, ref.norm().item())
         checked += 1
     assert checked >= 300, checked
+
+
+def test_planner_training_matches_reference_golden():
+    """DiffusionPlanner.forward (training objective) + backward on the GPU against the loss and the parameter-gradient
+    fingerprints of the unmodified reference (tests/golden/planner_train.pt; eval mode = dropout off, pinned noise
+    and timesteps)."""
+    import os
+    from tests.test_oracle_golden import check_grad_fingerprints
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "planner_train.pt"), weights_only=False)
+    m, _ = _planner()
+    m = m.cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    gt = cases.planner_gt_trajectory(batch=2, length=12)
+    assert synth.checksum(gt, inp["curr_gripper"]) == g["check"]
+    m._noise_fn = synth.NoiseStream("cdtr")
+    m._timestep_fn = lambda n: torch.tensor([37, 5])
+    loss = m(gt.cuda(), *[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction", "curr_gripper",
+                                                   "goal_gripper")])
+    assert abs(loss.item() - g["loss"].item()) <= 1e-4 * abs(g["loss"].item())
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    assert check_grad_fingerprints(grads, g["grads"], tol=1e-3) >= 200

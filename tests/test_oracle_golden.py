@@ -292,3 +292,41 @@ def test_planner_multiscale_head_and_sampling():
                                                  noise_fn=synth.NoiseStream("cdms"))
     close(sampled[..., :3], g["trajectory"][..., :3], 1e-4)
     close(sampled[..., 3:], g["trajectory"][..., 3:], 1e-4)
+
+
+def check_grad_fingerprints(named_grads, want, tol=1e-3):
+    """named_grads: name -> tensor; want: name -> synth.grad_summary dict."""
+    checked = 0
+    for name, w in want.items():
+        got = named_grads.get(name)
+        assert got is not None, f"{name}: no gradient"
+        got = got.detach().float().cpu()
+        r = synth.normal("proj:" + name, tuple(got.shape))
+        assert abs(got.norm().item() - w["norm"]) <= tol * w["norm"] + 1e-9, (name, got.norm().item(), w["norm"])
+        assert abs((got * r).sum().item() - w["proj"]) <= tol * w["norm"] * w["rnorm"] + 1e-9, name
+        if w["full"] is not None:
+            assert ((got - w["full"]).norm() / w["full"].norm()).item() <= tol, name
+        checked += 1
+    return checked
+
+
+def test_planner_training_loss_and_gradients():
+    """Oracle training objective + its autograd vs the reference's DiffusionPlanner.forward + backward."""
+    from model import DiffusionPlanner
+    g = load("planner_train")
+    m = DiffusionPlanner(**cases.PLANNER_KW).eval()
+    cases.install_synth_trunk(m.prediction_head, 120)
+    synth.fill_state_dict(m.state_dict(), skip_prefixes=("prediction_head.backbone.",))
+    head = m.prediction_head
+    sd = leaf_state_dict(head)
+    cfg = planner_ref.PlannerConfig(gripper_loc_bounds=synth.BOUNDS)
+    inp = cases.planner_inputs(batch=2, ncam=1, length=12, masked_tail=3)
+    gt = cases.planner_gt_trajectory(batch=2, length=12)
+    assert synth.checksum(gt, inp["curr_gripper"]) == g["check"]
+    loss = planner_ref.training_loss(sd, cfg, act3d_ref.trunk_from_module(head), gt, inp["trajectory_mask"], inp["rgb_obs"],
+                                     inp["pcd_obs"], inp["instruction"], inp["curr_gripper"], inp["goal_gripper"],
+                                     noise_fn=synth.NoiseStream("cdtr"), timesteps=torch.tensor([37, 5]))
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    loss.backward()
+    grads = {"prediction_head." + k: v.grad for k, v in sd.items() if v.grad is not None}
+    assert check_grad_fingerprints(grads, g["grads"], tol=1e-4) >= 200
