@@ -396,7 +396,6 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line (NCCL prints its version banner)
         torch.distributed.init_process_group("nccl", device_id=device)
     args.warmup = max(args.warmup, 3)
     line = run_ours(args, rank, world, device, local)
