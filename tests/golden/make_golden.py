@@ -131,6 +131,27 @@ def gen_planner(ref):
     save("planner_100step", dict(trajectory=traj, check=synth.checksum(inp["curr_gripper"], inp["goal_gripper"])))
 
 
+@torch.no_grad()
+def gen_act3d_variant(ref):
+    """Act3D with the branches the two main fixtures do not take: 6-D rotation from the top ghost point, offset
+    regression head, untied weights / ghost embeddings, two cameras, ragged ghost count."""
+    kw = dict(cases.ACT3D_KW, use_instruction=True, rotation_parametrization="6D_from_top_ghost",
+              regress_position_offset=True, weight_tying=False, gp_emb_tying=False, num_ghost_points_val=3 * 333)
+    torch.manual_seed(0)
+    model = ref.Act3D(**kw).eval()
+    cases.install_synth_trunk(model, kw["embedding_dim"])
+    synth.fill_state_dict(model.state_dict())
+    inp = cases.act3d_inputs(batch=2, ncam=2, seed=3)
+    sampler = synth.make_ghost_sampler(2, 333, seed=3)
+    model._sample_ghost_points = lambda total_timesteps, device, level, anchor=None: sampler(level, anchor)
+    out = model(inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"])
+    save("act3d_variant", dict(
+        position=out["position"], rotation=out["rotation"], gripper=out["gripper"],
+        position_pyramid=out["position_pyramid"], ghost_pcd_masks_pyramid=out["ghost_pcd_masks_pyramid"],
+        fine_ghost_pcd_offsets=out["fine_ghost_pcd_offsets"], query_features=out["query_features"],
+        check=synth.checksum(inp["curr_gripper"], inp["instruction"][:, :2])))
+
+
 def build_planner_ms(ref):
     torch.manual_seed(0)
     model = ref.DiffusionPlanner(**cases.PLANNER_MS_KW).eval()
@@ -256,6 +277,7 @@ def main():
     gen_act3d_train_grads(ref)
     gen_planner_multiscale(ref)
     gen_planner_train(ref)
+    gen_act3d_variant(ref)
 
 
 if __name__ == "__main__":

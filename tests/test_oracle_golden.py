@@ -330,3 +330,32 @@ def test_planner_training_loss_and_gradients():
     loss.backward()
     grads = {"prediction_head." + k: v.grad for k, v in sd.items() if v.grad is not None}
     assert check_grad_fingerprints(grads, g["grads"], tol=1e-4) >= 200
+
+
+def test_act3d_variant_branches():
+    """6-D rotation from the top ghost point, offset head, untied stacks, 2 cameras, 333 ghost points per level."""
+    from model import Act3D
+    g = load("act3d_variant")
+    kw = dict(cases.ACT3D_KW, use_instruction=True, rotation_parametrization="6D_from_top_ghost",
+              regress_position_offset=True, weight_tying=False, gp_emb_tying=False, num_ghost_points_val=3 * 333)
+    m = Act3D(**kw).eval()
+    cases.install_synth_trunk(m, kw["embedding_dim"])
+    synth.fill_state_dict(m.state_dict())
+    inp = cases.act3d_inputs(batch=2, ncam=2, seed=3)
+    assert synth.checksum(inp["curr_gripper"], inp["instruction"][:, :2]) == g["check"]
+    cfg = act3d_ref.Act3DConfig(gripper_loc_bounds=synth.BOUNDS, use_instruction=True, ghost_points_per_level=333,
+                                rotation_parametrization="6D_from_top_ghost", regress_position_offset=True)
+    with torch.no_grad():
+        out = act3d_ref.act3d_forward(m.state_dict(), cfg, act3d_ref.trunk_from_module(m), inp["visible_rgb"],
+                                      inp["visible_pcd"], inp["instruction"], inp["curr_gripper"],
+                                      ghost_sampler=synth.make_ghost_sampler(2, 333, seed=3))
+    for a, b in zip(out["position_pyramid"], g["position_pyramid"]):
+        assert torch.equal(a, b)
+    for lvl in range(3):
+        for j in range(2):
+            close(out["ghost_pcd_masks_pyramid"][lvl][j], g["ghost_pcd_masks_pyramid"][lvl][j], 1e-4, 1e-5)
+    close(out["position"], g["position"], 1e-5)
+    close(out["rotation"], g["rotation"], 1e-4)
+    close(out["gripper"], g["gripper"], 1e-5)
+    close(out["fine_ghost_pcd_offsets"], g["fine_ghost_pcd_offsets"], 1e-5, 1e-5)
+    close(out["query_features"], g["query_features"], 1e-4, 1e-5)
