@@ -1,4 +1,8 @@
-"""Build libact3d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libact3d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Each csrc/*.cu is compiled to an object under build/obj/ (in parallel, only when stale against its own source, the
+shared headers and include/*.h) and the objects are linked into one shared library."""
+import concurrent.futures
 import glob
 import os
 import shutil
@@ -6,11 +10,13 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, ".."))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libact3d_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
 
 
@@ -18,39 +24,64 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libact3d_b200.so cannot be built (and there is no fallback path)")
+    return nvcc
+
+
+def _obj_of(src):
+    return os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
+
+
+def _compile(nvcc, src, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, res
 
 
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library. Raises on failure."""
-    if not force and not _stale():
-        return LIB
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: libact3d_b200.so cannot be built (and there is no fallback path)")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max([os.path.getmtime(p) for p in _headers()] + [os.path.getmtime(__file__)])
+    todo = []
+    for src in sources():
+        o = _obj_of(src)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(src), hdr_t):
+            todo.append(src)
+    for o in glob.glob(os.path.join(OBJ, "*.o")):          # objects of deleted sources
+        if o not in [_obj_of(s) for s in sources()]:
+            os.remove(o)
+            force = True
+    if todo:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            for src, res in ex.map(lambda s: _compile(nvcc, s, verbose), todo):
+                if verbose:
+                    sys.stderr.write(res.stderr)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed on " + src + ":\n" + res.stdout + res.stderr)
+    objs = [_obj_of(s) for s in sources()]
+    if force or todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 
 def build_tools(verbose=False):
     """Compile the standalone micro-benchmarks under tools/micro/ (one executable each, into build/)."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    root = os.path.join(HERE, "..")
-    out_dir = os.path.join(root, "build")
+    nvcc = _nvcc()
+    out_dir = os.path.join(ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
     built = []
-    for src in sorted(glob.glob(os.path.join(root, "tools", "micro", "*.cu"))):
+    for src in sorted(glob.glob(os.path.join(ROOT, "tools", "micro", "*.cu"))):
         exe = os.path.join(out_dir, os.path.splitext(os.path.basename(src))[0])
         if os.path.exists(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
             built.append(exe)

@@ -18,6 +18,17 @@ namespace a3d {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// "done once" flag keyed by the current device: function attributes (cudaFuncSetAttribute) are per device, and a
+// process may drive several GPUs (one caller thread per device, include/act3d_b200.h).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& flag() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+};
+
 #define A3D_REQUIRE(cond, ...)                     \
     do {                                           \
         if (!(cond)) {                             \

@@ -351,17 +351,16 @@ using namespace a3d;
 
 // 0 (default): pick per launch -- the single-pass tcgen05 / TMEM core (a3d_xattn4.cu) for launches that fill the GPU,
 // the mma.sync core (this file) for the small ones (the 1-token query stack: 16 CTAs, runs on a side stream next to a
-// ghost-point launch whose CTAs own all of an SM's tensor memory); 2 / 3 / 4 force mma.sync / tcgen05 two-pass / single pass
+// ghost-point launch whose CTAs own all of an SM's tensor memory); 2 / 4 / 5 force mma.sync / tcgen05 single pass / its warp-specialised variant
 int g_xattn_core = 0;
-int a3d_launch_xattn3(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "xattn_core") == 0) {
-        A3D_REQUIRE(value == 0 || (value >= 2 && value <= 5),
-                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 3 (tcgen05, two-pass), 4 (tcgen05, single pass) "
+        A3D_REQUIRE(value == 0 || value == 2 || value == 4 || value == 5,
+                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 4 (tcgen05, single pass) "
                     "or 5 (tcgen05, single pass, warp-specialised exponentials)");
         g_xattn_core = value;
         return A3D_OK;
@@ -372,6 +371,23 @@ extern "C" int a3d_set_option(const char* name, int value) {
         return A3D_OK;
     }
     A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");
+}
+
+int a3d_xattn4_replays(unsigned long long* value, int reset);
+int a3d_xattn5_replays(unsigned long long* value, int reset);
+
+extern "C" int a3d_debug_counter(const char* name, int reset, unsigned long long* value_host) {
+    A3D_REQUIRE(name && value_host, "a3d_debug_counter: null pointer");
+    if (strcmp(name, "xattn_replays") == 0) {
+        unsigned long long v4 = 0, v5 = 0;
+        if (a3d_xattn4_replays(&v4, reset) != A3D_OK || a3d_xattn5_replays(&v5, reset) != A3D_OK) {
+            set_error("a3d_debug_counter: %s", cudaGetErrorString(cudaGetLastError()));
+            return A3D_ECUDA;
+        }
+        *value_host = v4 + v5;
+        return A3D_OK;
+    }
+    A3D_REQUIRE(false, "a3d_debug_counter: unknown counter '%s'", name);
 }
 
 extern "C" size_t a3d_xattn_layer_words(int embed, int ffn) {
@@ -417,13 +433,12 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.logits = logits;
     dim3 grid((nq + Xa2::ROWS - 1) / Xa2::ROWS, batch);
     const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 4 : 2);
-    if (core == 3) return a3d_launch_xattn3(a, grid, (cudaStream_t)stream);
     if (core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
     if (core == 5) return a3d_launch_xattn5(a, grid, (cudaStream_t)stream);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \
-        static bool once = false;                                                                                      \
-        if (!once) {                                                                                                   \
+        static PerDeviceOnce once_dev;                                                                                      \
+        if (bool& once = once_dev.flag(); !once) {                                                                                                   \
             cudaError_t e = cudaFuncSetAttribute(xattn2_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                                  (int)Xa2::SMEM);                                                      \
             if (e != cudaSuccess) {                                                                                    \

@@ -51,6 +51,9 @@ struct Xa4Bars {
     uint32_t overflow_count;      // bumped by every row thread whose fast pass produced a non-finite denominator
 };
 
+// layers replayed in safe mode since the last reset (one count per CTA and replay): a3d_debug_counter("xattn_replays")
+__device__ unsigned long long g_xa4_replays = 0;
+
 template <int PM>
 __global__ void __launch_bounds__(Xa4::THREADS, 2) xattn4_kernel(const Xa2Args a) {
     using C = Xa4;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(Xa4::THREADS, 2) xattn4_kernel(const Xa2Args a
                         ++ps;
                         break;
                     }
+                    atomicAdd(&g_xa4_replays, 1ull);
                 }
             }
         }
@@ -557,8 +561,8 @@ using namespace a3d;
 // launched by a3d_xattn_stack (a3d_xattn2.cu) when the "xattn_core" option selects this kernel
 template <int PM>
 static int launch_pm(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once_dev;
+    if (bool& once = once_dev.flag(); !once) {
         cudaError_t e = cudaFuncSetAttribute(xattn4_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Xa4::SMEM);
         if (e != cudaSuccess) {
             set_error("a3d_xattn_stack(tcgen05 v4): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -568,6 +572,13 @@ static int launch_pm(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
     }
     xattn4_kernel<PM><<<grid, Xa4::THREADS, Xa4::SMEM, stream>>>(a);
     return check_launch("a3d_xattn_stack(tcgen05 v4)");
+}
+
+int a3d_xattn4_replays(unsigned long long* value, int reset) {
+    const unsigned long long zero = 0;
+    if (cudaMemcpyFromSymbol(value, g_xa4_replays, sizeof(*value)) != cudaSuccess) return A3D_ECUDA;
+    if (reset && cudaMemcpyToSymbol(g_xa4_replays, &zero, sizeof(zero)) != cudaSuccess) return A3D_ECUDA;
+    return A3D_OK;
 }
 
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly) {

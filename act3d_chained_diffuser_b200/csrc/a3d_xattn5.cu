@@ -46,6 +46,9 @@ struct Xa5Bars {
     uint32_t overflow_count;      // bumped by every row thread whose fast pass produced a non-finite denominator
 };
 
+// layers replayed in safe mode since the last reset: a3d_debug_counter("xattn_replays")
+__device__ unsigned long long g_xa5_replays = 0;
+
 __global__ void __launch_bounds__(Xa5::THREADS, 2) xattn5_kernel(const Xa2Args a) {
     using C = Xa5;
     constexpr int E = C::E, H = C::H;
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(Xa5::THREADS, 2) xattn5_kernel(const Xa2Args a
                         ++ps;
                         break;
                     }
+                    atomicAdd(&g_xa5_replays, 1ull);
                 }
             }
         } else if (warp == C::ISSUE_WARP + 1 && lane == 0) {
@@ -618,9 +622,16 @@ __global__ void __launch_bounds__(Xa5::THREADS, 2) xattn5_kernel(const Xa2Args a
 using namespace a3d;
 
 // launched by a3d_xattn_stack (a3d_xattn2.cu) when the "xattn_core" option selects this kernel
+int a3d_xattn5_replays(unsigned long long* value, int reset) {
+    const unsigned long long zero = 0;
+    if (cudaMemcpyFromSymbol(value, g_xa5_replays, sizeof(*value)) != cudaSuccess) return A3D_ECUDA;
+    if (reset && cudaMemcpyToSymbol(g_xa5_replays, &zero, sizeof(zero)) != cudaSuccess) return A3D_ECUDA;
+    return A3D_OK;
+}
+
 int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream) {
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once_dev;
+    if (bool& once = once_dev.flag(); !once) {
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, xattn5_kernel) != cudaSuccess || fa.numRegs < Xa5::LAUNCH_REGS) {
             // setmaxnreg.inc would block forever: the CTA's register pool is too small for the warpgroup budgets

@@ -877,8 +877,8 @@ extern "C" int cd_ctx_lang(float* tok, int batch, int tok_rows, int nctx, int em
     A3D_REQUIRE(embed == E && heads == H, "cd_ctx_lang: built for embedding_dim 120 / 8 heads (got %d / %d)", embed, heads);
     A3D_REQUIRE(batch > 0 && nctx > 0 && nctx <= tok_rows && n_instr > 0 && n_instr <= 64 && nlayers > 0,
                 "cd_ctx_lang: bad sizes (nctx=%d rows=%d n_instr=%d)", nctx, tok_rows, n_instr);
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once_dev;
+    if (bool& once = once_dev.flag(); !once) {
         if (int rc = set_smem((const void*)cd_ctx_lang_kernel, SMEM_BYTES)) return rc;
         once = true;
     }
@@ -897,8 +897,8 @@ extern "C" int cd_step_begin(const float* traj, int batch, int length, const flo
     A3D_REQUIRE(batch > 0 && length > 0 && length <= ROWS, "cd_step_begin: trajectory length %d not in [1,64]", length);
     A3D_REQUIRE(!lang_w || (lang_v && lang_k && lang_vv && n_instr > 0 && n_instr <= 64), "cd_step_begin: instruction K/V missing");
     A3D_REQUIRE(!next_wq || (q_out && next_bq), "cd_step_begin: q_out / next_bq missing");
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once_dev;
+    if (bool& once = once_dev.flag(); !once) {
         if (int rc = set_smem((const void*)cd_step_begin_kernel, SMEM_BYTES)) return rc;
         once = true;
     }
@@ -953,8 +953,8 @@ extern "C" int cd_post(const float* traj, int batch, int length, const unsigned 
     A3D_REQUIRE(!do_update || (traj_out && pos_upd && cond_data && cond_mask && coef_host && reg_w && reg_dim == 6 &&
                                (last_step || (noise_pos && noise_rot))),
                 "cd_post: DDPM update needs traj_out, pos_upd, cond_*, coef, the rotation regressor and noise");
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once_dev;
+    if (bool& once = once_dev.flag(); !once) {
         if (int rc = set_smem((const void*)cd_post_kernel, SMEM_BYTES)) return rc;
         once = true;
     }

@@ -18,6 +18,7 @@ EXPORTS = {
     "a3d_last_error": (c_char_p, []),
     "a3d_abi_version": (c_int, []),
     "a3d_set_option": (c_int, [c_char_p, c_int]),
+    "a3d_debug_counter": (c_int, [c_char_p, c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "a3d_pcd_pyramid": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "a3d_local_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_traj_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -115,7 +116,18 @@ def _check(code, what):
 
 
 def set_option(name, value):
+    global _launches
     _check(load().a3d_set_option(name.encode(), int(value)), "a3d_set_option")
+    _launches -= 1                                    # not a kernel launch
+
+
+def debug_counter(name, reset=False):
+    """Diagnostics counter of the current device (synchronises it): see a3d_debug_counter in include/act3d_b200.h."""
+    global _launches
+    out = ctypes.c_ulonglong(0)
+    _check(load().a3d_debug_counter(name.encode(), int(bool(reset)), ctypes.byref(out)), "a3d_debug_counter")
+    _launches -= 1                                    # not a kernel launch
+    return int(out.value)
 
 
 def _ptr(t):

@@ -40,11 +40,15 @@ int a3d_abi_version(void);
 /* Process-wide tuning knobs (not part of the numerical contract):
  *   "xattn_core": attention core of a3d_xattn_stack: 0 (default) = per launch: the single-pass tcgen05 / TMEM kernel
  *                 for launches of >= 296 CTAs, the mma.sync kernel for small ones; 2 = mma.sync (HMMA) kernel,
- *                 3 = tcgen05 / TMEM two-pass kernel, 4 = tcgen05 / TMEM single-pass kernel, 5 = the single-pass kernel
+ *                 4 = tcgen05 / TMEM single-pass kernel, 5 = the single-pass kernel
  *                 with warp-specialised exponentials (MUFU warps + FMA-polynomial warps, setmaxnreg; study).
  *   "xattn_poly": how many of every 8 softmax exponentials of a3d_xattn_stack are evaluated with the
  *                 FMA-pipe polynomial instead of the MUFU unit: 0 (default, fastest measured), 2, 3 or 4. */
 int a3d_set_option(const char* name, int value);
+/* Test / diagnostics counters kept on the current device; the call SYNCHRONISES the device (it is not part of the
+ * hot path).  "xattn_replays": attention layers that a CTA of a3d_xattn_stack's tcgen05 kernels replayed in safe mode
+ * because the unchecked fast pass overflowed (see csrc/a3d_xattn4.cu).  reset != 0 zeroes the counter after reading. */
+int a3d_debug_counter(const char* name, int reset, unsigned long long* value_host);
 
 /* ---------------------------------------------------------------------------------
  * Point pyramid.  Replaces F.interpolate(pcd, scale_factor=1/f, mode='bilinear') +

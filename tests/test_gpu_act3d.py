@@ -33,8 +33,18 @@ def rel(a, b):
 LOGIT_TOL = 2e-3   # mask logits are <query, ghost> dot products: cancellation roughly doubles the 1e-3 feature budget
 
 
+@pytest.fixture
+def xattn_core(request):
+    """Force one attention core of a3d_xattn_stack for the test (0 = the library's own choice)."""
+    from act3d_chained_diffuser_b200 import lib
+    lib.set_option("xattn_core", request.param)
+    yield request.param
+    lib.set_option("xattn_core", 0)
+
+
+@pytest.mark.parametrize("xattn_core", [0, 2, 4, 5], indirect=True)
 @pytest.mark.parametrize("use_instruction", [False, True])
-def test_act3d_matches_golden_teacher_forced(use_instruction):
+def test_act3d_matches_golden_teacher_forced(use_instruction, xattn_core):
     g = torch.load(os.path.join(G, f"act3d_c0_instr{int(use_instruction)}.pt"), weights_only=False)
     m, kw = build(use_instruction)
     m = m.cuda()
