@@ -355,14 +355,21 @@ using namespace a3d;
 int g_xattn_core = 0;
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream);
+int a3d_launch_xattn6(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
+int g_xattn6_np = 8;    // a3d_set_option("xattn6_np", n): score pairs (of 16 per thread and unit) on the FMA-pipe polynomial
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "xattn_core") == 0) {
-        A3D_REQUIRE(value == 0 || value == 2 || value == 4 || value == 5,
-                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 4 (tcgen05, single pass) "
-                    "or 5 (tcgen05, single pass, warp-specialised exponentials)");
+        A3D_REQUIRE(value == 0 || value == 2 || value == 4 || value == 5 || value == 6,
+                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 4 (tcgen05, single pass), "
+                    "5 (tcgen05, single pass, warp-specialised exponentials) or 6 (tcgen05 attention + linear layers)");
         g_xattn_core = value;
+        return A3D_OK;
+    }
+    if (name && strcmp(name, "xattn6_np") == 0) {
+        A3D_REQUIRE(value == 0 || value == 4 || (value >= 6 && value <= 10), "a3d_set_option: xattn6_np must be 0, 4 or 6..10");
+        g_xattn6_np = value;
         return A3D_OK;
     }
     if (name && strcmp(name, "xattn_poly") == 0) {
@@ -375,16 +382,18 @@ extern "C" int a3d_set_option(const char* name, int value) {
 
 int a3d_xattn4_replays(unsigned long long* value, int reset);
 int a3d_xattn5_replays(unsigned long long* value, int reset);
+int a3d_xattn6_replays(unsigned long long* value, int reset);
 
 extern "C" int a3d_debug_counter(const char* name, int reset, unsigned long long* value_host) {
     A3D_REQUIRE(name && value_host, "a3d_debug_counter: null pointer");
     if (strcmp(name, "xattn_replays") == 0) {
-        unsigned long long v4 = 0, v5 = 0;
-        if (a3d_xattn4_replays(&v4, reset) != A3D_OK || a3d_xattn5_replays(&v5, reset) != A3D_OK) {
+        unsigned long long v4 = 0, v5 = 0, v6 = 0;
+        if (a3d_xattn4_replays(&v4, reset) != A3D_OK || a3d_xattn5_replays(&v5, reset) != A3D_OK ||
+            a3d_xattn6_replays(&v6, reset) != A3D_OK) {
             set_error("a3d_debug_counter: %s", cudaGetErrorString(cudaGetLastError()));
             return A3D_ECUDA;
         }
-        *value_host = v4 + v5;
+        *value_host = v4 + v5 + v6;
         return A3D_OK;
     }
     A3D_REQUIRE(false, "a3d_debug_counter: unknown counter '%s'", name);
@@ -435,6 +444,7 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 4 : 2);
     if (core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
     if (core == 5) return a3d_launch_xattn5(a, grid, (cudaStream_t)stream);
+    if (core == 6) return a3d_launch_xattn6(a, grid, (cudaStream_t)stream, g_xattn6_np);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \
         static PerDeviceOnce once_dev;                                                                                      \

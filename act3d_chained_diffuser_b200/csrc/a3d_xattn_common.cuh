@@ -1,5 +1,5 @@
 // Device helpers shared by the fused cross-attention kernels (a3d_xattn2.cu: mma.sync core,
-// a3d_xattn3.cu: tcgen05 / TMEM core): packed-weight layout, register-chained split GEMM,
+// a3d_xattn4/5/6.cu: tcgen05 / TMEM cores): packed-weight layout, register-chained split GEMM,
 // fragment-layout LayerNorm, exp2 variants.
 #pragma once
 #include "a3d_mma_gemm.cuh"
@@ -17,7 +17,10 @@ struct Xa2 {
     static constexpr size_t SMEM = X_BYTES + Q_BYTES + (size_t)STAGES * TILE_BYTES + 64;
     // packed weights of one layer: four fragment-ordered [K=64][N=64] matrices (uint4 units) ...
     static constexpr int MAT = 4 * 8 * 32;            // uint4 per matrix
-    static constexpr int W_Q = 0, W_O = MAT, W_1 = 2 * MAT, W_2 = 3 * MAT, LAYER_W = 4 * MAT;
+    static constexpr int W_Q = 0, W_O = MAT, W_1 = 2 * MAT, W_2 = 3 * MAT;
+    // ... followed by the same four matrices as tcgen05 operand images (a3d_xattn6.cu; packing.pack_umma_weight):
+    // image m at W_IMG + m * MAT, 16 KiB each = [hi | lo][4 k-slabs][64 out][16 in] fp16, SWIZZLE_32B rows
+    static constexpr int W_IMG = 4 * MAT, LAYER_W = 8 * MAT;
     // ... and eight fp32 vectors of 64
     static constexpr int B_Q = 0, B_O = 64, G_1 = 128, BE_1 = 192, B_1 = 256, B_2 = 320, G_2 = 384, BE_2 = 448,
                          LAYER_V = 512;

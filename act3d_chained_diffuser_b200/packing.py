@@ -29,8 +29,9 @@ def _kmajor(weight, width):
 
 
 def pack_xattn_layer(attn, norm, ffw, embed, heads):
-    """One layer of an Act3D stack -> (w int32 fragments, v floats) in the Xa2 order (csrc/a3d_xattn2.cu):
-    w = {W_q, W_o, W_1, W_2} as fragment-ordered fp16 (hi, lo) [K=64][N=64] matrices, v = {b_q, b_o, g1, be1,
+    """One layer of an Act3D stack -> (w int32 words, v floats) in the Xa2 order (csrc/a3d_xattn_common.cuh):
+    w = {W_q, W_o, W_1, W_2} as fragment-ordered fp16 (hi, lo) [K=64][N=64] matrices (mma.sync kernel) followed by the
+    same four matrices as tcgen05 operand images (pack_umma_weight), v = {b_q, b_o, g1, be1,
     b_1, b_2, g2, be2} (64 floats each).  The q projection carries hd^-1/2 (multihead_custom_attention.py:244,325)
     and log2(e) so the kernel's softmax is a bare exp2.  W_o's input (K) index is head-padded: k = 16 h + d
     <- attention dim 15 h + d (the pad slot carries the softmax denominator in the kernel; its weight is 0)."""
@@ -43,8 +44,8 @@ def pack_xattn_layer(attn, norm, ffw, embed, heads):
     wo_p = wo.new_zeros(e, ep)
     for h in range(heads):
         wo_p[:, 16 * h:16 * h + hd] = wo[:, hd * h:hd * (h + 1)]
-    w = torch.cat([pack_mma_weight(w_in[:e] * scale, ep, ep), pack_mma_weight(wo_p, ep, ep),
-                   pack_mma_weight(ffw.linear1.weight, ep, ep), pack_mma_weight(ffw.linear2.weight, ep, ep)])
+    mats = [w_in[:e] * scale, wo_p, ffw.linear1.weight, ffw.linear2.weight]
+    w = torch.cat([pack_mma_weight(m, ep, ep) for m in mats] + [pack_umma_weight(m, ep, ep) for m in mats])
     vec = lambda t: _pad_vec(t.detach().float(), ep)
     v = torch.cat([_pad_vec(b_in[:e] * scale, ep), vec(attn.out_proj.bias), vec(norm.weight), vec(norm.bias),
                    vec(ffw.linear1.bias), vec(ffw.linear2.bias), vec(ffw.norm.weight), vec(ffw.norm.bias)])
@@ -105,6 +106,25 @@ def pack_mma_weight(weight, kpad, npad):
         return t.reshape(ks, nt, 32, 2, 2)
     both = torch.stack([frag(hi), frag(lo)], dim=3).contiguous()          # (ks, nt, lane, plane, hsel, pair)
     return both.view(torch.int32).reshape(-1)
+
+
+def pack_umma_weight(weight, kpad, npad):
+    """nn.Linear weight (N_out, K_in) -> int32 buffer holding the B operand of a tcgen05.mma (csrc/a3d_xattn6.cu):
+    [plane: hi | lo][k-slab = K_in // 16][n][16 halves], hi = fp16(w), lo = fp16((w - hi) * 2^11).  One slab is a
+    K-major [npad rows][32 bytes] tile in the canonical SWIZZLE_32B layout -- exactly the layout of a K tile image of
+    a3d_ctx_kv with `n` in the place of the key: inside a 32-byte row the two 16-byte halves are swapped when (n>>2)&1."""
+    w = weight.detach().float()
+    full = w.new_zeros(npad, kpad)
+    full[: w.shape[0], : w.shape[1]] = w
+    hi = full.half()
+    lo = ((full - hi.float()) * 2048.0).half()
+    swap = ((torch.arange(npad, device=w.device) >> 2) & 1).bool()
+
+    def img(p):
+        t = p.view(npad, kpad // 16, 2, 8).permute(1, 0, 2, 3).contiguous()      # (slab, n, 16-byte half, 8)
+        t[:, swap] = t[:, swap].flip(2)
+        return t.reshape(-1)
+    return torch.cat([img(hi), img(lo)]).view(torch.int32)
 
 
 def _scaled_q(attn, e, heads):

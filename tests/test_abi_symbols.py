@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     loaded = lib.load()
     assert loaded.a3d_abi_version() == 1
-    assert lib.xattn_layer_floats(60, 60) == 8 * 64 and lib.xattn_layer_words(60, 60) == 4 * 4 * 8 * 32 * 4
+    assert lib.xattn_layer_floats(60, 60) == 8 * 64 and lib.xattn_layer_words(60, 60) == 2 * 4 * 4 * 8 * 32 * 4
     assert lib.kv_bytes(2, 3, 65, 4) == 2 * 3 * 2 * 2 * 4 * 2048
 
 

@@ -167,7 +167,8 @@ def test_ctx_kv_matches_oracle(lib, embed, heads):
 
 
 # ------------------------------------------------------------------------------- fused attention stack
-CORES = [2, 4, 5]      # attention cores of a3d_xattn_stack: mma.sync, tcgen05 single pass (production), its warp-specialised variant
+CORES = [2, 4, 5, 6]   # attention cores of a3d_xattn_stack: mma.sync, tcgen05 single pass, its warp-specialised variant,
+                       # tcgen05 attention + linear layers with FMA-pipe exponentials
 
 
 def run_stack(lib, sd, layers, x0, x0_mode, q_xyz, ctx, c_xyz, qvec=None, all_layers=False, rope=True, core=0):
@@ -283,7 +284,7 @@ def test_xattn_large_logit_range(lib, core):
     assert_close_attn(feat[0], want.transpose(0, 1), "peaky")
 
 
-@pytest.mark.parametrize("core", [4, 5])
+@pytest.mark.parametrize("core", [4, 5, 6])
 def test_xattn_safe_mode_replay_runs_and_is_exact(lib, core):
     """The tcgen05 cores run an UNCHECKED fast pass (shift = maximum of the first key tile + 6, P up to 2^16 in fp16)
     and replay a layer in safe mode when a later score overshoots that shift by more than 2^22.  Force it: the first
@@ -319,7 +320,7 @@ def test_xattn_safe_mode_replay_runs_and_is_exact(lib, core):
     assert lib.debug_counter("xattn_replays", reset=True) == 0
 
 
-@pytest.mark.parametrize("core", [0, 4, 5])
+@pytest.mark.parametrize("core", [0, 4, 5, 6])
 def test_xattn_c2_launch_subset_vs_oracle(lib, core):
     """BASELINE.json's C2 ghost launch (16 samples x 16384 ghost points x 4150 keys, 2 layers: 2048 CTAs, the shape the
     benchmark times) through the production core, checked against the CPU ORACLE on a 512-ghost subset: ghost points

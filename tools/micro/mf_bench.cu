@@ -50,6 +50,33 @@ __device__ __forceinline__ uint32_t poly16x2(float x0, float x1) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// two scores -> packed fp16 pair, fp32 polynomial on packed f32x2 registers (FADD2 / FFMA2)
+__device__ __forceinline__ unsigned long long pk64(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint32_t poly32x2(float x0, float x1) {
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const unsigned long long X = pk64(x0, x1);
+    const unsigned long long MP = pk64(12582912.0f, 12582912.0f), MN = pk64(-12582912.0f, -12582912.0f);
+    const unsigned long long NEG1 = pk64(-1.0f, -1.0f);
+    const unsigned long long C3 = pk64(0.055170901f, 0.055170901f), C2 = pk64(0.24260952f, 0.24260952f);
+    const unsigned long long C1 = pk64(0.69326097f, 0.69326097f), C0 = pk64(0.99992818f, 0.99992818f);
+    unsigned long long T, R, F, P;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(T) : "l"(X), "l"(MP));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(R) : "l"(T), "l"(MN));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(F) : "l"(R), "l"(NEG1), "l"(X));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(C3), "l"(F), "l"(C2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(P), "l"(F), "l"(C1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(P) : "l"(P), "l"(F), "l"(C0));
+    uint32_t t0, t1, p0, p1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(T));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(P));
+    return pack(__uint_as_float(p0 + (t0 << 23)), __uint_as_float(p1 + (t1 << 23)));
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c)); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
@@ -59,48 +86,173 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         : "memory");
 }
 
+#define R32(r) \
+    "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
+    "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), \
+    "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), \
+    "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define R32_IN(r) \
+    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), \
+    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),  \
+    "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),  \
+    "r"(r[31])
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : R32(r)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};"
+        :
+        : R32_IN(r), "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int NP, int POLY>
-__device__ __forceinline__ void unit(const float4* src, uint4* dst, int tid) {
-    float x[64];
-    uint32_t p[32];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(src + c * 256 + tid)));
-        x[4 * c] = v.x, x[4 * c + 1] = v.y, x[4 * c + 2] = v.z, x[4 * c + 3] = v.w;
+__device__ __forceinline__ uint32_t exp_pair(int i, uint32_t a, uint32_t b) {
+    const float x0 = __uint_as_float(a), x1 = __uint_as_float(b);
+    if (2 * i < NP) {
+        if (POLY == 1) return poly16x2(x0, x1);
+        if (POLY == 2) return poly32x2(x0, x1);
+        return pack(poly32(x0), poly32(x1));
     }
+    return pack(ex2(x0), ex2(x1));
+}
+
+// one unit = 64 scores of this thread's row: tensor memory -> exponentials -> packed halves -> tensor memory.
+// s = 64 fp32 score columns, pdst = 32 columns of packed P.  Simple two-half pipeline (second half in flight while the
+// first is exponentiated).
+template <int NP, int POLY>
+__device__ __forceinline__ void unit(uint32_t s, uint32_t pdst) {
+    uint32_t a[32], b[32], p[32];
+    tmem_ld32(s, a);
+    tmem_wait_ld();
+    tmem_ld32(s + 32, b);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (2 * i < NP) {
-            if (POLY == 1) p[i] = poly16x2(x[2 * i], x[2 * i + 1]);
-            else p[i] = pack(poly32(x[2 * i]), poly32(x[2 * i + 1]));
-        } else {
-            p[i] = pack(ex2(x[2 * i]), ex2(x[2 * i + 1]));
+    for (int i = 0; i < 16; ++i) p[i] = exp_pair<(NP + 1) / 2, POLY>(i, a[2 * i], a[2 * i + 1]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[16 + i] = exp_pair<NP / 2, POLY>(i, b[2 * i], b[2 * i + 1]);
+    tmem_wait_st();         // the previous unit's P
+    tmem_st32(pdst, p);
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+        :
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+        : "memory");
+}
+// half-split unit: one half of the 64 scores entirely on the FMA pipe, the other entirely on the MUFU unit
+template <bool POLY_FIRST, int POLY>
+__device__ __forceinline__ void unit_split(uint32_t s, uint32_t pdst) {
+    uint32_t a[32], b[32], p[32];
+    tmem_ld32(s, a);
+    tmem_wait_ld();
+    tmem_ld32(s + 32, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = exp_pair<POLY_FIRST ? 32 : 0, POLY>(i, a[2 * i], a[2 * i + 1]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[16 + i] = exp_pair<POLY_FIRST ? 0 : 32, POLY>(i, b[2 * i], b[2 * i + 1]);
+    tmem_wait_st();
+    tmem_st32(pdst, p);
+}
+// 32-column unit (a 128-row tile handled by 8 warps: two warps share the 32 lanes, 32 score columns each)
+template <int NP, int POLY>
+__device__ __forceinline__ void unit32(uint32_t s, uint32_t pdst) {
+    uint32_t a[32], p[16];
+    tmem_ld32(s, a);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = exp_pair<NP, POLY>(i, a[2 * i], a[2 * i + 1]);
+    tmem_wait_st();
+    tmem_st16(pdst, p);
+}
+
+// 16 warps, 32 columns per thread and unit.  MODE 5: in-warp mix (NP of 32 polynomial); MODE 6: whole units alternate
+template <int MODE, int NP, int POLY>
+__global__ void __launch_bounds__(512, 1) k16(const float* in, uint32_t* out, int units) {
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 2, w = warp & 3;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t base = tmem + ((uint32_t)(w * 32) << 16) + 128 * g;     // scores +0 / +32, P +64 / +80
+    {
+        uint32_t v[32];
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(in[(h * 32 + i + lane * 7 + warp * 131) & 4095]);
+            tmem_st32(base + 32 * h, v);
         }
+        tmem_wait_st();
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(dst + c * 256 + tid)), "r"(p[4 * c]), "r"(p[4 * c + 1]), "r"(p[4 * c + 2]),
-                     "r"(p[4 * c + 3])
-                     : "memory");
+    for (int u = 0; u < units; ++u) {
+        const uint32_t sb = base + 32 * (u & 1), pb = base + 64 + 16 * (u & 1);
+        if (MODE == 5) unit32<NP, POLY>(sb, pb);
+        else if (((u + g) & 1) == 0) unit32<0, POLY>(sb, pb);
+        else unit32<NP, POLY>(sb, pb);
+    }
+    tmem_wait_st();
+    uint32_t chk[32];
+    tmem_ld32(base + 64, chk);
+    tmem_wait_ld();
+    if (chk[3] == 0x12345678u && lane == 77) out[0] = chk[5];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 template <int MODE, int NP, int POLY>
 __global__ void __launch_bounds__(256, 1) k(const float* in, uint32_t* out, int units) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    float4* src = reinterpret_cast<float4*>(smem);                    // [16][256] float4
-    uint4* dst = reinterpret_cast<uint4*>(smem + 65536);              // [8][256] uint4
-    uint64_t* tok = reinterpret_cast<uint64_t*>(smem + 65536 + 32768);   // [2][4]
+    __shared__ uint64_t tok[8];
+    __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = warp >> 2, w = warp & 3;
-    for (int c = 0; c < 16; ++c) src[c * 256 + tid] = reinterpret_cast<const float4*>(in)[(c * 256 + tid) % 1024];
     if (tid < 8) mbar_init(tok + tid, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    // group g owns columns [256 g, 256 g + 256): scores at +0..63 (two buffers: +0, +64), P at +128..159 / +160..191
+    const uint32_t base = tmem + ((uint32_t)(w * 32) << 16) + 256 * g;
+    {
+        uint32_t v[32];
+        for (int h = 0; h < 4; ++h) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(in[(h * 32 + i + lane * 7 + warp * 131) & 4095]);
+            tmem_st32(base + 32 * h, v);
+        }
+        tmem_wait_st();
+    }
     int km = 0;
     for (int u = 0; u < units; ++u) {
+        const uint32_t sb = base + 64 * (u & 1), pb = base + 128 + 32 * (u & 1);
         if (MODE == 0) {
-            unit<0, POLY>(src, dst, tid);
+            unit<0, POLY>(sb, pb);
+        } else if (MODE == 4) {
+            if (g == 0) unit_split<true, POLY>(sb, pb);
+            else unit_split<false, POLY>(sb, pb);
         } else if (MODE == 3) {
-            unit<NP, POLY>(src, dst, tid);
+            unit<NP, POLY>(sb, pb);
         } else {
             const bool m_unit = ((u + g) & 1) == 0;
             if (m_unit) {
@@ -111,24 +263,30 @@ __global__ void __launch_bounds__(256, 1) k(const float* in, uint32_t* out, int 
                         mbar_wait(tok + w, km & 1);
                     }
                 }
-                unit<0, POLY>(src, dst, tid);
+                unit<0, POLY>(sb, pb);
                 if (MODE == 2) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tok + g * 4 + w);
                 }
                 ++km;
             } else {
-                unit<NP, POLY>(src, dst, tid);
+                unit<NP, POLY>(sb, pb);
             }
         }
     }
+    tmem_wait_st();
+    uint32_t chk[32];
+    tmem_ld32(base + 128, chk);
+    tmem_wait_ld();
+    if (chk[3] == 0x12345678u) out[0] = chk[5];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (dst[tid].x == 0x12345678u) out[0] = dst[tid].y;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 template <int MODE, int NP, int POLY>
 static void run(const char* what, const float* d_in, uint32_t* d_out, int sms) {
-    const int smem = 65536 + 32768 + 64, units = 4000;
+    const int smem = 200 * 1024, units = 4000;      // dynamic smem only forces 1 CTA / SM
     cudaFuncSetAttribute(k<MODE, NP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k<MODE, NP, POLY><<<sms, 256, smem>>>(d_in, d_out, 50);
     cudaDeviceSynchronize();
@@ -146,6 +304,26 @@ static void run(const char* what, const float* d_in, uint32_t* d_out, int sms) {
     printf("%-58s %8.3f ms  %7.1f cycles per 128-row unit per SM (MUFU floor 512)  %s\n", what, ms, cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+template <int MODE, int NP, int POLY>
+static void run16(const char* what, const float* d_in, uint32_t* d_out, int sms) {
+    const int smem = 200 * 1024, units = 4000;
+    cudaFuncSetAttribute(k16<MODE, NP, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k16<MODE, NP, POLY><<<sms, 512, smem>>>(d_in, d_out, 50);
+    cudaDeviceSynchronize();
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    cudaEventRecord(a);
+    k16<MODE, NP, POLY><<<sms, 512, smem>>>(d_in, d_out, units);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaError_t e = cudaGetLastError();
+    // 16 warps x 32 columns per loop iteration = 2 (128-row x 64-key) units
+    const double cyc = ms * 1e-3 * 1.965e9 / (2.0 * units);
+    printf("%-58s %8.3f ms  %7.1f cycles per 128-row unit per SM (MUFU floor 512)  %s\n", what, ms, cyc, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main() {
     int sms;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -156,23 +334,20 @@ int main() {
     cudaMalloc(&d_in, 4096 * 4);
     cudaMalloc(&d_out, 4);
     cudaMemcpy(d_in, h, 4096 * 4, cudaMemcpyHostToDevice);
-    run<0, 0, 0>("all MUFU", d_in, d_out, sms);
-    run<3, 16, 0>("in-warp mix 16/64 poly32", d_in, d_out, sms);
-    run<3, 24, 0>("in-warp mix 24/64 poly32", d_in, d_out, sms);
-    run<3, 32, 0>("in-warp mix 32/64 poly32", d_in, d_out, sms);
-    run<3, 24, 1>("in-warp mix 24/64 poly16x2", d_in, d_out, sms);
-    run<3, 32, 1>("in-warp mix 32/64 poly16x2", d_in, d_out, sms);
-    run<1, 64, 0>("alternate M/F(64 poly32), free", d_in, d_out, sms);
-    run<2, 64, 0>("alternate M/F(64 poly32), token", d_in, d_out, sms);
-    run<1, 48, 0>("alternate M/F(48 poly32), free", d_in, d_out, sms);
-    run<2, 48, 0>("alternate M/F(48 poly32), token", d_in, d_out, sms);
-    run<2, 56, 0>("alternate M/F(56 poly32), token", d_in, d_out, sms);
-    run<2, 40, 0>("alternate M/F(40 poly32), token", d_in, d_out, sms);
-    run<1, 64, 1>("alternate M/F(64 poly16x2), free", d_in, d_out, sms);
-    run<2, 64, 1>("alternate M/F(64 poly16x2), token", d_in, d_out, sms);
-    run<2, 56, 1>("alternate M/F(56 poly16x2), token", d_in, d_out, sms);
-    run<2, 48, 1>("alternate M/F(48 poly16x2), token", d_in, d_out, sms);
-    run<3, 64, 0>("all poly32 (FMA pipe only)", d_in, d_out, sms);
-    run<3, 64, 1>("all poly16x2 (FMA pipe only)", d_in, d_out, sms);
+    run<0, 0, 0>("8 warps: all MUFU", d_in, d_out, sms);
+    run<3, 24, 1>("8 warps: in-warp mix 24/64 poly16x2", d_in, d_out, sms);
+    run<3, 16, 2>("8 warps: in-warp mix 16/64 poly32x2", d_in, d_out, sms);
+    run<3, 24, 2>("8 warps: in-warp mix 24/64 poly32x2", d_in, d_out, sms);
+    run<3, 28, 2>("8 warps: in-warp mix 28/64 poly32x2", d_in, d_out, sms);
+    run<3, 32, 2>("8 warps: in-warp mix 32/64 poly32x2", d_in, d_out, sms);
+    run<3, 40, 2>("8 warps: in-warp mix 40/64 poly32x2", d_in, d_out, sms);
+    run<4, 32, 2>("8 warps: half-split anti-phase poly32x2", d_in, d_out, sms);
+    run<3, 64, 2>("8 warps: all poly32x2", d_in, d_out, sms);
+    run16<5, 8, 2>("16 warps x 32 cols: in-warp mix 8/32 poly32x2", d_in, d_out, sms);
+    run16<5, 12, 2>("16 warps x 32 cols: in-warp mix 12/32 poly32x2", d_in, d_out, sms);
+    run16<5, 16, 2>("16 warps x 32 cols: in-warp mix 16/32 poly32x2", d_in, d_out, sms);
+    run16<5, 20, 2>("16 warps x 32 cols: in-warp mix 20/32 poly32x2", d_in, d_out, sms);
+    run16<6, 32, 2>("16 warps x 32 cols: alternate units poly32x2", d_in, d_out, sms);
+    run16<5, 32, 2>("16 warps x 32 cols: all poly32x2", d_in, d_out, sms);
     return 0;
 }

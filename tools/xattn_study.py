@@ -69,7 +69,7 @@ def run(b, nq, nk, tensors, iters=1):
     return feat.cpu(), logits.cpu(), s.elapsed_time(e) / iters
 
 
-VARIANTS = [(2, 0), (4, 0), (5, 0)]          # (xattn_core, xattn_poly)
+VARIANTS = [(4, 0), (6, 0), (6, 4), (6, 6), (6, 7), (6, 8), (6, 9), (6, 10)]          # (xattn_core, xattn_poly | xattn6_np)
 
 
 def main():
@@ -79,7 +79,7 @@ def main():
     flops = 4.0 * nq * nk * E * 2 * b
     for core, poly in VARIANTS:
         lib.set_option("xattn_core", core)
-        lib.set_option("xattn_poly", poly)
+        lib.set_option("xattn6_np" if core == 6 else "xattn_poly", poly)
         run(b, nq, nk, t, iters=2)
         _, _, ms = run(b, nq, nk, t, iters=5)
         print(json.dumps({"shape": [b, nq, nk], "core": core, "poly": poly, "ms_per_launch": ms, "tflops_true": flops / ms / 1e9,
@@ -87,6 +87,7 @@ def main():
               flush=True)
     lib.set_option("xattn_core", 0)
     lib.set_option("xattn_poly", 0)
+    lib.set_option("xattn6_np", 8)
 
 
 if __name__ == "__main__":
