@@ -40,7 +40,8 @@ def _obj_of(src):
 
 
 def _compile(nvcc, src, verbose):
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
+    extra = os.environ.get("A3D_NVCC_EXTRA", "").split()          # study builds (e.g. -DA3D_X6_TRACE)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj_of(src), src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return src, res
 

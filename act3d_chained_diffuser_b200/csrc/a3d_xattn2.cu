@@ -349,21 +349,20 @@ __global__ void __launch_bounds__(256, 2) xattn2_kernel(const Xa2Args a) {
 
 using namespace a3d;
 
-// 0 (default): pick per launch -- the single-pass tcgen05 / TMEM core (a3d_xattn4.cu) for launches that fill the GPU,
+// 0 (default): pick per launch -- the tcgen05 / TMEM core (a3d_xattn6.cu) for launches that fill the GPU,
 // the mma.sync core (this file) for the small ones (the 1-token query stack: 16 CTAs, runs on a side stream next to a
-// ghost-point launch whose CTAs own all of an SM's tensor memory); 2 / 4 / 5 force mma.sync / tcgen05 single pass / its warp-specialised variant
+// ghost-point launch whose CTAs own all of an SM's tensor memory); 2 / 4 / 6 force mma.sync / the round-1 tcgen05 kernel (A/B reference) / a3d_xattn6.cu
 int g_xattn_core = 0;
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
-int a3d_launch_xattn5(const Xa2Args& a, dim3 grid, cudaStream_t stream);
 int a3d_launch_xattn6(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
-int g_xattn6_np = 8;    // a3d_set_option("xattn6_np", n): score pairs (of 16 per thread and unit) on the FMA-pipe polynomial
+int g_xattn6_np = 6;    // a3d_set_option("xattn6_np", n): score pairs (of 16 per thread and unit) on the FMA-pipe polynomial
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "xattn_core") == 0) {
-        A3D_REQUIRE(value == 0 || value == 2 || value == 4 || value == 5 || value == 6,
-                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 4 (tcgen05, single pass), "
-                    "5 (tcgen05, single pass, warp-specialised exponentials) or 6 (tcgen05 attention + linear layers)");
+        A3D_REQUIRE(value == 0 || value == 2 || value == 4 || value == 6,
+                    "a3d_set_option: xattn_core must be 0 (auto), 2 (mma.sync), 4 (tcgen05 attention, round-1 kernel) "
+                    "or 6 (tcgen05 attention + linear layers, FMA-pipe exponentials)");
         g_xattn_core = value;
         return A3D_OK;
     }
@@ -381,19 +380,17 @@ extern "C" int a3d_set_option(const char* name, int value) {
 }
 
 int a3d_xattn4_replays(unsigned long long* value, int reset);
-int a3d_xattn5_replays(unsigned long long* value, int reset);
 int a3d_xattn6_replays(unsigned long long* value, int reset);
 
 extern "C" int a3d_debug_counter(const char* name, int reset, unsigned long long* value_host) {
     A3D_REQUIRE(name && value_host, "a3d_debug_counter: null pointer");
     if (strcmp(name, "xattn_replays") == 0) {
-        unsigned long long v4 = 0, v5 = 0, v6 = 0;
-        if (a3d_xattn4_replays(&v4, reset) != A3D_OK || a3d_xattn5_replays(&v5, reset) != A3D_OK ||
-            a3d_xattn6_replays(&v6, reset) != A3D_OK) {
+        unsigned long long v4 = 0, v6 = 0;
+        if (a3d_xattn4_replays(&v4, reset) != A3D_OK || a3d_xattn6_replays(&v6, reset) != A3D_OK) {
             set_error("a3d_debug_counter: %s", cudaGetErrorString(cudaGetLastError()));
             return A3D_ECUDA;
         }
-        *value_host = v4 + v5 + v6;
+        *value_host = v4 + v6;
         return A3D_OK;
     }
     A3D_REQUIRE(false, "a3d_debug_counter: unknown counter '%s'", name);
@@ -441,9 +438,8 @@ extern "C" int a3d_xattn_stack(const float* x0, long x0_stride_b, long x0_stride
     a.nqv = nqv;
     a.logits = logits;
     dim3 grid((nq + Xa2::ROWS - 1) / Xa2::ROWS, batch);
-    const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 4 : 2);
+    const int core = g_xattn_core ? g_xattn_core : ((long)grid.x * grid.y >= 296 ? 6 : 2);
     if (core == 4) return a3d_launch_xattn4(a, grid, (cudaStream_t)stream, g_xattn_poly);
-    if (core == 5) return a3d_launch_xattn5(a, grid, (cudaStream_t)stream);
     if (core == 6) return a3d_launch_xattn6(a, grid, (cudaStream_t)stream, g_xattn6_np);
 #define A3D_XA2(PM)                                                                                                   \
     do {                                                                                                               \

@@ -49,6 +49,17 @@ struct Xa6Bars {
 // layers replayed in safe mode since the last reset: a3d_debug_counter("xattn_replays")
 __device__ unsigned long long g_xa6_replays = 0;
 
+#ifdef A3D_X6_TRACE
+// clock64 timeline of one CTA (study build only: A3D_NVCC_EXTRA=-DA3D_X6_TRACE; read with a3d_x6_trace_read)
+__device__ unsigned long long g_x6_trace[3][4096];
+__device__ __forceinline__ void x6_trace(bool on, int role, int& n, int tag, int idx) {
+    if (on && n < 4096) g_x6_trace[role][n++] = ((unsigned long long)tag << 56) | ((unsigned long long)(idx & 0xffff) << 40) | (clock64() & 0xffffffffffull);
+}
+#define X6_TRACE(on, role, n, tag, idx) x6_trace(on, role, n, tag, idx)
+#else
+#define X6_TRACE(on, role, n, tag, idx)
+#endif
+
 // ---- elect-predicated issue primitives: executed by all 32 lanes of the (converged) issuing warp, one lane acts
 __device__ __forceinline__ void umma_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -102,6 +113,11 @@ __device__ __forceinline__ void bulk_load_e(void* dst_smem, const void* src_gmem
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// one arrival for the whole (converged) warp: every lane's preceding writes are ordered before it by the warp barrier
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    mbar_arrive_e(bar);
+}
 __device__ __forceinline__ void bar_pair(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // 2^x for two scores on the FMA pipe, packed fp32 pairs (FADD2 / FFMA2): Cody-Waite split with the 1.5 * 2^23 trick +
@@ -150,6 +166,9 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, row0 = blockIdx.x * C::ROWS;
+#ifdef A3D_X6_TRACE
+    const unsigned long long t_start = clock64();
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -158,13 +177,13 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
         }
         for (int i = 0; i < C::NBUF; ++i) {
             mbar_init(bars->s_full + i, 1);
-            mbar_init(bars->p_full + i, 32 * C::EXP_WARPS);
+            mbar_init(bars->p_full + i, C::EXP_WARPS);      // one arrival per warp
         }
         for (int h = 0; h < C::H; ++h) mbar_init(bars->pv_done + h, 1);
-        mbar_init(&bars->q_ready, C::ROWS);
+        mbar_init(&bars->q_ready, C::ROWS / 32);
         mbar_init(&bars->o_full, 1);
-        mbar_init(&bars->verdict, C::ROWS);
-        mbar_init(&bars->a_ready, C::ROWS);
+        mbar_init(&bars->verdict, C::ROWS / 32);
+        mbar_init(&bars->a_ready, C::ROWS / 32);
         mbar_init(&bars->d_full, 1);
         bars->overflow_count = 0;
         mbar_fence_init();
@@ -174,41 +193,65 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem_raw = bars->tmem_base;
 
     const int nt = a.ntiles;
     const unsigned char* kv_sample = a.kv_base + (size_t)b * nt * C::TILE_BYTES;
 
     if (warp == C::EXP_WARPS) {
         // =========================================================== issuing warp (all lanes, warp-uniform control flow)
+        const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_raw, 0);      // provably warp-uniform: stays in uniform registers
         uint32_t gl = 0, gu = 0;              // ring items requested / consumed
         int ld_layer = 0, ld_pos = 0;         // next item to request: pos 0 = W_q, 1..nt = K/V tile pos-1, nt+1..nt+3 = W_o, W_1, W_2
         uint32_t gg = 0;                      // linear layers issued (4 per attention layer)
         uint32_t ps = 0;                      // passes over the keys (one per layer, plus one per safe-mode replay)
         uint32_t seen_overflows = 0;
+#ifdef A3D_X6_TRACE
+        const bool tr_on = (blockIdx.x == 37 && blockIdx.y == 5 && lane == 0);
+        int tr_n = 0;
+#endif
         const uint32_t ring_addr = smem_u32(ring), q_addr = smem_u32(qs);
+        // descriptors differ only in the 14-bit start-address field (bytes >> 4): offsets are plain additions
+        const uint64_t qdesc = sw32_desc(q_addr), kvdesc = sw32_desc(ring_addr);
 
-        auto load_next = [&]() {
-            if (ld_layer >= a.nlayers) return;
-            const unsigned char* src;
-            if (ld_pos >= 1 && ld_pos <= nt)
-                src = kv_sample + (size_t)ld_layer * a.kv_layer_stride + (size_t)(ld_pos - 1) * C::TILE_BYTES;
-            else
-                src = reinterpret_cast<const unsigned char*>(a.w + (size_t)ld_layer * Xa2::LAYER_W + Xa2::W_IMG +
-                                                             (size_t)(ld_pos == 0 ? 0 : ld_pos - nt) * Xa2::MAT);
-            const uint32_t s = gl % C::STAGES, use = gl / C::STAGES;
-            if (use >= 1) mbar_wait(bars->kv_empty + s, (use - 1) & 1);
-            bulk_load_e(ring + s * C::TILE_BYTES, src, C::TILE_BYTES, bars->kv_full + s);
-            ++gl;
-            if (++ld_pos == nt + 4) {
-                ld_pos = 0;
-                ++ld_layer;
+        // Ring requests are decoupled from consumption: a freed slot is re-armed as soon as its kv_empty barrier has
+        // completed (checked without blocking at every unit), so that the issuing warp never sits on the commit it
+        // has just made.  Invariant while the stream lasts: gl + pending == gu + STAGES.
+        int pending = C::STAGES;
+        auto pump = [&](bool block) {
+            while (pending > 0) {
+                if (ld_layer >= a.nlayers) {
+                    pending = 0;
+                    break;
+                }
+                const uint32_t s = gl % C::STAGES, use = gl / C::STAGES;
+                if (use >= 1) {
+                    if (block) mbar_wait(bars->kv_empty + s, (use - 1) & 1);
+                    else if (!mbar_test(bars->kv_empty + s, (use - 1) & 1)) break;
+                }
+                const unsigned char* src;
+                if (ld_pos >= 1 && ld_pos <= nt)
+                    src = kv_sample + (size_t)ld_layer * a.kv_layer_stride + (size_t)(ld_pos - 1) * C::TILE_BYTES;
+                else
+                    src = reinterpret_cast<const unsigned char*>(a.w + (size_t)ld_layer * Xa2::LAYER_W + Xa2::W_IMG +
+                                                                 (size_t)(ld_pos == 0 ? 0 : ld_pos - nt) * Xa2::MAT);
+                bulk_load_e(ring + s * C::TILE_BYTES, src, C::TILE_BYTES, bars->kv_full + s);
+                ++gl;
+                --pending;
+                if (++ld_pos == nt + 4) {
+                    ld_pos = 0;
+                    ++ld_layer;
+                }
             }
+        };
+        auto want_item = [&](uint32_t it) {          // item `it` must have been requested before its kv_full is waited on
+            if (gl <= it) pump(true);
         };
         // one linear layer: D (main, correction) = A (hi, lo; tensor memory) x W image (ring item gu)
         auto gemm_step = [&]() {
             mbar_wait(&bars->a_ready, gg & 1);
             const uint32_t s = gu % C::STAGES;
+            want_item(gu);
             mbar_wait(bars->kv_full + s, (gu / C::STAGES) & 1);
             tc_fence_after();
             const uint32_t w_addr = ring_addr + s * C::TILE_BYTES;
@@ -223,52 +266,83 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
             tc_commit_e(bars->kv_empty + s);
             ++gu;
             ++gg;
-            load_next();
+            ++pending;
+            pump(false);
         };
 
-        for (int i = 0; i < C::STAGES; ++i) load_next();
+        pump(true);
         for (int layer = 0; layer < a.nlayers; ++layer) {
             gemm_step();                                    // q projection
             mbar_wait(&bars->q_ready, layer & 1);           // Q tiles of this layer are in shared memory
             tc_fence_after();
             for (int attempt = 0; attempt < 2; ++attempt, ++ps) {
-                const uint32_t item0 = gu;                  // ring item of tile 0 of this pass
-                const uint32_t ubase = ps * nt * H;
                 // Software pipeline over units (tile t, head h): S(u) is issued two units ahead of the PV product that
                 // consumes P(u-2); S(u) may overwrite the buffer of unit u-3 without a wait because tcgen05.mma
-                // instructions execute in issue order.
-                for (int u = 0; u < nt * H + 2; ++u) {
-                    if (u < nt * H) {
-                        const int t = u / H, h = u % H;
-                        const uint32_t U = ubase + u, i = U % C::NBUF;
-                        const uint32_t it = item0 + t, s = it % C::STAGES;
-                        if (h == 0) {
-                            mbar_wait(bars->kv_full + s, (it / C::STAGES) & 1);
-                            tc_fence_after();
-                        }
-                        const uint32_t k_addr = ring_addr + s * C::TILE_BYTES;
-                        umma_ss_e(tmem + C::S_COL + 64 * i, sw32_desc(q_addr + h * 4096), sw32_desc(k_addr + h * 2048), kIdescS, 0);
-                        tc_commit_e(bars->s_full + i);
-                    }
-                    if (u >= 2) {
-                        const int v = u - 2, t = v / H, h = v % H;
-                        const uint32_t V = ubase + v, j = V % C::NBUF, k = V / C::NBUF;
-                        const uint32_t it = item0 + t, s = it % C::STAGES;
-                        mbar_wait(bars->p_full + j, k & 1);
-                        tc_fence_after();
-                        const uint32_t v_addr = ring_addr + s * C::TILE_BYTES + H * 2048 + h * 2048;
-                        const uint32_t pb = tmem + C::S_COL + 64 * j;
-                        // P of keys 0..31 sits in columns 0..15 of the buffer, P of keys 32..63 in columns 32..47
+                // instructions execute in issue order.  The loop is unrolled over the heads and every index (S / P
+                // buffer, ring slot, barrier parity) is carried incrementally: this warp's instruction count per
+                // unit bounds the whole kernel (a division-based version of this loop cost ~300 instructions and
+                // ~1000 cycles per unit, more than the exponentials of the unit).
+                const uint32_t ubase = ps * nt * H;
+                uint32_t bi = ubase % C::NBUF;                              // S buffer of the next S product
+                uint32_t pj = bi, pk = (ubase / C::NBUF) & 1;               // P buffer / p_full parity of the next PV product
+                uint32_t ts = gu % C::STAGES, tp = (gu / C::STAGES) & 1;    // ring slot / kv_full parity of tile t
+                uint32_t vs = ts;                                           // ring slot of tile t - 1
+                uint32_t item = gu;
+                for (int t = 0; t <= nt; ++t) {                             // the extra round drains the last two PV products
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_ts_e(tmem + C::O_COL + 16 * h, pb + 8 * (ks & 1) + 32 * (ks >> 1), sw32_desc(v_addr + ks * 512), kIdescPV,
-                                      (t > 0 || ks > 0) ? 1u : 0u);
-                        tc_commit_e(bars->pv_done + h);
-                        if (h == H - 1) {
-                            tc_commit_e(bars->kv_empty + s);
-                            ++gu;
-                            load_next();
+                    for (int h = 0; h < H; ++h) {
+                        if (pending) pump(false);
+                        if (t < nt) {
+                            if (h == 0) {
+                                want_item(item);
+                                mbar_wait(bars->kv_full + ts, tp);
+                                tc_fence_after();
+                            }
+                            umma_ss_e(tmem + C::S_COL + 64 * bi, qdesc + h * (4096 >> 4), kvdesc + ts * (C::TILE_BYTES >> 4) + h * (2048 >> 4),
+                                      kIdescS, 0);
+                            tc_commit_e(bars->s_full + bi);
+                            X6_TRACE(tr_on, 0, tr_n, 1, 4 * t + h);
+                            bi = (bi == C::NBUF - 1) ? 0 : bi + 1;
                         }
+                        // PV product of unit u - 2: head hv of tile t (h >= 2) or of tile t - 1 (h < 2)
+                        constexpr int kHvOf[4] = {2, 3, 0, 1};
+                        const int hv = kHvOf[h];
+                        const bool has_v = (h >= 2) ? (t < nt) : (t >= 1);
+                        if (has_v) {
+                            const uint32_t slot = (h >= 2) ? ts : vs;
+                            const uint32_t first = (h >= 2) ? (t == 0) : (t == 1);     // first tile of the pass: overwrite O_h
+                            X6_TRACE(tr_on, 0, tr_n, 2, 4 * t + h - 2);
+                            mbar_wait(bars->p_full + pj, pk);
+                            tc_fence_after();
+                            X6_TRACE(tr_on, 0, tr_n, 3, 4 * t + h - 2);
+                            const uint64_t vd = kvdesc + slot * (C::TILE_BYTES >> 4) + ((H * 2048 + hv * 2048) >> 4);
+                            const uint32_t pb = tmem + C::S_COL + 64 * pj;
+                            // P of keys 0..31 sits in columns 0..15 of the buffer, P of keys 32..63 in columns 32..47
+                            umma_ts_e(tmem + C::O_COL + 16 * hv, pb, vd, kIdescPV, first ? 0u : 1u);
+                            umma_ts_e(tmem + C::O_COL + 16 * hv, pb + 8, vd + (512 >> 4), kIdescPV, 1u);
+                            umma_ts_e(tmem + C::O_COL + 16 * hv, pb + 32, vd + (1024 >> 4), kIdescPV, 1u);
+                            umma_ts_e(tmem + C::O_COL + 16 * hv, pb + 40, vd + (1536 >> 4), kIdescPV, 1u);
+                            tc_commit_e(bars->pv_done + hv);
+                            if (hv == H - 1) {
+                                tc_commit_e(bars->kv_empty + slot);
+                                ++gu;
+                                ++pending;
+                            }
+                            if (pj == C::NBUF - 1) {
+                                pj = 0;
+                                pk ^= 1;
+                            } else {
+                                ++pj;
+                            }
+                        }
+                    }
+                    vs = ts;
+                    ++item;
+                    if (ts == C::STAGES - 1) {
+                        ts = 0;
+                        tp ^= 1;
+                    } else {
+                        ++ts;
                     }
                 }
                 tc_commit_e(&bars->o_full);
@@ -291,7 +365,8 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                 }
                 ld_layer = layer;
                 ld_pos = 1;
-                for (int i = 0; i < C::STAGES; ++i) load_next();
+                pending = C::STAGES;
+                pump(true);
                 if (lane == 0) atomicAdd(&g_xa6_replays, 1ull);
             }
             gemm_step();                                    // out projection
@@ -300,6 +375,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
         }
     } else {
         // =========================================================== exponential warps; warps 0-3 also own the rows
+        const uint32_t tmem = tmem_raw;
         const int wq = warp & 3, half = warp >> 2;
         const int lrow = wq * 32 + lane;                              // row inside the tile == TMEM lane
         const int row = row0 + lrow;
@@ -308,6 +384,11 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
         uint32_t gg = 0;                                              // linear layers consumed (row owners)
         uint32_t ps = 0, seen_overflows = 0;
         uint32_t xch = 0;                                             // pair-exchange counter (mailbox parity)
+#ifdef A3D_X6_TRACE
+        const bool tr_on = (blockIdx.x == 37 && blockIdx.y == 5 && lane == 0 && wq == 0);
+        int tr_n = 0, tr_n2 = 3000;
+        const int tr_role = 1 + half;
+#endif
 
         auto xchunk = [&](int c) -> float4* {                         // 16-byte chunk c (0..15) of this thread's row
             return reinterpret_cast<float4*>(xpark + lrow * 64) + (c ^ (lrow & 15));
@@ -323,7 +404,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
         auto a_done = [&]() {
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&bars->a_ready);
+            mbar_arrive_warp(&bars->a_ready);
         };
         auto d_wait = [&]() {
             mbar_wait(&bars->d_full, gg & 1);
@@ -428,9 +509,11 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
 
         for (int layer = 0; layer < a.nlayers; ++layer) {
             const float* vv = a.v + (size_t)layer * Xa2::LAYER_V;
+            X6_TRACE(tr_on, 1, tr_n2, 10, layer);
             if (owner) {
                 // ------------------------------------------------------------ Q = rotary(x Wq^T + bq) -> smem (SW32 tiles per head)
                 d_wait();
+                X6_TRACE(tr_on, 1, tr_n2, 11, layer);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float y[16], bb[16];
@@ -467,7 +550,8 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                 for (int h = 0; h < H; ++h) *reinterpret_cast<__half*>(q_pad + h * 4096) = __float2half_rn(0.f);
                 fence_async_smem();                 // generic-proxy writes of Q -> visible to the tensor-core (async) proxy
                 tc_fence_before();
-                mbar_arrive(&bars->q_ready);
+                mbar_arrive_warp(&bars->q_ready);
+                X6_TRACE(tr_on, 1, tr_n2, 12, layer);
             }
 
             // ---------------------------------------------------------------- softmax over the keys (all 8 warps)
@@ -540,7 +624,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                         tmem_st16(sb, p);
                         tmem_wait_st();
                         tc_fence_before();
-                        mbar_arrive(bars->p_full + i);
+                        mbar_arrive_warp(bars->p_full + i);
                     }
                 }
             };
@@ -553,33 +637,60 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                     explicit_tiles(0, nt);             // safe mode: every unit tracks the exact running maximum
                 } else {
                     explicit_tiles(0, 1);              // the first tile fixes the shift of every row
-                    int pend = -1;                     // buffer whose P hand-over is still owed (its tcgen05.st in flight)
-                    for (int t = 1; t < nt; ++t) {
+                    X6_TRACE(tr_on, 1, tr_n2, 13, layer);
+                    // ---- remaining tiles, software-pipelined inside the warp in chunks of 16 scores: chunk B of a unit is
+                    //      in flight while chunk A is exponentiated, chunk A of the NEXT unit while chunk B is; the probe of
+                    //      the next unit's s_full barrier is issued before chunk A's arithmetic and consumed after it, and
+                    //      the hand-over of P(u-1) (tcgen05.wait::st + arrive) sits behind chunk A as well -- nothing with a
+                    //      latency is waited on right after it was started.
+                    if (nt > 1) {
+                        constexpr int NPA = (NP + 1) / 2, NPB = NP / 2;       // polynomial pairs of chunk A / chunk B
+                        uint32_t ca[16], cb[16], p[16];
+                        uint32_t U = (ps * nt + 1) * H;                         // current unit
+                        uint32_t i = U % C::NBUF, k = (U / C::NBUF) & 1;
+                        const uint32_t s0 = lane_addr + C::S_COL + 32 * half;
+                        mbar_wait(bars->s_full + i, k);
+                        tc_fence_after();
+                        tmem_ld16(s0 + 64 * i, ca);
+                        tmem_wait_ld();
+                        int pend = -1;                 // buffer whose P hand-over is still owed (its tcgen05.st in flight)
+                        const int units = (nt - 1) * H;
+                        for (int u = 0; u < units; ++u) {
+                            const uint32_t sb = s0 + 64 * i;
+                            const uint32_t in = (i == C::NBUF - 1) ? 0 : i + 1, kn = (i == C::NBUF - 1) ? (k ^ 1) : k;
+                            const bool has_next = u + 1 < units;
+                            X6_TRACE(tr_on, tr_role, tr_n, 4, u + 4);
+                            tmem_ld16(sb + 16, cb);
+                            const bool ready = has_next ? mbar_test(bars->s_full + in, kn) : true;
 #pragma unroll
-                        for (int h = 0; h < H; ++h) {
-                            const uint32_t U = (ps * nt + t) * H + h, i = U % C::NBUF, k = U / C::NBUF;
-                            const uint32_t sb = lane_addr + C::S_COL + 64 * i + 32 * half;
-                            uint32_t r[32], p[16];
-                            mbar_wait(bars->s_full + i, k & 1);
-                            tc_fence_after();
-                            tmem_ld32(sb, r);
+                            for (int c = 0; c < 8; ++c)
+                                p[c] = (c < NPA) ? exp2_poly_pair(ca[2 * c], ca[2 * c + 1]) : exp2_mufu_pair(ca[2 * c], ca[2 * c + 1]);
                             if (pend >= 0) {                   // P of the previous unit has landed by now
                                 tmem_wait_st();
                                 tc_fence_before();
-                                mbar_arrive(bars->p_full + pend);
+                                mbar_arrive_warp(bars->p_full + pend);
                             }
                             tmem_wait_ld();
+                            X6_TRACE(tr_on, tr_role, tr_n, 5, u + 4);
+                            if (has_next) {
+                                if (!ready) mbar_wait(bars->s_full + in, kn);
+                                tc_fence_after();
+                                tmem_ld16(s0 + 64 * in, ca);
+                            }
+                            X6_TRACE(tr_on, tr_role, tr_n, 6, u + 4);
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                p[c] = (c < NP) ? exp2_poly_pair(r[2 * c], r[2 * c + 1]) : exp2_mufu_pair(r[2 * c], r[2 * c + 1]);
+                            for (int c = 0; c < 8; ++c)
+                                p[8 + c] = (c < NPB) ? exp2_poly_pair(cb[2 * c], cb[2 * c + 1]) : exp2_mufu_pair(cb[2 * c], cb[2 * c + 1]);
                             tmem_st16(sb, p);
+                            X6_TRACE(tr_on, tr_role, tr_n, 7, u + 4);
                             pend = (int)i;
+                            if (has_next) tmem_wait_ld();
+                            i = in;
+                            k = kn;
                         }
-                    }
-                    if (pend >= 0) {
                         tmem_wait_st();
                         tc_fence_before();
-                        mbar_arrive(bars->p_full + pend);
+                        mbar_arrive_warp(bars->p_full + pend);
                     }
                 }
                 if (owner) {
@@ -588,6 +699,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                     for (int h = 0; h < H; ++h) *reinterpret_cast<__half*>(q_pad + h * 4096) = __float2half_rn(0.f);
                     fence_async_smem();
                 }
+                X6_TRACE(tr_on, 1, tr_n2, 14, layer);
                 if (attempt == 1) continue;            // (the loop increment counts the replay pass)
                 // verdict on the fast pass: a non-finite denominator anywhere in the CTA -> replay the layer in safe mode
                 if (owner) {
@@ -604,7 +716,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                     tc_fence_before();
                     if (bad) atomicAdd(&bars->overflow_count, 1u);
                     __threadfence_block();
-                    mbar_arrive(&bars->verdict);
+                    mbar_arrive_warp(&bars->verdict);
                 }
                 mbar_wait(&bars->verdict, layer & 1);
                 const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&bars->overflow_count);
@@ -615,6 +727,7 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                     break;
                 }
             }
+            X6_TRACE(tr_on, 1, tr_n2, 15, layer);
             if (!owner) continue;
 
             // ---------------------------------------------------------------- O / l -> A operand of the out projection
@@ -635,12 +748,16 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                 put_a16(h, v);
             }
             a_done();
+            X6_TRACE(tr_on, 1, tr_n2, 16, layer);
             // ---------------------------------------------------------------- x = LN(x + O Wo^T + bo)
             d_wait();
+            X6_TRACE(tr_on, 1, tr_n2, 17, layer);
             residual_ln(vv + Xa2::B_O, vv + Xa2::G_1, vv + Xa2::BE_1);
             row_to_a();
+            X6_TRACE(tr_on, 1, tr_n2, 18, layer);
             // ---------------------------------------------------------------- hid = relu(x W1^T + b1)
             d_wait();
+            X6_TRACE(tr_on, 1, tr_n2, 19, layer);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float y[16], bb[16];
@@ -651,11 +768,14 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
                 put_a16(j, y);
             }
             a_done();
+            X6_TRACE(tr_on, 1, tr_n2, 20, layer);
             // ---------------------------------------------------------------- x = LN(x + hid W2^T + b2)
             d_wait();
+            X6_TRACE(tr_on, 1, tr_n2, 21, layer);
             residual_ln(vv + Xa2::B_2, vv + Xa2::G_2, vv + Xa2::BE_2);
             const bool last = (layer == a.nlayers - 1);
             if (!last) row_to_a();                      // A operand of the next layer's q projection
+            X6_TRACE(tr_on, 1, tr_n2, 22, layer);
             // ---- outputs of this layer
             if (row < a.nq) {
                 if (a.feat_out && (a.feat_all || last)) {
@@ -682,10 +802,14 @@ __global__ void __launch_bounds__(Xa6::THREADS, 2) xattn6_kernel(const Xa2Args a
         }
     }
     // ---- teardown
+#ifdef A3D_X6_TRACE
+    if (blockIdx.x == 37 && blockIdx.y == 5 && threadIdx.x == 0) g_x6_trace[1][4000] = (23ull << 56) | (clock64() & 0xffffffffffull);
+    if (blockIdx.x == 37 && blockIdx.y == 5 && threadIdx.x == 0) g_x6_trace[1][4001] = (9ull << 56) | (t_start & 0xffffffffffull);
+#endif
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == C::EXP_WARPS) tmem_dealloc(tmem, C::TMEM_COLS);
+    if (warp == C::EXP_WARPS) tmem_dealloc(tmem_raw, C::TMEM_COLS);
 }
 
 }  // namespace a3d
@@ -698,6 +822,12 @@ int a3d_xattn6_replays(unsigned long long* value, int reset) {
     if (reset && cudaMemcpyToSymbol(g_xa6_replays, &zero, sizeof(zero)) != cudaSuccess) return A3D_ECUDA;
     return A3D_OK;
 }
+
+#ifdef A3D_X6_TRACE
+extern "C" int a3d_x6_trace_read(unsigned long long* host) {
+    return cudaMemcpyFromSymbol(host, g_x6_trace, sizeof(g_x6_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 template <int NP>
 static int launch_np(const Xa2Args& a, dim3 grid, cudaStream_t stream) {

@@ -38,12 +38,13 @@ extern "C" {
 const char* a3d_last_error(void);
 int a3d_abi_version(void);
 /* Process-wide tuning knobs (not part of the numerical contract):
- *   "xattn_core": attention core of a3d_xattn_stack: 0 (default) = per launch: the single-pass tcgen05 / TMEM kernel
- *                 for launches of >= 296 CTAs, the mma.sync kernel for small ones; 2 = mma.sync (HMMA) kernel,
- *                 4 = tcgen05 / TMEM single-pass kernel, 5 = the single-pass kernel
- *                 with warp-specialised exponentials (MUFU warps + FMA-polynomial warps, setmaxnreg; study).
- *   "xattn_poly": how many of every 8 softmax exponentials of a3d_xattn_stack are evaluated with the
- *                 FMA-pipe polynomial instead of the MUFU unit: 0 (default, fastest measured), 2, 3 or 4. */
+ *   "xattn_core": attention core of a3d_xattn_stack: 0 (default) = per launch: the tcgen05 / TMEM kernel (attention and
+ *                 linear layers on tcgen05.mma, part of the exponentials on the FMA pipe; csrc/a3d_xattn6.cu) for launches
+ *                 of >= 296 CTAs, the mma.sync kernel for small ones; 2 = mma.sync (HMMA) kernel, 4 = the round-1
+ *                 tcgen05 kernel (attention only on tcgen05; kept as A/B reference), 6 = a3d_xattn6.cu.
+ *   "xattn6_np":  how many of the 16 score pairs a thread of a3d_xattn6.cu exponentiates per unit go through the FMA-pipe
+ *                 polynomial instead of the MUFU unit: 0, 4, 6 (default, fastest measured), 7, 8, 9, 10.
+ *   "xattn_poly": the same knob of the round-1 kernels (of every 8 scores): 0 (default), 2, 3 or 4. */
 int a3d_set_option(const char* name, int value);
 /* Test / diagnostics counters kept on the current device; the call SYNCHRONISES the device (it is not part of the
  * hot path).  "xattn_replays": attention layers that a CTA of a3d_xattn_stack's tcgen05 kernels replayed in safe mode

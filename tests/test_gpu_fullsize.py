@@ -59,9 +59,9 @@ def test_act3d_c2_ghost_points_are_scored_independently(ng):
         lib.set_option("xattn_core", 0)
         return out
 
-    full = run(base, core=4)                        # same core for the three runs (auto would pick mma.sync for the subset)
-    shuffled = run([p[:, perm] for p in base], core=4)
-    subset = run([p[:, sub] for p in base], core=4)
+    full = run(base, core=6)                        # same core for the three runs (auto would pick mma.sync for the subset)
+    shuffled = run([p[:, perm] for p in base], core=6)
+    subset = run([p[:, sub] for p in base], core=6)
     legacy = run(base, core=2)
     lo_d, hi_d = lo.cuda(), hi.cuda()
     for lvl in range(3):

@@ -13,7 +13,9 @@ sys.path.insert(0, ROOT)
 from act3d_chained_diffuser_b200 import lib  # noqa: E402
 from oracle.attention import relative_cross_attn_stack  # noqa: E402
 from oracle.rope import rope3d_table  # noqa: E402
-from tools.xattn_study import E, H, VARIANTS, run, setup  # noqa: E402
+from tools.xattn_study import E, H, run, setup  # noqa: E402
+
+VARIANTS = [(2, 0), (4, 0), (6, 0), (6, 6), (6, 10)]          # (xattn_core, xattn_poly | xattn6_np)
 
 
 def main():
@@ -30,7 +32,7 @@ def main():
         rel = lambda a, r: ((a.double() - r).norm() / r.norm()).item()
         for core, poly in VARIANTS:
             lib.set_option("xattn_core", core)
-            lib.set_option("xattn_poly", poly)
+            lib.set_option("xattn6_np" if core == 6 else "xattn_poly", poly)
             feat, logits, _ = run(b, nq, nk, t)
             print(json.dumps({"case": tag, "core": core, "poly": poly, "feat_rel_l2": rel(feat[0], want64),
                               "logit_rel_l2": rel(logits, lg64),
@@ -38,6 +40,7 @@ def main():
                   flush=True)
     lib.set_option("xattn_core", 0)
     lib.set_option("xattn_poly", 0)
+    lib.set_option("xattn6_np", 6)
 
 
 if __name__ == "__main__":

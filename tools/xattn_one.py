@@ -13,6 +13,8 @@ from tools.xattn_study import run, setup  # noqa: E402
 lib.load()
 if os.environ.get("A3D_XATTN_POLY"):
     lib.set_option("xattn_poly", int(os.environ["A3D_XATTN_POLY"]))
+if os.environ.get("A3D_XATTN6_NP"):
+    lib.set_option("xattn6_np", int(os.environ["A3D_XATTN6_NP"]))
 b, nq, nk = 16, 16384, 4150
 t = setup(b, nq, nk, 1.0)
 _, _, ms = run(b, nq, nk, t, iters=int(sys.argv[1]) if len(sys.argv) > 1 else 4)

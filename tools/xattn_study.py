@@ -69,10 +69,33 @@ def run(b, nq, nk, tensors, iters=1):
     return feat.cpu(), logits.cpu(), s.elapsed_time(e) / iters
 
 
-VARIANTS = [(4, 0), (6, 0), (6, 4), (6, 6), (6, 7), (6, 8), (6, 9), (6, 10)]          # (xattn_core, xattn_poly | xattn6_np)
+VARIANTS = [(4, 0), (6, 0), (6, 4), (6, 6), (6, 8)]          # (xattn_core, xattn_poly | xattn6_np)
+
+
+def decomp(core, np_):
+    """Marginal cost per key tile and fixed cost per launch: time the C2 query shape at several key counts."""
+    lib.load()
+    lib.set_option("xattn_core", core)
+    if core == 6:
+        lib.set_option("xattn6_np", np_)
+    b, nq = 16, 16384
+    pts = []
+    for nk in (64 * 8, 64 * 16, 64 * 32, 64 * 65):
+        t = setup(b, nq, nk, 1.0)
+        run(b, nq, nk, t, iters=2)
+        _, _, ms = run(b, nq, nk, t, iters=5)
+        pts.append((nk // 64, ms))
+    (t0, m0), (t1, m1) = pts[0], pts[-1]
+    slope = (m1 - m0) / (t1 - t0)
+    print(json.dumps({"core": core, "np": np_, "ms_by_tiles": pts, "ms_per_tile": slope, "fixed_ms": m0 - slope * t0}), flush=True)
+    lib.set_option("xattn_core", 0)
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "decomp":
+        for core, np_ in ((4, 0), (6, 0), (6, 6)):
+            decomp(core, np_)
+        return
     lib.load()
     b, nq, nk = 16, 16384, 4150
     t = setup(b, nq, nk, 1.0)
@@ -87,7 +110,7 @@ def main():
               flush=True)
     lib.set_option("xattn_core", 0)
     lib.set_option("xattn_poly", 0)
-    lib.set_option("xattn6_np", 8)
+    lib.set_option("xattn6_np", 6)
 
 
 if __name__ == "__main__":
