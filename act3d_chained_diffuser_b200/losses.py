@@ -50,6 +50,8 @@ def keypose_loss(pred, gt_action, position_loss_coeff=1.0, position_offset_loss_
             losses[f"position_ce_level{i}"] = ce.mean() * position_loss_coeff / len(levels)
     if pred.get("fine_ghost_pcd_offsets") is not None:                                 # main_keypose.py:405-417
         with_off = pred["ghost_pcd_pyramid"][-1] + pred["fine_ghost_pcd_offsets"]
+        if pred["ghost_pcd_pyramid"][-1].shape[-1] != pred["ghost_pcd_pyramid"][0].shape[-1]:
+            with_off = with_off[:, :, -(pred["ghost_pcd_pyramid"][-1].shape[-1] // len(levels)):]
         losses["position_offset"] = (F.mse_loss(with_off, gt_pos.unsqueeze(-1).expand_as(with_off))
                                      * (position_offset_loss_coeff * position_loss_coeff))
     pred["position"] = pred["position"].detach()                                       # main_keypose.py:419-424
@@ -63,5 +65,11 @@ def keypose_loss(pred, gt_action, position_loss_coeff=1.0, position_offset_loss_
             losses["rotation"] = (sel * a + (1 - sel) * b).mean() * rotation_loss_coeff
         else:
             losses["rotation"] = F.mse_loss(rot, gt_quat) * rotation_loss_coeff
+    else:
+        # the reference's LossAndMetrics supervises quaternions only (main_keypose.py:426-444 indexes gt_action[:, 3:7]
+        # against pred["rotation"] and fails on a (B, 3, 3) matrix); training without rotation supervision would be silent
+        raise NotImplementedError("keypose_loss: rotation supervision is implemented for quaternion heads "
+                                  "(rotation_parametrization='quat_from_query' / 'quat_from_top_ghost'), "
+                                  f"got a rotation of shape {tuple(rot.shape)}")
     losses["gripper"] = F.mse_loss(pred["gripper"], gt_action[:, 7:8]) * gripper_loss_coeff
     return losses

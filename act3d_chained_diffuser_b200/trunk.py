@@ -200,9 +200,14 @@ class EvalTrunk:
         if self._plan is not None and self._fused_ok and x.is_cuda:
             try:
                 return self._run_fpn(fpn, self._run_resnet(self._plan, x), set(needed), defer_bias)
+            except torch.cuda.OutOfMemoryError:
+                raise                     # transient: must not demote the trunk to the slow path for the process lifetime
             except RuntimeError as exc:   # cuDNN fused entry points unavailable for this build / shape
-                if "libact3d_b200" in str(exc) or "a3d_" in str(exc):
-                    raise
+                msg = str(exc)
+                if any(k in msg for k in ("libact3d_b200", "a3d_", "CUDA error", "out of memory", "device-side assert")):
+                    raise                 # our own kernels / device faults are never swallowed
+                import warnings
+                warnings.warn("fused cuDNN conv+bias+ReLU path unavailable, using the unfused trunk from now on: " + msg)
                 self._fused_ok = False
         if x.shape[1] == 4:
             x = x[:, :3].contiguous(memory_format=torch.channels_last)

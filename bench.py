@@ -32,6 +32,10 @@ TRAIN_WORKLOAD = dict(name="act3d_C4_train", batch=16, ncam=4, ghost_total=1000,
 PLANNER_WORKLOAD = dict(name="planner_C3", batch=32, ncam=4, hw=256, length=50, steps=100, embed=120, heads=8)
 
 
+CONFIG_WORKLOAD = ("Act3D forward C2: 4 views 256x256 RGB-D, 16384 ghost pts/level x 3 levels, batch 16/GPU, "
+                   "E=60 H=4, use_instruction=1, backbone=resnet50 (random init, cuDNN)")
+
+
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
@@ -160,14 +164,66 @@ def run_planner(rank, world, device, iters=3):
         fn()
     e.record()
     torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / iters
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = t.item()
+    from act3d_chained_diffuser_b200.sharding import max_over_ranks
+    ms = max_over_ranks(s.elapsed_time(e) / iters, device)
     return {"metric": "denoise-steps/s", "value": round(w["batch"] * w["steps"] * world / (ms * 1e-3), 1),
             "ms_per_trajectory_batch": round(ms, 3),
             "workload": "ChainedDiffuser compute_trajectory C3: batch 32/GPU, 50 waypoints, 100 DDPM steps, 4 views, E=120 H=8"}
+
+
+def _ddp(model, local, world):
+    """Stock DistributedDataParallel as the reference wraps its models (engine.py:121-124: find_unused_parameters=True,
+    broadcast_buffers=False) plus static_graph / gradient_as_bucket_view: the set of unused parameters (6 FPN tensors,
+    SURVEY App. B.2) is the same every step, so DDP records it once instead of walking the autograd graph per step."""
+    if world == 1:
+        return model
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                     find_unused_parameters=True, static_graph=True,
+                                                     gradient_as_bucket_view=True)
+
+
+def _ddp_gradient_check(model, net, step_loss, reseed, world, device):
+    """Once per run under N > 1: the gradients DDP leaves on every rank equal the mean over ranks of the gradients each
+    rank computes alone on its own shard (NCCL all-reduce of gradients only), and are identical on all ranks."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    reseed()
+    model.zero_grad(set_to_none=True)
+    step_loss(model).backward()                                  # local gradients, no DDP hooks
+    local = [torch.zeros_like(p) if p.grad is None else p.grad.detach().clone() for p in params]
+    for g in local:
+        torch.distributed.all_reduce(g)
+        g /= world
+    reseed()
+    model.zero_grad(set_to_none=True)
+    step_loss(net).backward()                                    # through DDP: bucketed all-reduce
+    worst = 0.0
+    for p, want in zip(params, local):
+        got = torch.zeros_like(p) if p.grad is None else p.grad.detach()
+        lo, hi = got.clone(), got.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "DDP left different gradients on different ranks"
+        denom = want.abs().max().item() + 1e-12
+        worst = max(worst, (got - want).abs().max().item() / denom)
+    assert worst <= 1e-4, f"DDP gradients differ from the all-reduced mean of the per-rank gradients: {worst:.2e}"
+    model.zero_grad(set_to_none=True)
+    return worst
+
+
+def _time_train(step, world, device, iters, warmup):
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    from act3d_chained_diffuser_b200.sharding import max_over_ranks
+    return max_over_ranks(s.elapsed_time(e) / iters, device), float(loss.detach())
 
 
 def run_train(rank, world, device, local, iters=6, warmup=3):
@@ -182,43 +238,74 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
                   gripper_loc_bounds=synth.BOUNDS, num_ghost_points=w["ghost_total"], num_sampling_level=3,
                   use_instruction=True).to(device).train()
     model.seed_ghost_sampler(99 + rank)
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
-                                                        find_unused_parameters=True)
+    net = _ddp(model, local, world)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     rgb, pcd, instr, grip = [t.to(device) for t in act3d_inputs(w["batch"], w["ncam"], seed=300 + rank)]
     gt = grip.clone()
     gt[:, :3] += 0.02
 
+    def step_loss(m):
+        out = m(rgb, pcd, instr, grip, gt_action=gt)
+        return sum(keypose_loss(out, gt).values())
+
     def step():
-        out = net(rgb, pcd, instr, grip, gt_action=gt)
-        loss = sum(keypose_loss(out, gt).values())
+        loss = step_loss(net)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
+    check = None
     if world > 1:
-        torch.distributed.barrier()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(iters):
-        loss = step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / iters
+        check = _ddp_gradient_check(model, net, step_loss, lambda: model.seed_ghost_sampler(99 + rank), world, device)
+    ms, loss = _time_train(step, world, device, iters, warmup)
+    out = {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only, static graph)",
+           "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
+                       "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
+    if check is not None:
+        out["ddp_gradient_check_max_rel"] = float(f"{check:.2e}")
+    return out
+
+
+def run_train_planner(rank, world, device, local, iters=6, warmup=3):
+    """Secondary figure: ChainedDiffuser training step (main_trajectory.py:177-199: noise one random timestep, one
+    denoiser call, L1 losses, backward, AdamW) under stock DDP: the 17 MB gradient all-reduce of SURVEY 8(e)."""
+    w = PLANNER_WORKLOAD
+    torch.manual_seed(0)
+    model = build_planner().to(device).train()
+    net = _ddp(model, local, world)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    mask, rgb, pcd, instr, cur, goal = [t.to(device) for t in planner_inputs(w["batch"], w["ncam"], w["length"], 500 + rank)]
+    g = torch.Generator().manual_seed(700 + rank)
+    alpha = torch.linspace(0, 1, w["length"]).view(1, -1, 1)
+    gt_traj = (cur.cpu().unsqueeze(1) * (1 - alpha) + goal.cpu().unsqueeze(1) * alpha + 0.01 * torch.randn(w["batch"], w["length"], 7, generator=g))
+    gt_traj[..., 3:] = gt_traj[..., 3:] / gt_traj[..., 3:].norm(dim=-1, keepdim=True)
+    gt_traj = gt_traj.to(device)
+
+    def step_loss(m):
+        return m(gt_traj, mask, rgb, pcd, instr, cur, goal)
+
+    def step():
+        loss = step_loss(net)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    check = None
     if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = t.item()
-    return {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
-            "final_loss": round(float(loss.detach()), 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
-            "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
-                        "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
+        check = _ddp_gradient_check(model, net, step_loss, lambda: torch.manual_seed(1234 + rank), world, device)
+    ms, loss = _time_train(step, world, device, iters, warmup)
+    nbytes = sum(p.numel() * 4 for p in model.parameters() if p.requires_grad)
+    out = {"metric": "train trajectories/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only, static graph)",
+           "gradient_bytes": int(nbytes),
+           "workload": f"ChainedDiffuser training step: {w['batch']} trajectories/GPU, {w['length']} waypoints, 4 views 256x256, "
+                       "E=120 H=8, frozen ResNet-50, fp32, AdamW"}
+    if check is not None:
+        out["ddp_gradient_check_max_rel"] = float(f"{check:.2e}")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -232,9 +319,9 @@ def run_ours(args, rank, world, device, local=0):
     dev_in = [t.to(device) for t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)          # > 126 MB L2
 
-    def step_resident():
+    def step_resident(inputs=None):
         with torch.no_grad():
-            return model(*dev_in)
+            return model(*(inputs or dev_in))
 
     def step_e2e():
         with torch.no_grad():
@@ -272,10 +359,22 @@ def run_ours(args, rank, world, device, local=0):
     clk = clocks.stop()
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
-    if world > 1:
-        t = torch.tensor([ms_res, ms_e2e], device=device, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_res, ms_e2e = t.tolist()
+    # ---- strong scaling: the SAME 16 keyframes split over the N ranks (16 / N per GPU), no data-path collective
+    strong = None
+    if world > 1 and w["batch"] % world == 0:
+        from act3d_chained_diffuser_b200.sharding import shard_bounds
+        lo, hi = shard_bounds(w["batch"], rank, world)
+        per = hi - lo
+        shard = [t[lo:hi].contiguous() for t in dev_in]
+        k_strong = max(5, args.steps // 2)
+        from act3d_chained_diffuser_b200.sharding import max_over_ranks
+        ms_strong = max_over_ranks(timed(lambda: step_resident(shard), k_strong, 3)[0], device)
+        strong = {"metric": "keyframes/s", "scaling": "strong", "value": round(w["batch"] * k_strong / (ms_strong * 1e-3), 1),
+                  "ms_per_step": round(ms_strong / k_strong, 3), "keyframes_total": w["batch"], "keyframes_per_gpu": per,
+                  "note": "16 keyframes in total, sharded over the ranks; compare with the N=1 value of the same line format"}
+
+    from act3d_chained_diffuser_b200.sharding import max_over_ranks
+    ms_res, ms_e2e = max_over_ranks(ms_res, device), max_over_ranks(ms_e2e, device)
 
     # ---- roofline of the dominant kernel: fused ghost-point cross-attention stack
     peaks = measured_peaks()
@@ -286,13 +385,14 @@ def run_ours(args, rank, world, device, local=0):
     if kern_ms:
         avg = sum(kern_ms) / len(kern_ms)
         ach = flops_launch / (avg * 1e-3) / 1e12
-        # dram__bytes_read + write of one launch from profiles/r1_xattn_ghost_v4_ncu.txt (37.6 MB + 19.6 MB): the K/V
-        # tile images stay in L2, the DRAM traffic is the first touch of K/V plus the part of the ghost features that
-        # spills past L2 -- nowhere near the HBM roofline (0.26 % of peak).
-        roof = {"kernel": "xattn4_kernel (fused ghost-point cross-attention stack, tcgen05/TMEM single pass)",
+        # traffic = dram__bytes_read + write of one launch from the committed ncu capture (37.6 MB + 19.9 MB; it cannot be
+        # measured outside a profiler): the K/V tile images stay in L2, DRAM sees the first touch of K/V plus the part of
+        # the ghost features that spills past L2 -- nowhere near the HBM roofline.
+        roof = {"kernel": "xattn6_kernel (fused ghost-point cross-attention stack: tcgen05/TMEM attention + linear layers, "
+                          "FMA-pipe polynomial for 6 of 16 exponentials)",
                 "bound": "tensor", "achieved": round(ach, 2),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
-                "traffic": 57.1e6, "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
+                "traffic": 57.5e6, "traffic_source": "profiles/r2_xattn6_ncu.txt (ncu --set full, one C2 launch)", "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
                 "share_of_step": round(sum(kern_ms) / ms_res, 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
                 "binding_unit": {"unit": "MUFU ex2 (16 / clk / SM at 1.965 GHz, measured 15.9 with tools/micro/mufu_bench.cu)",
@@ -300,8 +400,8 @@ def run_ours(args, rank, world, device, local=0):
                                  "frac": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3 / avg, 4)},
                 "note": "true-E attention FLOPs 4*Nq*Nk*E per layer-sample.  head_dim 15 means one exp per 30 useful FLOPs: "
                         "the binding unit is MUFU (16 ex2/clk/SM, measured with tools/micro/mufu_bench.cu), not the tensor pipe; "
-                        "binding_unit.floor_ms is the launch time at 100 % XU.  ncu: XU pipe 79 %, tensor pipe 13 % "
-                        "(profiles/r1_xattn_ghost_v4_ncu.txt)"}
+                        "binding_unit.floor_ms is the launch time with every exponential on the XU at 100 %; the kernel moves "
+                        "6 of 16 to the FMA pipe (ncu: XU 59 %, ALU 34 %, FMA 21 %, tensor 9 %; profiles/r2_xattn6_ncu.txt)"}
 
     kf = w["batch"] * world * args.steps
     line = {
@@ -309,9 +409,7 @@ def run_ours(args, rank, world, device, local=0):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (fp16 tensor-core operands, fp32 accumulate)",
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": "Act3D forward C2: 4 views 256x256 RGB-D, 16384 ghost pts/level x 3 levels, batch 16/GPU, "
-                               "E=60 H=4, use_instruction=1, backbone=resnet50 (random init, cuDNN)",
-                   "batch_per_gpu": w["batch"], "l2": "flushed between steps (256 MiB write)",
+        "config": {"workload": CONFIG_WORKLOAD, "batch_per_gpu": w["batch"], "l2": "flushed between steps (256 MiB write)",
                    "parallelism": f"replicas x{world} (no data-path collective)"},
         "e2e": {"value": round(kf / (ms_e2e * 1e-3), 3), "unit": "keyframes/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
@@ -320,17 +418,29 @@ def run_ours(args, rank, world, device, local=0):
         "clocks": clk,
         "roofline": roof,
     }
+    also = {}
+    if strong is not None:
+        also["strong_scaling"] = strong
     if not args.no_planner:
         line["secondary"] = run_planner(rank, world, device)
+        also["planner_denoise_steps_per_s"] = line["secondary"]["value"]
     if not args.no_train:
         line["secondary_train"] = run_train(rank, world, device, local)
+        line["secondary_train_planner"] = run_train_planner(rank, world, device, local)
+        also["train_keyframes_per_s_ddp"] = line["secondary_train"]["value"]
+        also["train_trajectories_per_s_ddp"] = line["secondary_train_planner"]["value"]
+        if "ddp_gradient_check_max_rel" in line["secondary_train"]:
+            also["ddp_gradient_check_max_rel"] = max(line["secondary_train"]["ddp_gradient_check_max_rel"],
+                                                     line["secondary_train_planner"]["ddp_gradient_check_max_rel"])
+    line["config"]["also_measured"] = also          # the driver keeps `config`: secondary figures travel with it
     return line
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_act3d_keyframes_per_s(steps, warmup, threads):
+def cpu_act3d_keyframes_per_s(steps, warmup, threads, budget_s=150.0):
     """The reference's CPU implementation restated (oracle port), B=1 keyframe of the C2 workload per step
-    (the reference materialises a 1 GB score tensor per sample-layer; it is batch-linear, so B=1 is the bounded sample)."""
+    (the reference materialises a 1 GB score tensor per sample-layer; it is batch-linear, so B=1 is the bounded sample).
+    Warm-up steps beyond the first are dropped when one step takes so long that the run would not end in minutes."""
     from oracle import act3d_ref
     from tests.golden import synth
     torch.set_num_threads(threads)
@@ -343,30 +453,77 @@ def cpu_act3d_keyframes_per_s(steps, warmup, threads):
     trunk = act3d_ref.trunk_from_module(model)
     import numpy as np
     np.random.seed(0)
-    times = []
+    times, warm_done, t_begin = [], 0, time.perf_counter()
     with torch.no_grad():
-        for i in range(warmup + steps):
+        while len(times) < steps:
             t0 = time.perf_counter()
             act3d_ref.act3d_forward(sd, cfg, trunk, rgb, pcd, instr, grip)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    return len(times) / sum(times), sum(times) / len(times)
+            dt = time.perf_counter() - t0
+            if warm_done < warmup and (warm_done == 0 or (time.perf_counter() - t_begin) + (steps + 1) * dt < budget_s):
+                warm_done += 1
+                continue
+            times.append(dt)
+    return len(times) / sum(times), sum(times) / len(times), warm_done
+
+
+def gpu_eager_reference_keyframes_per_s(device, steps=3):
+    """The same oracle port (plain eager PyTorch, fp32, materialised score tensors, host ghost sampler: the reference's
+    own execution model, act3d.py:176-357) on THIS GPU at the benchmark's batch: the stand-in for "the reference
+    single-GPU PyTorch keyframes/sec at batch 16" of north_star (the reference itself cannot travel to the GPU box).
+    Falls back to smaller batches if the 17 GB-per-layer score tensors do not fit."""
+    from oracle import act3d_ref
+    from tests.golden import synth
+    import numpy as np
+    w = WORKLOAD
+    model = build_act3d().to(device)
+    sd = {k: v for k, v in model.state_dict().items()}
+    cfg = act3d_ref.Act3DConfig(gripper_loc_bounds=synth.BOUNDS, use_instruction=w["use_instruction"],
+                                ghost_points_per_level=w["ghost_per_level"])
+    trunk = act3d_ref.trunk_from_module(model)
+    batch = w["batch"]
+    while batch >= 1:
+        try:
+            ins = [t.to(device) for t in act3d_inputs(batch, w["ncam"], seed=7)]
+            np.random.seed(0)
+            with torch.no_grad():
+                act3d_ref.act3d_forward(sd, cfg, trunk, *ins)              # warm-up (cuDNN autotune, allocator)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    out = act3d_ref.act3d_forward(sd, cfg, trunk, *ins)
+                    out["position"].cpu()
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / steps
+            peak = torch.cuda.max_memory_allocated(device) / 2 ** 30
+            del ins, out
+            torch.cuda.empty_cache()
+            return {"value": round(batch / dt, 2), "unit": "keyframes/s", "batch": batch, "ms_per_step": round(dt * 1e3, 2),
+                    "steps": steps, "peak_memory_gib": round(peak, 1),
+                    "what": "oracle port of the reference forward, eager PyTorch fp32 on this GPU (kind: port)"}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            batch //= 2
+    return {"value": None, "what": "eager PyTorch port ran out of memory even at batch 1"}
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own execution model on the host cores (oracle port; a Python reference cannot
+    travel to the GPU box), same metric / unit / config / steps as our arm; every step is a bounded sample of the
+    16-keyframe batch: one keyframe (the model is batch-linear: no cross-sample operation)."""
     if rank != 0:
         return None
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 4))
-    warm = 1 if args.warmup > 0 else 0
-    kfs, sec = cpu_act3d_keyframes_per_s(steps, warm, threads)
+    kfs, sec, warm = cpu_act3d_keyframes_per_s(args.steps, args.warmup, threads)
+    w = WORKLOAD
     return {
         "metric": "keyframes/s", "value": round(kfs, 4), "unit": "keyframes/s", "impl": "reference",
-        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "Act3D forward C2 (same as the GPU arm), CPU, one keyframe per step (batch-linear model)"},
+        "config": {"workload": CONFIG_WORKLOAD, "batch_per_gpu": w["batch"], "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": f"replicas x{world} (no data-path collective)"},
         "cpu_baseline": {"value": round(kfs, 4), "unit": "keyframes/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} keyframes (B=1 per step) after {warm} warm-up, {sec:.2f} s each"},
+                         "sample": f"{args.steps} steps of 1 keyframe each (of the 16-keyframe batch; batch-linear model) after {warm} "
+                                   f"warm-up step(s), {sec:.2f} s per keyframe; arithmetic in plain fp32"},
         "e2e": {"value": round(kfs, 4), "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -402,9 +559,11 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            kfs, sec = cpu_act3d_keyframes_per_s(2, 1, threads)
+            ref_gpu = gpu_eager_reference_keyframes_per_s(device)
+            kfs, sec, warm = cpu_act3d_keyframes_per_s(6, 1, threads, budget_s=60.0)
             line["cpu_baseline"] = {"value": round(kfs, 4), "unit": "keyframes/s", "cores": threads, "kind": "port",
-                                    "sample": f"2 keyframes (B=1 per step) of the same workload after 1 warm-up, {sec:.2f} s each"}
+                                    "sample": f"6 keyframes (B=1 per step) of the same workload after {warm} warm-up, {sec:.2f} s each",
+                                    "ref_gpu": ref_gpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
