@@ -26,27 +26,6 @@ constexpr int LPR = THREADS / ROWS;        // lanes per row in the row-wise pass
 constexpr int NTW = 4;                     // n tiles per warp in the CTA GEMM
 constexpr int PITCH = 136;                 // halfs per row of an A plane (272 B: conflict-free ldmatrix)
 constexpr int PLANE = ROWS * PITCH;        // halfs per plane
-constexpr int FRAG = 32;                   // uint4 per (k step, n tile)
-constexpr int U = 8 * 16 * FRAG;           // uint4 of one [K=128][N=128] weight
-
-// ------------------------------------------------------------------ packed weight layouts
-// fragment-ordered fp16 (hi, lo) weights, offsets in uint4 (packing.py mirrors these tables)
-struct LangW { static constexpr int WQ = 0, WO = U, W1 = 2 * U, W2 = W1 + 8 * 64 * FRAG, SIZE = W2 + 32 * 16 * FRAG; };
-struct AdaW {
-    static constexpr int C_WQ = 0, C_WO = U, S_WQ = 2 * U, S_WK = 3 * U, S_WV = 4 * U, S_WO = 5 * U, W1 = 6 * U,
-                         W2 = W1 + 8 * 64 * FRAG, SIZE = W2 + 32 * 16 * FRAG;
-};
-struct MlpW { static constexpr int W1 = 0, W2 = U, SIZE = 2 * U; };
-// fp32 vectors (biases, LayerNorm), offsets in floats
-struct LangV { static constexpr int BQ = 0, BO = EP, G12 = 2 * EP, B12 = 3 * EP, B1 = 4 * EP, B2 = B1 + FFP, G122 = B2 + EP, B122 = G122 + EP, SIZE = B122 + EP; };
-struct AdaV {
-    static constexpr int C_BQ = 0, C_BO = EP, G12 = 2 * EP, B12 = 3 * EP, S_BQ = 4 * EP, S_BK = 5 * EP, S_BV = 6 * EP,
-                         S_BO = 7 * EP, G1 = 8 * EP, B1N = 9 * EP, B1 = 10 * EP, B2 = B1 + FFP, G122 = B2 + EP,
-                         B122 = G122 + EP, SIZE = B122 + EP;
-};
-struct MlpV { static constexpr int B1 = 0, B2 = EP, SIZE = 2 * EP; };
-constexpr int ADA_ROW = 3 * 2 * EP;   // per (timestep, layer): {adaln_12, adaln_1, adaln_ff1} x {scale, shift}
-
 // ------------------------------------------------------------------ shared memory map
 constexpr int TILE_E = E * RP;             // floats of a K-major activation tile (only the E real channels are stored)
 constexpr size_t SMEM_BYTES = (size_t)4 * TILE_E * 4 + (size_t)4 * PLANE * 2 + (size_t)kRingStages * kSlabBytes +

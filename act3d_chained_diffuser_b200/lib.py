@@ -63,6 +63,10 @@ EXPORTS = {
                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                         c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                         ctypes.POINTER(c_float), c_void_p, c_void_p, c_void_p]),
+    "cd_denoise_loop": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
 }
 
 _lib = None
@@ -420,3 +424,20 @@ def cd_post(traj, mask, wp_pe, t_idx, ada, ada_layers, ada_layer, x_in, att, lay
                           _ptr(u.get("traj_out")), _ptr(u.get("pos_upd")), _ptr(u.get("cond_data")),
                           _ptr(u.get("cond_mask")), coef, _ptr(u.get("noise_pos")), _ptr(u.get("noise_rot")),
                           _stream()), "cd_post")
+
+
+def cd_denoise_loop(traj, cond, cond_mask, mask, wp_pe, timesteps, ada, n_traj_layers, coef, noise_pos, noise_rot, enc1, enc2,
+                    enc2_b, lang_w, lang_v, lang_k, lang_vv, ada_w, ada_v, pos_reg, rot_reg, kv, kv_set_bytes, nk):
+    """The whole DDPM sampling loop in ONE persistent cluster kernel (csrc/cd_loop.cu): traj (B, L, 9) is updated in
+    place from x_T to x_0.  timesteps: int32 (n_steps,) on the device; coef: fp32 (T, 6) on the device; ada_w / ada_v:
+    lists of the per-layer AdaW / AdaV packs (shared layers, then the two position and the two rotation layers)."""
+    b, length, _ = traj.shape
+    nl = len(ada_w)
+    wp = (c_void_p * nl)(*[_raw(t) for t in ada_w])
+    vp = (c_void_p * nl)(*[_raw(t) for t in ada_v])
+    n_instr = lang_k.shape[1] if lang_k is not None else 0
+    _check(load().cd_denoise_loop(_ptr(_f32(traj)), b, length, int(timesteps.numel()), _ptr(_f32(cond)), _ptr(cond_mask), _ptr(mask),
+                                  _ptr(wp_pe), _ptr(timesteps), _ptr(ada), nl, n_traj_layers, _ptr(_f32(coef)), _ptr(noise_pos),
+                                  _ptr(noise_rot), _raw(enc1), _raw(enc2), _raw(enc2_b), _raw(lang_w), _raw(lang_v), _ptr(lang_k),
+                                  _ptr(lang_vv), n_instr, wp, vp, _raw(pos_reg[0]), _raw(pos_reg[1]), _raw(rot_reg[0]),
+                                  _raw(rot_reg[1]), kv.data_ptr(), kv_set_bytes, nk, _stream()), "cd_denoise_loop")

@@ -474,7 +474,8 @@ class DiffusionPlanner(nn.Module):
         self._noise_fn = None          # test hook: callable(shape) -> CPU/GPU tensor, called in the reference's order
         self._timestep_fn = None       # test hook: callable(batch) -> long tensor of training timesteps
         self.rng_compat = False        # True: draw Gaussian noise with the reference's torch.randn call sequence
-        self.use_cuda_graph = True     # capture the 100-step loop once per shape and replay it
+        self.use_cuda_graph = True     # launch-per-layer path only: capture the 100-step loop once per shape and replay it
+        self.persistent_loop = True    # single-offset sampling: the whole loop in ONE persistent cluster kernel (cd_loop.cu)
         self._samplers = {}
 
     # ------------------------------------------------------------------ frame conversions (torch, elementwise)
@@ -590,6 +591,21 @@ class DiffusionPlanner(nn.Module):
             # coarse-to-fine refinement (feat_scales_to_use > 1 / attn_rounds > 1): the local context is rebuilt from
             # the running estimate inside every step; launched eagerly (no graph), DDPM update as elementwise torch ops
             self._run_steps_multi(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
+            return st["traj"].clone()
+        if self.persistent_loop:
+            # the whole loop in one persistent cluster kernel (csrc/cd_loop.cu): trajectory state in shared memory
+            head_w = ctx["w"]
+            if "coef" not in st:
+                pc, rc = self.position_noise_scheduler.coef, self.rotation_noise_scheduler.coef
+                st["coef"] = torch.cat([pc, rc], dim=1).float().contiguous().to(dev)
+                st["steps_dev"] = torch.tensor(timesteps, device=dev, dtype=torch.int32)
+            lang = head_w["lang"] if self.prediction_head.use_instruction else (None, None)
+            enc1, enc2, enc2_b = head_w["traj_enc"]
+            lib.cd_denoise_loop(st["traj"], st["cond"], st["cmask"], work["mask_u8"] if has_mask else None, work["wp_pe"],
+                                st["steps_dev"], head_w["ada"], len(head.traj_attention[0].layers), st["coef"],
+                                st["noise_pos"], st["noise_rot"], enc1, enc2, enc2_b, lang[0], lang[1], ctx["lang_k"],
+                                ctx["lang_v"], head_w["ada_w"], head_w["ada_v"], head_w["pos_reg"], head_w["rot_reg"],
+                                ctx["kv"], ctx["set_bytes"], ctx["nk"])
             return st["traj"].clone()
         if not self.use_cuda_graph:
             self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])

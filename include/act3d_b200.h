@@ -293,6 +293,28 @@ int cd_post(const float* traj, int batch, int length, const unsigned char* mask,
             float* traj_out, const float* pos_upd, const float* cond_data, const unsigned char* cond_mask,
             const float* coef_host, const float* noise_pos, const float* noise_rot, void* stream);
 
+/* The whole sampling loop as ONE persistent kernel.  Replaces DiffusionPlanner.conditional_sample's loop
+ * (diffusion_model.py:98-117) around DiffusionHead.forward (diffusion_head.py:200-277, 279-363) for the single-offset
+ * configuration: `n_steps` denoiser evaluations + DDPM posterior steps (both schedulers, inpainting, clip_sample,
+ * fixed_small variance) without leaving the SMs.  One thread-block cluster of 4 CTAs per sample (16 waypoint rows each);
+ * trajectory, token tile and all intermediates live in shared memory for the whole loop; the context K/V tile images
+ * are fetched once per cluster with multicast bulk copies; the self-attention K/V rows are exchanged through
+ * distributed shared memory (csrc/cd_loop.cu).
+ * traj [B][L][9]: in = x_T (+ conditioning), out = x_0 (normalised frame).  timesteps [n_steps] (DEVICE int32: row of
+ * `ada` / `coef` used by every iteration), coef [T][6] DEVICE fp32 = {c_x0, c_xt, sigma} of the position then the
+ * rotation scheduler, noise_pos [n_steps][B][L][3] / noise_rot [n_steps][B][L][6] (the last iteration's are unused).
+ * ada_w_host / ada_v_host: HOST arrays of `ada_layers` device pointers (AdaW / AdaV packs: n_traj_layers shared layers,
+ * then 2 position and 2 rotation layers); kv: the `ada_layers` K/V sets of a3d_ctx_kv, kv_set_bytes apart.
+ * Other arguments as in cd_step_begin / cd_post. */
+int cd_denoise_loop(float* traj, int batch, int length, int n_steps, const float* cond, const unsigned char* cond_mask,
+                    const unsigned char* mask, const float* wp_pe, const int* timesteps, const float* ada, int ada_layers,
+                    int n_traj_layers, const float* coef, const float* noise_pos, const float* noise_rot,
+                    const float* traj_enc1, const void* traj_enc2, const float* traj_enc2_b, const void* lang_w,
+                    const float* lang_v, const float* lang_k, const float* lang_vv, int n_instr,
+                    const void* const* ada_w_host, const float* const* ada_v_host, const void* pos_reg_w,
+                    const float* pos_reg_v, const void* rot_reg_w, const float* rot_reg_v, const void* kv,
+                    size_t kv_set_bytes, int nk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,44 @@ def test_denoiser_vs_oracle_full_length_multicam():
     assert (got[:, -1, :3] - inp["goal_gripper"][:, :3]).abs().max() <= 1e-5
 
 
+@pytest.mark.parametrize("length,ncam,masked_tail,batch", [(12, 1, 3, 2), (50, 2, 0, 3), (64, 1, 5, 1), (17, 1, 0, 5)])
+def test_persistent_loop_matches_the_launch_per_layer_path(length, ncam, masked_tail, batch):
+    """csrc/cd_loop.cu (one persistent cluster kernel for all 100 steps, trajectory state in shared memory) against the
+    launch-per-layer kernels of csrc/cd_denoiser.cu on identical noise: same math, different tiling / summation order."""
+    inp = cases.planner_inputs(batch=batch, ncam=ncam, length=length, masked_tail=masked_tail, seed=11)
+    outs = []
+    for persistent in (True, False):
+        m, _ = build()
+        m = m.cuda()
+        m.persistent_loop = persistent
+        m.use_cuda_graph = False
+        m._noise_fn = synth.NoiseStream("pl")
+        outs.append(m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
+                                                                   "curr_gripper", "goal_gripper")]).cpu())
+    a, b = outs
+    assert torch.isfinite(a).all()
+    assert (a[..., :3] - b[..., :3]).abs().max() <= 3e-4, (a[..., :3] - b[..., :3]).abs().max()
+    qd = torch.minimum((a[..., 3:] - b[..., 3:]).abs().max(-1).values, (a[..., 3:] + b[..., 3:]).abs().max(-1).values)
+    assert qd.max() <= 1e-3, qd.max()
+
+
+def test_persistent_loop_without_instruction_and_is_deterministic():
+    m, _ = build(use_instruction=False)
+    m = m.cuda()
+    inp = cases.planner_inputs(batch=2, ncam=1, length=20, seed=2)
+    args = [inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction", "curr_gripper", "goal_gripper")]
+    m._noise_fn = synth.NoiseStream("pd")
+    a = m.compute_trajectory(*args).cpu()
+    m._noise_fn = synth.NoiseStream("pd")
+    b = m.compute_trajectory(*args).cpu()
+    assert torch.equal(a, b)
+    m.persistent_loop = False
+    m.use_cuda_graph = False
+    m._noise_fn = synth.NoiseStream("pd")
+    c = m.compute_trajectory(*args).cpu()
+    assert (a[..., :3] - c[..., :3]).abs().max() <= 3e-4
+
+
 def test_training_loss_fused_and_differentiable_paths_agree():
     """Same noise / timesteps: the loss evaluated under no_grad (fused denoiser kernels) equals the loss of the
     differentiable path (csrc/a3d_train.cu behind autograd); eval mode so that dropout is off in both."""
@@ -114,6 +152,7 @@ def test_parallel_heads_are_bit_identical_to_the_sequential_order():
         m = m.cuda()
         m.prediction_head.parallel_heads = parallel
         m.use_cuda_graph = graph
+        m.persistent_loop = False                      # this test is about the launch-per-layer path
         m._noise_fn = synth.NoiseStream("cd")
         outs.append(m.compute_trajectory(*[inp[k].cuda() for k in ("trajectory_mask", "rgb_obs", "pcd_obs", "instruction",
                                                                    "curr_gripper", "goal_gripper")]).cpu())
