@@ -9,11 +9,15 @@
 //   * every linear layer, LayerNorm, adaLN, rotary and the cross-attention are row-local: a warp owns one 8-column
 //     n tile of the [16 x 128] output, takes its weight fragments STRAIGHT from L2 with all k steps in flight (no
 //     staging, no barrier inside a GEMM) and the stage costs one block barrier;
-//   * the cross-attention K/V tile images (32 KiB per 64 keys, all 8 heads) are fetched ONCE per cluster: the leader
-//     CTA's producer warp issues cp.async.bulk ... .multicast::cluster into the same ring slot of all 4 CTAs (TMA
-//     engine, mbarrier complete_tx in every CTA), 3 slots, freed through remote mbarrier arrivals;
-//   * only the self-attention needs other rows: every CTA writes its 16 rows of K / V (fp16 hi, lo planes) into the
-//     planes of all 4 CTAs through distributed shared memory, fenced by two cluster-scope mbarriers.
+//   * the cross-attention is split BY KEYS instead: every CTA streams its own quarter of the context K/V tile images
+//     (32 KiB per 64 keys, all 8 heads; cp.async.bulk on a 3-slot mbarrier ring fed by its own producer warp, with
+//     cp.async.bulk.prefetch.L2 running 12 tiles ahead) against the Q of ALL 64 rows, and the unnormalised partial results
+//     go to the CTA that owns the rows.  (A first version kept the rows split here too and multicast every tile to the
+//     4 CTAs: 96 KiB in flight per cluster against ~2 us of HBM + multicast latency made the ring latency-bound, 54 us per
+//     layer, ncu: 20 % of all stall samples on the tile barrier; the key split puts 4 x 96 KiB in flight per sample.)
+//   * three exchanges per layer go through distributed shared memory, each fenced by one cluster-scope mbarrier: the
+//     rotary Q rows (all-gather), the cross-attention partials (to the row owners) and the 16 rows of K / V of the
+//     self-attention (all-gather into the fp16 hi / lo planes of all 4 CTAs).
 // Math is the same as cd_denoiser.cu (error-compensated split-fp16 mma.sync GEMMs, exact softmax in the 64-key
 // self-attention, online softmax in the cross-attention, fp32 everywhere else): the 16-row tiles leave no room for a
 // 64/128-row tcgen05.mma, and at these sizes the stage latency, not tensor throughput, is the bound (the tcgen05
@@ -32,7 +36,7 @@ constexpr int CT = CW * 32;               // compute threads
 constexpr int LT = CT + 32;               // + producer warp
 constexpr int LP = 136;                   // halfs per row of an fp16 plane (272 B: conflict-free ldmatrix)
 constexpr int FPT = 132;                  // floats per row of an fp32 tile
-constexpr int QXP = 24;                   // halfs per row of the cross-attention Q tiles
+constexpr int PF_TILES = 12;              // L2 prefetch distance of the K/V stream (tiles of this CTA's own sequence)
 constexpr int KV_TILE = 2 * H * 2048;     // K image + V image of 64 keys, all heads
 constexpr int ST = 3;                     // ring slots
 constexpr int MAXL = 12;
@@ -70,15 +74,16 @@ struct LoopSmem {
     unsigned char* ring;                  // ST x KV_TILE
     __half *kh, *kl, *vh, *vl;            // [64][LP] self-attention / instruction K, V planes (head-padded columns)
     __half *ah, *al, *hh, *hl;            // [16][LP] GEMM input planes
-    float *xs, *t1, *ty, *ysave;          // [16][FPT]
-    __half* qx;                           // [H][16][QXP] rotary Q of the next cross-attention
+    float *xs, *t1, *ysave;               // [16][FPT]
+    __half* qx;                           // [H][64][16] rotary Q of ALL rows for the next cross-attention (SWIZZLE_32B rows)
+    float* part;                          // [CL sources][H][17][16] cross-attention partials of this CTA's rows (aliases the K/V planes)
     float *trj, *upd;                     // [16][9] trajectory rows; [16][9] position update (3) + rotation (6)
     float* freq;                          // [20]
     unsigned char* kmask;                 // [64]
-    uint64_t *full, *empty, *kv_free, *kv_ready;
-    int* cnt;
-    static constexpr size_t BYTES = (size_t)ST * KV_TILE + (size_t)4 * 64 * LP * 2 + (size_t)4 * RB * LP * 2 + (size_t)4 * RB * FPT * 4 +
-                                    (size_t)H * RB * QXP * 2 + 2 * RB * 9 * 4 + 32 * 4 + 64 + (2 * ST + 2) * 8 + ST * 4 + 64;
+    uint64_t *full, *empty, *kv_free, *kv_ready, *q_ready, *p_ready;
+    static constexpr size_t BYTES = (size_t)ST * KV_TILE + (size_t)4 * 64 * LP * 2 + (size_t)4 * RB * LP * 2 + (size_t)3 * RB * FPT * 4 +
+                                    (size_t)H * 64 * 16 * 2 + 2 * RB * 9 * 4 + 32 * 4 + 64 + (2 * ST + 4) * 8 + 64;
+    static_assert((size_t)CL * H * 17 * RB * 4 <= (size_t)4 * 64 * LP * 2, "partials must fit in the K/V planes");
     __device__ explicit LoopSmem(unsigned char* b) {
         ring = b;
         kh = reinterpret_cast<__half*>(b + (size_t)ST * KV_TILE);
@@ -91,10 +96,10 @@ struct LoopSmem {
         hl = hh + RB * LP;
         xs = reinterpret_cast<float*>(hl + RB * LP);
         t1 = xs + RB * FPT;
-        ty = t1 + RB * FPT;
-        ysave = ty + RB * FPT;
+        ysave = t1 + RB * FPT;
         qx = reinterpret_cast<__half*>(ysave + RB * FPT);
-        trj = reinterpret_cast<float*>(qx + H * RB * QXP);
+        part = reinterpret_cast<float*>(kh);
+        trj = reinterpret_cast<float*>(qx + H * 64 * 16);
         upd = trj + RB * 9;
         freq = upd + RB * 9;
         kmask = reinterpret_cast<unsigned char*>(freq + 32);
@@ -102,7 +107,8 @@ struct LoopSmem {
         empty = full + ST;
         kv_free = empty + ST;
         kv_ready = kv_free + 1;
-        cnt = reinterpret_cast<int*>(kv_ready + 1);
+        q_ready = kv_ready + 1;
+        p_ready = q_ready + 1;
     }
 };
 
@@ -140,12 +146,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         "r"(parity)
         : "memory");
 }
-// one 1-D bulk copy global -> the same shared-memory offset of every CTA in `mask`; each CTA's mbarrier gets the bytes
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
+__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+// warm L2 for a later bulk copy (TMA engine, no destination)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }   // the 16 compute warps
 
@@ -294,18 +300,21 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
     const int row0 = RB * (int)rank;                                  // first global row of this CTA
     const int nloc = max(0, min(RB, a.nrows - row0));                 // valid rows here
     const int ntiles = a.ntiles;
+    // this CTA's quarter of the key tiles
+    const int tiles_per = (ntiles + CL - 1) / CL;
+    const int t_begin = min((int)rank * tiles_per, ntiles), my_tiles = min(t_begin + tiles_per, ntiles) - t_begin;
 
     // ---------------------------------------------------------------- one-time setup
     if (tid == 0) {
         for (int i = 0; i < ST; ++i) {
             mbar_init(s.full + i, 1);
-            mbar_init(s.empty + i, CL);
-            s.cnt[i] = 0;
+            mbar_init(s.empty + i, CW);
         }
         mbar_init(s.kv_free, CL);
         mbar_init(s.kv_ready, CL);
+        mbar_init(s.q_ready, CL);
+        mbar_init(s.p_ready, CL);
         mbar_fence_init();
-        for (int i = 0; i < ST; ++i) mbar_expect_tx(s.full + i, KV_TILE);      // first use of every slot
     }
     for (int i = tid; i < (4 * 64 + 4 * RB) * LP / 2; i += LT) reinterpret_cast<uint32_t*>(s.kh)[i] = 0u;   // all planes (pad columns stay 0)
     if (tid < E / 6) s.freq[tid] = rope_freq<E>(tid);
@@ -318,32 +327,37 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
     cluster_sync_all();                                               // barriers of every CTA are initialised and armed
 
     if (w == CW) {
-        // ================================================================ producer warp: K/V tiles, leader CTA only
-        if (rank == 0 && lane == 0) {
-            const unsigned char* kv_b = a.kv + (size_t)b * ntiles * KV_TILE;
-            uint32_t gi = 0;
-            for (int step = 0; step < a.n_steps; ++step)
-                for (int l = 0; l < a.nl; ++l) {
-                    const unsigned char* src = kv_b + (size_t)l * a.kv_set_bytes;
-                    for (int t = 0; t < ntiles; ++t, ++gi) {
-                        const uint32_t slot = gi % ST, use = gi / ST;
-                        if (use >= 1) mbar_wait_cluster(s.empty + slot, (use - 1) & 1);   // all 4 CTAs released (and re-armed) the slot
-                        bulk_g2s_multicast(s.ring + slot * KV_TILE, src + (size_t)t * KV_TILE, KV_TILE, s.full + slot, (uint16_t)((1u << CL) - 1));
-                    }
-                }
+        // ================================================================ producer warp: this CTA's K/V tile stream
+        if (lane == 0 && my_tiles > 0) {
+            const unsigned char* kv_b = a.kv + ((size_t)b * ntiles + t_begin) * KV_TILE;
+            const uint32_t total = (uint32_t)a.n_steps * a.nl * my_tiles;
+            auto src_of = [&](uint32_t j) {                       // j-th tile of the sequence (steps x layers x my tiles)
+                const uint32_t l = (j / my_tiles) % a.nl, t = j % my_tiles;
+                return kv_b + (size_t)l * a.kv_set_bytes + (size_t)t * KV_TILE;
+            };
+            for (uint32_t j = 0; j < (uint32_t)PF_TILES && j < total; ++j) bulk_prefetch_l2(src_of(j), KV_TILE);
+            for (uint32_t j = 0; j < total; ++j) {
+                if (j + PF_TILES < total) bulk_prefetch_l2(src_of(j + PF_TILES), KV_TILE);
+                const uint32_t slot = j % ST, use = j / ST;
+                if (use >= 1) mbar_wait(s.empty + slot, (use - 1) & 1);
+                mbar_expect_tx(s.full + slot, KV_TILE);
+                bulk_g2s(s.ring + slot * KV_TILE, src_of(j), KV_TILE, s.full + slot);
+            }
         }
     } else {
         // ================================================================ compute warps
-        const uint32_t empty_leader = mapa(smem_u32(s.empty), 0);
-        uint32_t kvf_remote[CL], kvr_remote[CL], kvp_remote[CL];
+        uint32_t kvf_remote[CL], kvr_remote[CL], kvp_remote[CL], qr_remote[CL], pr_remote[CL], qx_remote[CL];
 #pragma unroll
         for (int r = 0; r < CL; ++r) {
             kvf_remote[r] = mapa(smem_u32(s.kv_free), r);
             kvr_remote[r] = mapa(smem_u32(s.kv_ready), r);
-            kvp_remote[r] = mapa(smem_u32(s.kh), r);
+            kvp_remote[r] = mapa(smem_u32(s.kh), r);           // K/V planes == partial buffer
+            qr_remote[r] = mapa(smem_u32(s.q_ready), r);
+            pr_remote[r] = mapa(smem_u32(s.p_ready), r);
+            qx_remote[r] = mapa(smem_u32(s.qx), r);
         }
         uint32_t gtile = 0;            // tiles consumed so far (all layers / steps): ring slot and parity
-        uint32_t xphase = 0;           // K/V all-gathers done so far: parity of kv_free / kv_ready
+        uint32_t xphase = 0;           // layers done so far: parity of q_ready / p_ready / kv_free / kv_ready
         const float* pe_row = a.wp_pe + (size_t)(row0 + w) * E;      // this warp's row in the row-wise stages (row = warp)
         const bool row_ok = w < nloc;
 
@@ -451,7 +465,9 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 }
             }
         };
-        // rotary Q of a cross-attention: fp16 [H][16][QXP] (pad slot 15 of every head = 0)
+        // rotary Q of a cross-attention: fp16 [H][64][16], 32-byte rows with the two 16-byte halves swapped when (row>>2)&1
+        // (the K tile layout: conflict-free ldmatrix); this CTA writes rows row0 .. row0+15; pad slot 15 of every head = 0
+        auto qx_at = [&](int hh_, int grow, int d) { return (hh_ * 64 + grow) * 16 + ((((d >> 3) ^ ((grow >> 2) & 1))) << 3) + (d & 7); };
         auto epi_qx = [&](const float (&acc)[4], const float* bias) {
             const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ocol));
 #pragma unroll
@@ -461,11 +477,11 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 if (ocol < E) {
                     rotate(r, ocol, v0, v1);
                     const int h0 = ocol / HD, h1 = (ocol + 1) / HD;
-                    s.qx[(h0 * RB + r) * QXP + (ocol - h0 * HD)] = __float2half_rn(v0);
-                    s.qx[(h1 * RB + r) * QXP + (ocol + 1 - h1 * HD)] = __float2half_rn(v1);
+                    s.qx[qx_at(h0, row0 + r, ocol - h0 * HD)] = __float2half_rn(v0);
+                    s.qx[qx_at(h1, row0 + r, ocol + 1 - h1 * HD)] = __float2half_rn(v1);
                 } else {   // GEMM columns 120..127 own the pad slot of head c - 120
-                    s.qx[((ocol - E) * RB + r) * QXP + 15] = __float2half_rn(0.f);
-                    s.qx[((ocol + 1 - E) * RB + r) * QXP + 15] = __float2half_rn(0.f);
+                    s.qx[qx_at(ocol - E, row0 + r, 15)] = __float2half_rn(0.f);
+                    s.qx[qx_at(ocol + 1 - E, row0 + r, 15)] = __float2half_rn(0.f);
                 }
             }
         };
@@ -485,6 +501,19 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
             float acc[4];
             gemm16<8>(s.ah, s.al, wq, lane, acc);
             epi_qx(acc, a.ada_v[layer] + AdaV::C_BQ);
+            csync();
+            // all-gather: this CTA's 16 rows of every head (512 contiguous bytes each) -> the same rows of the three peers
+            // (they have all left the previous cross-attention: their K/V rows of that layer were needed to get here)
+            for (int i = tid; i < H * 32; i += CT) {
+                const uint32_t off = (uint32_t)(((i >> 5) * 64 + row0) * 32 + (i & 31) * 16);
+                const uint4 val = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(s.qx) + off);
+#pragma unroll
+                for (int r = 0; r < CL; ++r)
+                    if (r != (int)rank) st_cluster_v4(qx_remote[r] + off, val);
+            }
+            csync();
+            if (tid == 0)
+                for (int r = 0; r < CL; ++r) mbar_arrive_cluster(qr_remote[r]);
         };
         // regressor head Linear(E,E) -> ReLU -> Linear(E,d) on the tile `x` -> s.upd[r][col0 + d]  (uses the kv planes as scratch)
         auto regress = [&](const float* x, const uint4* rw, const float* rv, int col0, int dim) {
@@ -591,143 +620,161 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 __syncwarp();
             }
             make_q(s.xs, 0, ada_t);
-            // this CTA is done with the K/V planes (instruction attention): peers may write the next all-gather
-            csync();
-            if (tid == 0)
-                for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvf_remote[r]);
 
             for (int l = 0; l < a.nl; ++l) {
                 const uint4* lw = a.ada_w[l];
                 const float* lv = a.ada_v[l];
                 const float* ada = ada_t + (size_t)l * ADA_ROW;
                 // ======================================================== cross-attention over the cached context K/V
-                // warp = (head, key half): tiles t = kh, kh + 2, ...; online softmax; the two halves merge through smem
+                // Keys are split over the 4 CTAs; every CTA runs all 64 rows against its quarter of the tiles.
+                // warp = (head, 32-row half): two m16 tiles, online softmax per row; the unnormalised partials
+                // {O (15), denominator, row max} go to the CTA that owns the rows.
+                mbar_wait_cluster(s.q_ready, xphase & 1);          // rotary Q of all 64 rows has landed (and the K/V planes of
+                                                                   // every CTA are idle: they double as the partial buffers)
                 {
-                    const int h = w & 7, khalf = w >> 3;
-                    uint32_t qf[4];
-                    {
-                        const int row = (lane & 7) + 8 * ((lane >> 3) & 1);
-                        ldmatrix_x4(qf, smem_u32(s.qx + (h * RB + row) * QXP + 8 * (lane >> 4)));
+                    const int h = w & 7, rhalf = w >> 3;
+                    uint32_t qf[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const int row = 32 * rhalf + 16 * mt + (lane & 7) + 8 * ((lane >> 3) & 1);
+                        ldmatrix_x4(qf[mt], smem_u32(s.qx) + (uint32_t)((h * 64 + row) * 32 + (((lane >> 4) ^ ((row >> 2) & 1)) << 4)));
                     }
-                    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                    float m0 = -INFINITY, m1 = -INFINITY;
+                    float o[2][2][4];
+                    float mrow[2][2];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mrow[mt][0] = mrow[mt][1] = -INFINITY;
+#pragma unroll
+                        for (int n = 0; n < 2; ++n)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[mt][n][e] = 0.f;
+                    }
                     const bool tail_mask = (a.nk % kTileKeys) != 0;
-                    for (int t = khalf; t < ntiles; t += 2) {
+                    for (int t = 0; t < my_tiles; ++t) {
                         const uint32_t gi = gtile + t, slot = gi % ST;
                         mbar_wait(s.full + slot, (gi / ST) & 1);
                         const uint32_t kbase = smem_u32(s.ring + slot * KV_TILE) + h * 2048, vbase = kbase + H * 2048;
-                        float sc[8][4];
+                        const bool mask_tile = tail_mask && (t_begin + t == ntiles - 1);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
+                        for (int mt = 0; mt < 2; ++mt) {
+                            float sc[8][4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+                            for (int jj = 0; jj < 8; ++jj)
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int key = kk * 16 + (lane & 7) + 8 * (lane >> 4);
-                            const int chunk = (lane >> 3) & 1;
-                            uint32_t r[4];
-                            ldmatrix_x4(r, kbase + key * 32 + ((chunk ^ ((key >> 2) & 1)) << 4));
-                            mma_16816(sc[2 * kk], qf, r[0], r[1]);
-                            mma_16816(sc[2 * kk + 1], qf, r[2], r[3]);
+                                for (int e = 0; e < 4; ++e) sc[jj][e] = 0.f;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const int key = kk * 16 + (lane & 7) + 8 * (lane >> 4);
+                                const int chunk = (lane >> 3) & 1;
+                                uint32_t r[4];
+                                ldmatrix_x4(r, kbase + key * 32 + ((chunk ^ ((key >> 2) & 1)) << 4));
+                                mma_16816(sc[2 * kk], qf[mt], r[0], r[1]);
+                                mma_16816(sc[2 * kk + 1], qf[mt], r[2], r[3]);
+                            }
+                            if (mask_tile) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if ((t_begin + t) * kTileKeys + 8 * jj + 2 * q4 + (e & 1) >= a.nk) sc[jj][e] = -INFINITY;
+                            }
+                            float mx0 = sc[0][0], mx1 = sc[0][2];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                mx0 = fmaxf(mx0, fmaxf(sc[jj][0], sc[jj][1]));
+                                mx1 = fmaxf(mx1, fmaxf(sc[jj][2], sc[jj][3]));
+                            }
+                            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                            const float n0 = fmaxf(mrow[mt][0], mx0), n1 = fmaxf(mrow[mt][1], mx1);
+                            const float al0 = exp2_fast(mrow[mt][0] - n0), al1 = exp2_fast(mrow[mt][1] - n1);
+                            mrow[mt][0] = n0;
+                            mrow[mt][1] = n1;
+#pragma unroll
+                            for (int n = 0; n < 2; ++n) {
+                                o[mt][n][0] *= al0;
+                                o[mt][n][1] *= al0;
+                                o[mt][n][2] *= al1;
+                                o[mt][n][3] *= al1;
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                uint32_t pa[4];
+                                pa[0] = pack_h2(exp2_fast(sc[2 * kk][0] - n0), exp2_fast(sc[2 * kk][1] - n0));
+                                pa[1] = pack_h2(exp2_fast(sc[2 * kk][2] - n1), exp2_fast(sc[2 * kk][3] - n1));
+                                pa[2] = pack_h2(exp2_fast(sc[2 * kk + 1][0] - n0), exp2_fast(sc[2 * kk + 1][1] - n0));
+                                pa[3] = pack_h2(exp2_fast(sc[2 * kk + 1][2] - n1), exp2_fast(sc[2 * kk + 1][3] - n1));
+                                const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+                                const int chunk = lane >> 4;
+                                uint32_t r[4];
+                                ldmatrix_x4_trans(r, vbase + key * 32 + ((chunk ^ ((key >> 2) & 1)) << 4));
+                                mma_16816(o[mt][0], pa, r[0], r[1]);
+                                mma_16816(o[mt][1], pa, r[2], r[3]);
+                            }
                         }
-                        if (tail_mask && t == ntiles - 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (t * kTileKeys + 8 * j + 2 * q4 + (e & 1) >= a.nk) sc[j][e] = -INFINITY;
-                        }
-                        float mx0 = sc[0][0], mx1 = sc[0][2];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
-                            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
-                        }
-                        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-                        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-                        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-                        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-                        const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
-                        const float al0 = exp2_fast(m0 - n0), al1 = exp2_fast(m1 - n1);
-                        m0 = n0;
-                        m1 = n1;
-#pragma unroll
-                        for (int n = 0; n < 2; ++n) {
-                            o[n][0] *= al0;
-                            o[n][1] *= al0;
-                            o[n][2] *= al1;
-                            o[n][3] *= al1;
-                        }
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            uint32_t pa[4];
-                            pa[0] = pack_h2(exp2_fast(sc[2 * kk][0] - n0), exp2_fast(sc[2 * kk][1] - n0));
-                            pa[1] = pack_h2(exp2_fast(sc[2 * kk][2] - n1), exp2_fast(sc[2 * kk][3] - n1));
-                            pa[2] = pack_h2(exp2_fast(sc[2 * kk + 1][0] - n0), exp2_fast(sc[2 * kk + 1][1] - n0));
-                            pa[3] = pack_h2(exp2_fast(sc[2 * kk + 1][2] - n1), exp2_fast(sc[2 * kk + 1][3] - n1));
-                            const int key = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-                            const int chunk = lane >> 4;
-                            uint32_t r[4];
-                            ldmatrix_x4_trans(r, vbase + key * 32 + ((chunk ^ ((key >> 2) & 1)) << 4));
-                            mma_16816(o[0], pa, r[0], r[1]);
-                            mma_16816(o[1], pa, r[2], r[3]);
-                        }
-                        // release the slot: the 8th warp (one per head) re-arms this CTA's barrier and tells the leader
                         __syncwarp();
-                        if (lane == 0) {
-                            if (atomicAdd(s.cnt + slot, 1) == H - 1) {
-                                s.cnt[slot] = 0;
-                                mbar_expect_tx(s.full + slot, KV_TILE);
-                                mbar_arrive_cluster(empty_leader + slot * 8);
-                            }
-                        }
+                        if (lane == 0) mbar_arrive(s.empty + slot);
                     }
-                    gtile += ntiles;
-                    WFrag<8> wo;                                   // out-projection weights: in flight during the merge
-                    wo.load(lw + AdaW::C_WO, 16, w, lane);
-                    // ---- merge the two key halves of every (row, head): half 1 parks {O (16), m} in the idle t1 / ty tiles
-                    float* part = s.t1;                                           // [H][17][16] floats (t1 and ty are contiguous)
-                    if (khalf == 1) {
+                    gtile += my_tiles;
+                    // ---- partials -> the owner of the rows: m tile mt of this warp = rows of CTA 2 rhalf + mt
+                    //      owner layout part[source CTA][head][17][16 rows] (floats)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint32_t dst = kvp_remote[2 * rhalf + mt] + (uint32_t)(((rank * H + h) * 17) * RB * 4);
 #pragma unroll
                         for (int n = 0; n < 2; ++n)
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) part[(h * 17 + 8 * n + 2 * q4 + (e & 1)) * RB + g + 8 * (e >> 1)] = o[n][e];
+                            for (int e = 0; e < 4; ++e)
+                                st_cluster_f32(dst + (uint32_t)(((8 * n + 2 * q4 + (e & 1)) * RB + g + 8 * (e >> 1)) * 4), o[mt][n][e]);
                         if (q4 == 0) {
-                            part[(h * 17 + 16) * RB + g] = m0;
-                            part[(h * 17 + 16) * RB + g + 8] = m1;
+                            st_cluster_f32(dst + (uint32_t)((16 * RB + g) * 4), mrow[mt][0]);
+                            st_cluster_f32(dst + (uint32_t)((16 * RB + g + 8) * 4), mrow[mt][1]);
                         }
                     }
-                    csync();
-                    if (khalf == 0) {
-                        const float pm0 = part[(h * 17 + 16) * RB + g], pm1 = part[(h * 17 + 16) * RB + g + 8];
-                        const float M0 = fmaxf(m0, pm0), M1 = fmaxf(m1, pm1);
-                        const float wa0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - M0), wb0 = (pm0 == -INFINITY) ? 0.f : exp2f(pm0 - M0);
-                        const float wa1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - M1), wb1 = (pm1 == -INFINITY) ? 0.f : exp2f(pm1 - M1);
+                }
+                WFrag<8> wo;                                       // out-projection weights: in flight during the exchange
+                wo.load(lw + AdaW::C_WO, 16, w, lane);
+                csync();
+                if (tid == 0)
+                    for (int r = 0; r < CL; ++r) mbar_arrive_cluster(pr_remote[r]);
+                mbar_wait_cluster(s.p_ready, xphase & 1);          // the partials of all four key quarters are here
+                // ---- merge: warp = head, lane = (row, 8-wide half of the head dimension)
+                if (w < H) {
+                    const int h = w, r = lane & 15, dh = lane >> 4;
+                    float m[CL], big = -INFINITY;
 #pragma unroll
-                        for (int n = 0; n < 2; ++n)
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float po = part[(h * 17 + 8 * n + 2 * q4 + (e & 1)) * RB + g + 8 * (e >> 1)];
-                                o[n][e] = (e >> 1) ? (o[n][e] * wa1 + po * wb1) : (o[n][e] * wa0 + po * wb0);
-                            }
-                        // denominators rode in V's slot 15: held by the lane with q4 == 3 (n = 1, e = 1 / 3)
-                        const float l0 = __shfl_sync(0xffffffffu, o[1][1], (lane & ~3) | 3), l1 = __shfl_sync(0xffffffffu, o[1][3], (lane & ~3) | 3);
-                        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-#pragma unroll
-                        for (int n = 0; n < 2; ++n)
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int d = 8 * n + 2 * q4 + (e & 1);
-                                if (d < HD) {
-                                    const int row = g + 8 * (e >> 1);
-                                    __half x, y;
-                                    split_h(o[n][e] * ((e >> 1) ? i1 : i0), x, y);
-                                    s.ah[row * LP + h * HD + d] = x;
-                                    s.al[row * LP + h * HD + d] = y;
-                                }
-                            }
+                    for (int sp = 0; sp < CL; ++sp) {
+                        m[sp] = s.part[((sp * H + h) * 17 + 16) * RB + r];
+                        big = fmaxf(big, m[sp]);
                     }
-                    csync();
+                    float acc[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+#pragma unroll
+                    for (int sp = 0; sp < CL; ++sp) {
+                        const float wgt = (m[sp] == -INFINITY) ? 0.f : exp2f(m[sp] - big);
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) acc[d] = fmaf(wgt, s.part[((sp * H + h) * 17 + 8 * dh + d) * RB + r], acc[d]);
+                    }
+                    const float den = __shfl_sync(0xffffffffu, acc[7], r | 16);     // slot 15 = denominator (rode in V's slot 15)
+                    const float inv = 1.0f / den;
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) {
+                        if (8 * dh + d < HD) {
+                            __half x, y;
+                            split_h(acc[d] * inv, x, y);
+                            s.ah[r * LP + h * HD + 8 * dh + d] = x;
+                            s.al[r * LP + h * HD + 8 * dh + d] = y;
+                        }
+                    }
+                }
+                csync();
+                // the partial buffer (= K/V planes) of this CTA is free: peers may write their K / V rows of this layer
+                if (tid == 0)
+                    for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvf_remote[r]);
+                {
                     // ---- out projection + residual + LN_12                                       (layers.py:146-147)
                     float acc[4];
                     gemm16<8>(s.ah, s.al, wo, lane, acc);
@@ -801,6 +848,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 }
                 csync();
                 // ---- x = LN_1(x + sa); y = adaLN_ff(x); FFN                                      (layers.py:183-209)
+                float yv[4];
                 {
                     float v[4], t[4];
                     ld_row4(s.xs, v);
@@ -809,7 +857,8 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     for (int i = 0; i < 4; ++i) v[i] += t[i];
                     layernorm4(v, lv + AdaV::G1, lv + AdaV::B1N);
                     modulate4(v, ada + 4 * EP, ada + 5 * EP);
-                    st_row4(s.ty, v);                              // y (fp32) for the residual
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) yv[i] = v[i];      // y stays in this warp's registers for the residual
                     st_planes4(s.ah, s.al, v);
                 }
                 {
@@ -846,10 +895,9 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 const int last_shared = a.n_traj - 1, p1 = a.n_traj + 1, r1 = a.n_traj + 3;
                 {
                     float v[4], t[4];
-                    ld_row4(s.ty, v);
                     ld_row4(s.t1, t);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] += t[i];
+                    for (int i = 0; i < 4; ++i) v[i] = yv[i] + t[i];
                     layernorm4(v, lv + AdaV::G122, lv + AdaV::B122);
                     st_row4(s.xs, v);
                     if (l == last_shared) st_row4(s.ysave, v);     // both heads start from the output of the shared stack
@@ -868,11 +916,6 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     regress(s.xs, a.rot_w, a.rot_v, 3, 6);
                 }
                 if (l + 1 < a.nl) make_q(s.xs, l + 1, ada_t);
-                // this CTA is done with the K/V planes until the next all-gather (the one of layer 0 of the next step is
-                // announced after that step's instruction attention)
-                csync();
-                if (l + 1 < a.nl && tid == 0)
-                    for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvf_remote[r]);
             }
             // ============================================================ denoiser output + DDPM posterior step
             // (diffusion_head.py:271-274: position is residual on the noisy input, rotation is direct;
