@@ -41,6 +41,14 @@ constexpr int KV_TILE = 2 * H * 2048;     // K image + V image of 64 keys, all h
 constexpr int ST = 3;                     // ring slots
 constexpr int MAXL = 12;
 
+#ifdef A3D_CDL_TRACE
+// clock64 timeline of one layer of one CTA (study build only: A3D_NVCC_EXTRA=-DA3D_CDL_TRACE; cd_loop_trace_read)
+__device__ long long g_cdl_trace[64];
+#define CDL_TRACE(k) do { if (tr_on) g_cdl_trace[k] = clock64(); } while (0)
+#else
+#define CDL_TRACE(k)
+#endif
+
 struct LoopArgs {
     int batch, nrows, n_steps, nl, n_traj, nk, ntiles, n_instr;
     float* traj;                          // [B][L][9] in: x_T (+ conditioning), out: x_0
@@ -74,15 +82,19 @@ struct LoopSmem {
     unsigned char* ring;                  // ST x KV_TILE
     __half *kh, *kl, *vh, *vl;            // [64][LP] self-attention / instruction K, V planes (head-padded columns)
     __half *ah, *al, *hh, *hl;            // [16][LP] GEMM input planes
-    float *xs, *t1, *ysave;               // [16][FPT]
+    float* t1;                            // [16][FPT] GEMM output handed to the row-wise stages
+    float* vecs;                          // AdaV of the current layer (biases, LayerNorm parameters): staged by a bulk copy
+    float* qv;                            // [2][QV] {C_BQ, adaLN row} of the current / next layer (double-buffered)
     __half* qx;                           // [H][64][16] rotary Q of ALL rows for the next cross-attention (SWIZZLE_32B rows)
     float* part;                          // [CL sources][H][17][16] cross-attention partials of this CTA's rows (aliases the K/V planes)
     float *trj, *upd;                     // [16][9] trajectory rows; [16][9] position update (3) + rotation (6)
     float* freq;                          // [20]
     unsigned char* kmask;                 // [64]
-    uint64_t *full, *empty, *kv_free, *kv_ready, *q_ready, *p_ready;
-    static constexpr size_t BYTES = (size_t)ST * KV_TILE + (size_t)4 * 64 * LP * 2 + (size_t)4 * RB * LP * 2 + (size_t)3 * RB * FPT * 4 +
-                                    (size_t)H * 64 * 16 * 2 + 2 * RB * 9 * 4 + 32 * 4 + 64 + (2 * ST + 4) * 8 + 64;
+    uint64_t *full, *empty, *kv_free, *kv_ready, *q_ready, *p_ready, *vec_full, *qv_full;
+    static constexpr int QV = EP + ADA_ROW;          // floats of one {C_BQ, adaLN row} block
+    static constexpr size_t BYTES = (size_t)ST * KV_TILE + (size_t)4 * 64 * LP * 2 + (size_t)4 * RB * LP * 2 + (size_t)RB * FPT * 4 +
+                                    (size_t)(AdaV::SIZE + 2 * QV) * 4 + (size_t)H * 64 * 16 * 2 + 2 * RB * 9 * 4 + 32 * 4 + 64 +
+                                    (2 * ST + 7) * 8 + 64;
     static_assert((size_t)CL * H * 17 * RB * 4 <= (size_t)4 * 64 * LP * 2, "partials must fit in the K/V planes");
     __device__ explicit LoopSmem(unsigned char* b) {
         ring = b;
@@ -94,10 +106,10 @@ struct LoopSmem {
         al = ah + RB * LP;
         hh = al + RB * LP;
         hl = hh + RB * LP;
-        xs = reinterpret_cast<float*>(hl + RB * LP);
-        t1 = xs + RB * FPT;
-        ysave = t1 + RB * FPT;
-        qx = reinterpret_cast<__half*>(ysave + RB * FPT);
+        t1 = reinterpret_cast<float*>(hl + RB * LP);
+        vecs = t1 + RB * FPT;
+        qv = vecs + AdaV::SIZE;
+        qx = reinterpret_cast<__half*>(qv + 2 * QV);
         part = reinterpret_cast<float*>(kh);
         trj = reinterpret_cast<float*>(qx + H * 64 * 16);
         upd = trj + RB * 9;
@@ -109,6 +121,8 @@ struct LoopSmem {
         kv_ready = kv_free + 1;
         q_ready = kv_ready + 1;
         p_ready = q_ready + 1;
+        vec_full = p_ready + 1;
+        qv_full = vec_full + 1;          // [2]
     }
 };
 
@@ -170,22 +184,28 @@ struct WFrag {
 template <int KS>
 __device__ __forceinline__ void gemm16(const __half* __restrict__ ah, const __half* __restrict__ al, const WFrag<KS>& w, int lane,
                                        float (&acc)[4]) {
-    float cor[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] = 0.f;
+    // six independent accumulator chains (main / hi*lo / lo*hi, even / odd k steps): a single chain of dependent HMMAs
+    // (24 for K = 128) would cost ~30 cycles each with nothing else to issue in this warp
+    float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f},
+          d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
     const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), acol = 8 * (lane >> 4);
     const uint32_t ahb = smem_u32(ah + arow * LP + acol), alb = smem_u32(al + arow * LP + acol);
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        uint32_t fh[4], fl[4];
-        ldmatrix_x4(fh, ahb + ks * 32);
-        ldmatrix_x4(fl, alb + ks * 32);
-        mma_16816(acc, fh, w.b[ks].x, w.b[ks].y);
-        mma_16816(cor, fh, w.b[ks].z, w.b[ks].w);
-        mma_16816(cor, fl, w.b[ks].x, w.b[ks].y);
+    for (int ks = 0; ks < KS; ks += 2) {
+        uint32_t fh0[4], fl0[4], fh1[4], fl1[4];
+        ldmatrix_x4(fh0, ahb + ks * 32);
+        ldmatrix_x4(fl0, alb + ks * 32);
+        ldmatrix_x4(fh1, ahb + (ks + 1) * 32);
+        ldmatrix_x4(fl1, alb + (ks + 1) * 32);
+        mma_16816(m0, fh0, w.b[ks].x, w.b[ks].y);
+        mma_16816(c0, fh0, w.b[ks].z, w.b[ks].w);
+        mma_16816(d0, fl0, w.b[ks].x, w.b[ks].y);
+        mma_16816(m1, fh1, w.b[ks + 1].x, w.b[ks + 1].y);
+        mma_16816(c1, fh1, w.b[ks + 1].z, w.b[ks + 1].w);
+        mma_16816(d1, fl1, w.b[ks + 1].x, w.b[ks + 1].y);
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] = fmaf(cor[e], kLoScaleInv, acc[e]);
+    for (int e = 0; e < 4; ++e) acc[e] = fmaf((c0[e] + c1[e]) + (d0[e] + d1[e]), kLoScaleInv, m0[e] + m1[e]);
 }
 
 // self / instruction attention of this CTA's 16 rows: warp = head; q planes [16][LP] head-padded (carry hd^-1/2 log2 e),
@@ -314,6 +334,9 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
         mbar_init(s.kv_ready, CL);
         mbar_init(s.q_ready, CL);
         mbar_init(s.p_ready, CL);
+        mbar_init(s.vec_full, 1);
+        mbar_init(s.qv_full, 1);
+        mbar_init(s.qv_full + 1, 1);
         mbar_fence_init();
     }
     for (int i = tid; i < (4 * 64 + 4 * RB) * LP / 2; i += LT) reinterpret_cast<uint32_t*>(s.kh)[i] = 0u;   // all planes (pad columns stay 0)
@@ -368,13 +391,9 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
             const float2 x1 = *reinterpret_cast<const float2*>(tile + w * FPT + 64 + 2 * lane);
             v[0] = x0.x, v[1] = x0.y, v[2] = x1.x, v[3] = x1.y;
         };
-        auto st_row4 = [&](float* tile, const float (&v)[4]) {
-            *reinterpret_cast<float2*>(tile + w * FPT + 2 * lane) = make_float2(v[0], v[1]);
-            *reinterpret_cast<float2*>(tile + w * FPT + 64 + 2 * lane) = make_float2(v[2], v[3]);
-        };
-        auto ld_vec4 = [&](const float* p, float (&v)[4]) {           // a [128]-padded parameter vector
-            const float2 x0 = __ldg(reinterpret_cast<const float2*>(p + 2 * lane));
-            const float2 x1 = __ldg(reinterpret_cast<const float2*>(p + 64 + 2 * lane));
+        auto ld_vec4 = [&](const float* p, float (&v)[4]) {           // a [128]-padded parameter vector (shared or global)
+            const float2 x0 = *reinterpret_cast<const float2*>(p + 2 * lane);
+            const float2 x1 = *reinterpret_cast<const float2*>(p + 64 + 2 * lane);
             v[0] = x0.x, v[1] = x0.y, v[2] = x1.x, v[3] = x1.y;
         };
         auto ld_pe4 = [&](float (&v)[4]) {                            // waypoint embedding of this row ([E] floats, 8-byte aligned)
@@ -441,13 +460,13 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
         // GEMM epilogues.  Warp w owns output columns 8 w + 2 q4 + {0, 1} of rows g and g + 8.
         const int ocol = 8 * w + 2 * q4;
         auto epi_tile = [&](const float (&acc)[4], const float* bias, float* tile) {          // tile = acc + bias (fp32)
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ocol));
+            const float2 bb = *reinterpret_cast<const float2*>(bias + ocol);
             *reinterpret_cast<float2*>(tile + g * FPT + ocol) = make_float2(acc[0] + bb.x, acc[1] + bb.y);
             *reinterpret_cast<float2*>(tile + (g + 8) * FPT + ocol) = make_float2(acc[2] + bb.x, acc[3] + bb.y);
         };
         // head-padded planes of (rotary)(acc + bias): rows [prow0 + g, prow0 + g + 8] of a [.][LP] plane pair
         auto epi_heads = [&](const float (&acc)[4], const float* bias, bool rope, __half* ph, __half* pl, int prow0) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ocol));
+            const float2 bb = *reinterpret_cast<const float2*>(bias + ocol);
 #pragma unroll
             for (int hr = 0; hr < 2; ++hr) {
                 const int r = g + 8 * hr;
@@ -469,7 +488,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
         // (the K tile layout: conflict-free ldmatrix); this CTA writes rows row0 .. row0+15; pad slot 15 of every head = 0
         auto qx_at = [&](int hh_, int grow, int d) { return (hh_ * 64 + grow) * 16 + ((((d >> 3) ^ ((grow >> 2) & 1))) << 3) + (d & 7); };
         auto epi_qx = [&](const float (&acc)[4], const float* bias) {
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ocol));
+            const float2 bb = *reinterpret_cast<const float2*>(bias + ocol);
 #pragma unroll
             for (int hr = 0; hr < 2; ++hr) {
                 const int r = g + 8 * hr;
@@ -485,22 +504,37 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 }
             }
         };
-        // next cross-attention's Q from a residual tile: A = adaLN_12[layer](src + pe); qx = rotary(A Wq^T + bq)
-        auto make_q = [&](const float* src_tile, int layer, const float* ada_t) {
-            float v[4], pe[4];
-            ld_row4(src_tile, v);
-            ld_pe4(pe);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += pe[i];
-            const float* ada = ada_t + (size_t)layer * ADA_ROW;
-            modulate4(v, ada + 0, ada + EP);
-            st_planes4(s.ah, s.al, v);
+        // ---- per-layer parameter vectors staged in shared memory by bulk copies (issued by one thread, a layer ahead):
+        //      G = global layer index (step * nl + layer); block {C_BQ, adaLN row} of layer G in qv[G & 1], AdaV in vecs
+        auto issue_qv = [&](int G) {            // tid 0 only
+            const int st_ = G / a.nl, l_ = G - st_ * a.nl;
+            const int tt = __ldg(a.timesteps + st_);
+            float* dst = s.qv + (G & 1) * LoopSmem::QV;
+            mbar_expect_tx(s.qv_full + (G & 1), LoopSmem::QV * 4);
+            bulk_g2s(dst, a.ada_v[l_] + AdaV::C_BQ, EP * 4, s.qv_full + (G & 1));
+            bulk_g2s(dst + EP, a.ada + ((size_t)tt * a.nl + l_) * ADA_ROW, ADA_ROW * 4, s.qv_full + (G & 1));
+        };
+        auto issue_vecs = [&](int G) {          // tid 0 only; every warp has left the previous layer's last use of vecs
+            mbar_expect_tx(s.vec_full, AdaV::SIZE * 4);
+            bulk_g2s(s.vecs, a.ada_v[G % a.nl], AdaV::SIZE * 4, s.vec_full);
+        };
+        const int g_total = a.n_steps * a.nl;
+        // next cross-attention's Q from the residual row held in registers: A = adaLN_12[layer](x + pe); qx = rotary(A Wq^T + bq)
+        auto make_q = [&](const float (&src)[4], int layer, int G) {
             WFrag<8> wq;
             wq.load(a.ada_w[layer] + AdaW::C_WQ, 16, w, lane);
+            float v[4], pe[4];
+            ld_pe4(pe);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = src[i] + pe[i];
+            mbar_wait(s.qv_full + (G & 1), (G >> 1) & 1);
+            const float* qb = s.qv + (G & 1) * LoopSmem::QV;
+            modulate4(v, qb + EP, qb + 2 * EP);
+            st_planes4(s.ah, s.al, v);
             csync();
             float acc[4];
             gemm16<8>(s.ah, s.al, wq, lane, acc);
-            epi_qx(acc, a.ada_v[layer] + AdaV::C_BQ);
+            epi_qx(acc, qb);
             csync();
             // all-gather: this CTA's 16 rows of every head (512 contiguous bytes each) -> the same rows of the three peers
             // (they have all left the previous cross-attention: their K/V rows of that layer were needed to get here)
@@ -516,10 +550,8 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 for (int r = 0; r < CL; ++r) mbar_arrive_cluster(qr_remote[r]);
         };
         // regressor head Linear(E,E) -> ReLU -> Linear(E,d) on the tile `x` -> s.upd[r][col0 + d]  (uses the kv planes as scratch)
-        auto regress = [&](const float* x, const uint4* rw, const float* rv, int col0, int dim) {
-            float v[4];
-            ld_row4(x, v);
-            st_planes4(s.hh, s.hl, v);
+        auto regress = [&](const float (&x)[4], const uint4* rw, const float* rv, int col0, int dim) {
+            st_planes4(s.hh, s.hl, x);
             WFrag<8> w1, w2;
             w1.load(rw + MlpW::W1, 16, w, lane);
             if (w == 0) w2.load(rw + MlpW::W2, 16, 0, lane);
@@ -547,9 +579,15 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
             // the scratch rows go back to zero padding-clean state is not needed: rows 0..15 are fully rewritten by every all-gather
         };
 
+        if (tid == 0) {
+            issue_qv(0);
+            issue_vecs(0);
+        }
+        float xr[4], ys[4];            // residual row of this warp (row = warp) / output of the shared stack, in registers
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ys[i] = 0.f;
         for (int step = 0; step < a.n_steps; ++step) {
             const int tstep = __ldg(a.timesteps + step);
-            const float* ada_t = a.ada + (size_t)tstep * a.nl * ADA_ROW;
             // ============================================================ step begin: trajectory encoder (+ instruction attention)
             {
                 // Linear(9, E) + ReLU in fp32 (K = 9), straight into the GEMM planes
@@ -572,8 +610,9 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 csync();
                 float acc[4];
                 gemm16<8>(s.ah, s.al, w2, lane, acc);
-                epi_tile(acc, a.enc2_b, s.xs);
+                epi_tile(acc, a.enc2_b, s.t1);
                 csync();
+                ld_row4(s.t1, xr);
             }
             if (a.lang_w) {
                 // trajectory tokens attend to the instruction tokens (diffusion_head.py:330-336): x = LN(x + Wo attn((x + pe) Wq, K, V))
@@ -581,12 +620,12 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 wq.load(a.lang_w + LangW::WQ, 16, w, lane);
                 {
                     float v[4], pe[4];
-                    ld_row4(s.xs, v);
                     ld_pe4(pe);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] += pe[i];
+                    for (int i = 0; i < 4; ++i) v[i] = xr[i] + pe[i];
                     st_planes4(s.ah, s.al, v);
                 }
+                csync();                                           // every warp has read the encoder output out of t1
                 // instruction K / V (fp32, per sample) -> head-padded planes, all 64 rows
                 const float* lk = a.lang_k + (size_t)b * a.n_instr * E;
                 const float* lv = a.lang_vv + (size_t)b * a.n_instr * E;
@@ -610,27 +649,31 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 gemm16<8>(s.ah, s.al, wo, lane, acc);
                 epi_tile(acc, a.lang_v + LangV::BO, s.t1);
                 csync();
-                float v[4], t[4];
-                ld_row4(s.xs, v);
+                float t[4];
                 ld_row4(s.t1, t);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] += t[i];
-                layernorm4(v, a.lang_v + LangV::G12, a.lang_v + LangV::B12);
-                st_row4(s.xs, v);
-                __syncwarp();
+                for (int i = 0; i < 4; ++i) xr[i] += t[i];
+                layernorm4(xr, a.lang_v + LangV::G12, a.lang_v + LangV::B12);
             }
-            make_q(s.xs, 0, ada_t);
+            make_q(xr, 0, step * a.nl);
 
             for (int l = 0; l < a.nl; ++l) {
+#ifdef A3D_CDL_TRACE
+                const bool tr_on = (blockIdx.x == 21 && tid == 0 && step == 10 && l == 2);
+#endif
+                CDL_TRACE(0);
+                const int G = step * a.nl + l;
                 const uint4* lw = a.ada_w[l];
-                const float* lv = a.ada_v[l];
-                const float* ada = ada_t + (size_t)l * ADA_ROW;
+                const float* lv = s.vecs;                                      // AdaV of this layer (shared memory)
+                const float* ada = s.qv + (G & 1) * LoopSmem::QV + EP;         // adaLN row of (timestep, layer)
+                if (tid == 0 && G + 1 < g_total) issue_qv(G + 1);              // {C_BQ, adaLN row} of the next layer
                 // ======================================================== cross-attention over the cached context K/V
                 // Keys are split over the 4 CTAs; every CTA runs all 64 rows against its quarter of the tiles.
                 // warp = (head, 32-row half): two m16 tiles, online softmax per row; the unnormalised partials
                 // {O (15), denominator, row max} go to the CTA that owns the rows.
                 mbar_wait_cluster(s.q_ready, xphase & 1);          // rotary Q of all 64 rows has landed (and the K/V planes of
                                                                    // every CTA are idle: they double as the partial buffers)
+                CDL_TRACE(1);
                 {
                     const int h = w & 7, rhalf = w >> 3;
                     uint32_t qf[2][4];
@@ -717,6 +760,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(s.empty + slot);
                     }
+                CDL_TRACE(2);
                     gtile += my_tiles;
                     // ---- partials -> the owner of the rows: m tile mt of this warp = rows of CTA 2 rhalf + mt
                     //      owner layout part[source CTA][head][17][16 rows] (floats)
@@ -734,12 +778,14 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                         }
                     }
                 }
+                CDL_TRACE(3);
                 WFrag<8> wo;                                       // out-projection weights: in flight during the exchange
                 wo.load(lw + AdaW::C_WO, 16, w, lane);
                 csync();
                 if (tid == 0)
                     for (int r = 0; r < CL; ++r) mbar_arrive_cluster(pr_remote[r]);
                 mbar_wait_cluster(s.p_ready, xphase & 1);          // the partials of all four key quarters are here
+                CDL_TRACE(4);
                 // ---- merge: warp = head, lane = (row, 8-wide half of the head dimension)
                 if (w < H) {
                     const int h = w, r = lane & 15, dh = lane >> 4;
@@ -771,6 +817,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     }
                 }
                 csync();
+                CDL_TRACE(5);
                 // the partial buffer (= K/V planes) of this CTA is free: peers may write their K / V rows of this layer
                 if (tid == 0)
                     for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvf_remote[r]);
@@ -778,6 +825,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     // ---- out projection + residual + LN_12                                       (layers.py:146-147)
                     float acc[4];
                     gemm16<8>(s.ah, s.al, wo, lane, acc);
+                    mbar_wait(s.vec_full, G & 1);                  // this layer's parameter vectors have landed (issued a layer ago)
                     epi_tile(acc, lv + AdaV::C_BO, s.t1);
                 }
                 WFrag<8> wv, wk;
@@ -786,12 +834,12 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 csync();
                 {
                     float v[4], t[4], pe[4];
-                    ld_row4(s.xs, v);
                     ld_row4(s.t1, t);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] += t[i];
-                    layernorm4(v, lv + AdaV::G12, lv + AdaV::B12);
-                    st_row4(s.xs, v);
+                    for (int i = 0; i < 4; ++i) xr[i] += t[i];
+                    layernorm4(xr, lv + AdaV::G12, lv + AdaV::B12);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = xr[i];
                     // ---- self-attention inputs: q = k = adaLN_1(x + pe) -> (ah, al); v = adaLN_1(x) -> (hh, hl)   (layers.py:165-182)
                     ld_pe4(pe);
                     float qk[4];
@@ -803,8 +851,10 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     st_planes4(s.hh, s.hl, v);
                 }
                 csync();
+                CDL_TRACE(6);
                 // every CTA has released the K/V planes of its previous use (end of the previous layer / step begin)
                 mbar_wait_cluster(s.kv_free, xphase & 1);
+                CDL_TRACE(7);
                 {
                     float acc[4];
                     gemm16<8>(s.hh, s.hl, wv, lane, acc);
@@ -812,6 +862,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     gemm16<8>(s.ah, s.al, wk, lane, acc);
                     epi_heads(acc, lv + AdaV::S_BK, true, s.kh, s.kl, row0);
                 }
+                CDL_TRACE(8);
                 WFrag<8> wq;
                 wq.load(lw + AdaW::S_WQ, 16, w, lane);
                 csync();                                           // own rows of K / V complete; (hh, hl) free for Q
@@ -837,24 +888,27 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 csync();                                           // remote stores issued by every thread; Q planes complete
                 if (tid == 0)
                     for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvr_remote[r]);
+                CDL_TRACE(9);
                 mbar_wait_cluster(s.kv_ready, xphase & 1);         // all four row blocks of K / V have landed here
                 ++xphase;
+                CDL_TRACE(10);
                 if (w < H) mha16(w, lane, s.hh, s.hl, s.kh, s.kl, s.vh, s.vl, a.nrows, a.mask ? s.kmask : nullptr, s.ah, s.al);
                 csync();
+                CDL_TRACE(11);
                 {
                     float acc[4];
                     gemm16<8>(s.ah, s.al, wso, lane, acc);
                     epi_tile(acc, lv + AdaV::S_BO, s.t1);
                 }
                 csync();
+                CDL_TRACE(12);
                 // ---- x = LN_1(x + sa); y = adaLN_ff(x); FFN                                      (layers.py:183-209)
                 float yv[4];
                 {
                     float v[4], t[4];
-                    ld_row4(s.xs, v);
                     ld_row4(s.t1, t);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] += t[i];
+                    for (int i = 0; i < 4; ++i) v[i] = xr[i] + t[i];
                     layernorm4(v, lv + AdaV::G1, lv + AdaV::B1N);
                     modulate4(v, ada + 4 * EP, ada + 5 * EP);
 #pragma unroll
@@ -873,7 +927,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                         gemm16<8>(s.ah, s.al, w1, lane, acc);
                         if (ch + 1 < FFP / 128) w1.load(lw + AdaW::W1, 64, 16 * (ch + 1) + w, lane);
                         {
-                            const float2 bb = __ldg(reinterpret_cast<const float2*>(lv + AdaV::B1 + 128 * ch + ocol));
+                            const float2 bb = *reinterpret_cast<const float2*>(lv + AdaV::B1 + 128 * ch + ocol);
                             uint32_t h0, l0, h1, l1;
                             split_h2(fmaxf(acc[0] + bb.x, 0.f), fmaxf(acc[1] + bb.y, 0.f), h0, l0);
                             split_h2(fmaxf(acc[2] + bb.x, 0.f), fmaxf(acc[3] + bb.y, 0.f), h1, l1);
@@ -891,31 +945,33 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                     epi_tile(sum, lv + AdaV::B2, s.t1);
                 }
                 csync();
+                CDL_TRACE(14);
                 // ---- layer output x' = LN_122(y + FFN(y)); routing of the position / rotation heads   (diffusion_head.py:338-363)
                 const int last_shared = a.n_traj - 1, p1 = a.n_traj + 1, r1 = a.n_traj + 3;
                 {
-                    float v[4], t[4];
+                    float t[4];
                     ld_row4(s.t1, t);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = yv[i] + t[i];
-                    layernorm4(v, lv + AdaV::G122, lv + AdaV::B122);
-                    st_row4(s.xs, v);
-                    if (l == last_shared) st_row4(s.ysave, v);     // both heads start from the output of the shared stack
-                    __syncwarp();
+                    for (int i = 0; i < 4; ++i) xr[i] = yv[i] + t[i];
+                    layernorm4(xr, lv + AdaV::G122, lv + AdaV::B122);
+                    if (l == last_shared) {                        // both heads start from the output of the shared stack
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ys[i] = xr[i];
+                    }
                 }
+                csync();                                           // every warp is done with this layer's vectors (and with t1)
+                if (tid == 0 && G + 1 < g_total) issue_vecs(G + 1);
                 if (l == p1) {
-                    csync();
-                    regress(s.xs, a.pos_w, a.pos_v, 0, 3);
+                    regress(xr, a.pos_w, a.pos_v, 0, 3);
                     // the rotation head restarts from the shared-stack output
-                    float v[4];
-                    ld_row4(s.ysave, v);
-                    st_row4(s.xs, v);
-                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xr[i] = ys[i];
                 } else if (l == r1) {
-                    csync();
-                    regress(s.xs, a.rot_w, a.rot_v, 3, 6);
+                    regress(xr, a.rot_w, a.rot_v, 3, 6);
                 }
-                if (l + 1 < a.nl) make_q(s.xs, l + 1, ada_t);
+                CDL_TRACE(15);
+                if (l + 1 < a.nl) make_q(xr, l + 1, G + 1);
+                CDL_TRACE(16);
             }
             // ============================================================ denoiser output + DDPM posterior step
             // (diffusion_head.py:271-274: position is residual on the noisy input, rotation is direct;
@@ -953,6 +1009,12 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
 
 using namespace a3d;
 using namespace a3d::cd;
+
+#ifdef A3D_CDL_TRACE
+extern "C" int cd_loop_trace_read(long long* host) {
+    return cudaMemcpyFromSymbol(host, g_cdl_trace, sizeof(g_cdl_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int cd_denoise_loop(float* traj, int batch, int length, int n_steps, const float* cond, const unsigned char* cond_mask,
                                const unsigned char* mask, const float* wp_pe, const int* timesteps, const float* ada,
