@@ -226,6 +226,198 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
     }
 }
 
+// ------------------------------------------------------------------ cluster variant (n <= 65536)
+// The single-CTA kernel above is latency-bound (150 us at 65536 points: four passes that recompute every distance, one
+// SM per sample).  Here a thread-block cluster of 8 CTAs owns a sample: every CTA takes a contiguous eighth of the points
+// and keeps its keys IN REGISTERS (<= 8 per thread, computed once from one coalesced read of the points), so the radix
+// passes touch no memory but shared-memory histograms; the 8 histograms are combined in the leader CTA through
+// distributed shared memory (remote atomics), the survivors are written into the leader's buffer at offsets derived from
+// the per-CTA counts (CTA rank order == index order, so exact ties keep the lowest indices), and the leader sorts them.
+// Same keys, same tie rule, same output as topk_kernel: bit-exact.
+constexpr int kTopkCluster = 8;
+constexpr int kKeysPerThread = 8;
+
+template <bool kTraj>
+__global__ void __cluster_dims__(kTopkCluster, 1, 1) __launch_bounds__(kTopkThreads, 1)
+    topk_cluster_kernel(const float* __restrict__ center, int traj_len, const float* __restrict__ pts, int n, int k,
+                        int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    extern __shared__ unsigned long long sh_sel[];   // leader: next_pow2(k) composites (key << 32 | idx)
+    __shared__ uint32_t hist[2048];                  // this CTA's histogram of the current pass
+    __shared__ uint32_t ghist[2][2048];              // leader: cluster-wide histogram, double-buffered over the passes
+    __shared__ uint32_t sh_scan[32];
+    __shared__ uint32_t sh_res[2];
+    __shared__ uint32_t sh_below[kTopkCluster], sh_ties[kTopkCluster];   // per-CTA counts, replicated in every CTA
+    __shared__ uint32_t sh_cnt[2];
+    __shared__ float sh_c[3 * 64];
+
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    auto remote = [](const void* p, uint32_t r) {    // address of the same shared-memory object in CTA r of the cluster
+        uint32_t a = (uint32_t)__cvta_generic_to_shared(p), o;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(o) : "r"(a), "r"(r));
+        return o;
+    };
+    auto cluster_sync = []() {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    };
+    const int b = blockIdx.x / kTopkCluster;
+    const int t = threadIdx.x;
+    const float* p = pts + (long)b * n * 3;
+    const int clen = kTraj ? traj_len : 1;
+    for (int i = t; i < 3 * clen; i += blockDim.x) sh_c[i] = center[(long)b * 3 * clen + i];
+    for (int i = t; i < 2 * 2048; i += blockDim.x) (&ghist[0][0])[i] = 0;
+    __syncthreads();
+
+    // ---- this CTA's points: [lo, hi), thread t owns lo + j * 1024 + t
+    const int per = (n + kTopkCluster - 1) / kTopkCluster;
+    const int lo = min((int)rank * per, n), hi = min(lo + per, n);
+    uint32_t key[kKeysPerThread];
+#pragma unroll
+    for (int j = 0; j < kKeysPerThread; ++j) {
+        const int i = lo + j * kTopkThreads + t;
+        key[j] = (i < hi) ? dist_key<kTraj>(p, i, sh_c, traj_len) : 0xffffffffu;
+    }
+    const uint32_t my_valid = (uint32_t)max(0, min(kKeysPerThread, (hi - lo - t + kTopkThreads - 1) / kTopkThreads));
+    cluster_sync();                                   // the leader's histograms are zeroed before anyone adds to them
+
+    uint32_t prefix = 0, need = (uint32_t)k, fixed_mask = 0;
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = t; i < 2048; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const int sh = shifts[pass];
+        const uint32_t bm = (1u << widths[pass]) - 1u;
+#pragma unroll
+        for (int j = 0; j < kKeysPerThread; ++j)
+            if ((uint32_t)j < my_valid && (key[j] & fixed_mask) == prefix) atomicAdd(&hist[(key[j] >> sh) & bm], 1u);
+        __syncthreads();
+        {   // this CTA's bins -> the leader's histogram of this pass (remote shared-memory reductions)
+            const uint32_t g = remote(&ghist[pass & 1][0], 0);
+            for (int i = t; i < (1 << widths[pass]); i += blockDim.x) {
+                const uint32_t v = hist[i];
+                if (v) asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(g + 4u * i), "r"(v) : "memory");
+            }
+        }
+        cluster_sync();
+        if (rank == 0) {
+            find_bin(ghist[pass & 1], 1 << widths[pass], need, sh_scan, sh_res);
+            for (int i = t; i < 2048; i += blockDim.x) ghist[pass & 1][i] = 0;   // ready for pass + 2
+        }
+        cluster_sync();
+        {   // everybody reads the leader's verdict
+            uint32_t r0, r1;
+            const uint32_t a = remote(sh_res, 0);
+            asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(r0) : "r"(a));
+            asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(r1) : "r"(a + 4u));
+            prefix |= r0 << sh;
+            fixed_mask |= bm << sh;
+            need -= r1;
+        }
+        cluster_sync();                               // sh_res may be rewritten by the next pass only after all have read it
+    }
+    const uint32_t kth = prefix, ties_wanted = need, n_below = (uint32_t)k - ties_wanted;
+
+    // ---- counts of this CTA -> every CTA
+    if (t == 0) {
+        sh_cnt[0] = 0;
+        sh_cnt[1] = 0;
+    }
+    __syncthreads();
+    {
+        uint32_t nb = 0, nt = 0;
+#pragma unroll
+        for (int j = 0; j < kKeysPerThread; ++j)
+            if ((uint32_t)j < my_valid) {
+                nb += key[j] < kth;
+                nt += key[j] == kth;
+            }
+        nb = __reduce_add_sync(0xffffffffu, nb);
+        nt = __reduce_add_sync(0xffffffffu, nt);
+        if ((t & 31) == 0) {
+            atomicAdd(&sh_cnt[0], nb);
+            atomicAdd(&sh_cnt[1], nt);
+        }
+    }
+    __syncthreads();
+    if (t < kTopkCluster) {
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote(&sh_below[rank], t)), "r"(sh_cnt[0]) : "memory");
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote(&sh_ties[rank], t)), "r"(sh_cnt[1]) : "memory");
+    }
+    int kp = 1;
+    while (kp < k) kp <<= 1;
+    if (rank == 0)
+        for (int i = t; i < kp; i += blockDim.x) sh_sel[i] = ~0ull;
+    cluster_sync();
+    uint32_t base_below = 0, base_tie = 0;
+    for (uint32_t r = 0; r < rank; ++r) {
+        base_below += sh_below[r];
+        base_tie += sh_ties[r];
+    }
+    // ---- survivors -> the leader's buffer
+    if (t == 0) {
+        sh_cnt[0] = 0;
+        sh_cnt[1] = 0;
+    }
+    __syncthreads();
+    const uint32_t sel0 = remote(sh_sel, 0);
+#pragma unroll
+    for (int j = 0; j < kKeysPerThread; ++j) {
+        const bool ok = (uint32_t)j < my_valid;
+        const uint32_t i = (uint32_t)(lo + j * kTopkThreads + t);
+        if (ok && key[j] < kth) {
+            const uint32_t slot = base_below + atomicAdd(&sh_cnt[0], 1u);
+            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(sel0 + 8u * slot), "l"(((unsigned long long)key[j] << 32) | i) : "memory");
+        }
+        // ties in index order: (ties of lower ranks) + (earlier chunks of this CTA) + (lower threads of this chunk)
+        const bool tie = ok && key[j] == kth;
+        const unsigned bal = __ballot_sync(0xffffffffu, tie);
+        if (__syncthreads_or(tie)) {
+            const int lane = t & 31, wid = t >> 5;
+            if (lane == 0) sh_scan[wid] = __popc(bal);
+            __syncthreads();
+            uint32_t before = base_tie + sh_cnt[1];
+            for (int w2 = 0; w2 < wid; ++w2) before += sh_scan[w2];
+            const uint32_t trank = before + __popc(bal & ((1u << lane) - 1u));
+            if (tie && trank < ties_wanted)
+                asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(sel0 + 8u * (n_below + trank)), "l"(((unsigned long long)key[j] << 32) | i)
+                             : "memory");
+            __syncthreads();
+            if (t == 0) {
+                uint32_t tot = 0;
+                for (int w2 = 0; w2 < 32; ++w2) tot += sh_scan[w2];
+                sh_cnt[1] += tot;
+            }
+            __syncthreads();
+        }
+    }
+    cluster_sync();                                   // all survivors have landed in the leader
+    if (rank != 0) return;
+
+    // ---- bitonic sort of kp composites (padding = ~0 sorts last)
+    for (int size = 2; size <= kp; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < (kp >> 1); i += blockDim.x) {
+                const int l2 = 2 * i - (i & (stride - 1));
+                const int h2 = l2 + stride;
+                const bool up = ((l2 & size) == 0);
+                const unsigned long long a = sh_sel[l2], c2 = sh_sel[h2];
+                if ((a > c2) == up) {
+                    sh_sel[l2] = c2;
+                    sh_sel[h2] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < k; i += blockDim.x) {
+        const unsigned long long v = sh_sel[i];
+        idx_out[(long)b * k + i] = (int32_t)(uint32_t)(v & 0xffffffffu);
+        if (dist_out) dist_out[(long)b * k + i] = __uint_as_float((uint32_t)(v >> 32));
+    }
+}
+
 // =================================================================== token gather
 // tok[b][r][c] = feat[b*ncam + cam][c][pix],  (cam, pix) = divmod(idx[b][r], hw); pos likewise.
 // A block moves 32 tokens x E channels through a padded shared tile so that the scattered
@@ -456,6 +648,17 @@ static int launch_topk(bool traj, const float* center, int traj_len, const float
     int kp = 1;
     while (kp < k) kp <<= 1;
     const size_t smem = (size_t)kp * sizeof(unsigned long long);
+    if (n <= kTopkCluster * kKeysPerThread * kTopkThreads && n >= 4096) {
+        // cluster of 8 CTAs per sample, keys in registers (see topk_cluster_kernel)
+        if (traj) {
+            cudaFuncSetAttribute(topk_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            topk_cluster_kernel<true><<<batch * kTopkCluster, kTopkThreads, smem, (cudaStream_t)stream>>>(center, traj_len, pts, n, k, idx, dist);
+        } else {
+            cudaFuncSetAttribute(topk_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            topk_cluster_kernel<false><<<batch * kTopkCluster, kTopkThreads, smem, (cudaStream_t)stream>>>(center, 1, pts, n, k, idx, dist);
+        }
+        return check_launch("a3d_topk(cluster)");
+    }
     if (traj) {
         cudaFuncSetAttribute(topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         topk_kernel<true><<<batch, kTopkThreads, smem, (cudaStream_t)stream>>>(center, traj_len, pts, n, k, idx, dist);

@@ -167,6 +167,10 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+// every thread that wrote into a peer's shared memory orders those stores at cluster scope BEFORE the block barrier after
+// which one thread announces them with a release-arrive (a release by that one thread does not cover the other warps'
+// in-flight remote stores: seen as a rare run-to-run difference before this fence was added)
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }   // the 16 compute warps
 
 __device__ __forceinline__ int head_slot16(int c) { return c + c / HD; }
@@ -545,6 +549,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 for (int r = 0; r < CL; ++r)
                     if (r != (int)rank) st_cluster_v4(qx_remote[r] + off, val);
             }
+            fence_cluster();
             csync();
             if (tid == 0)
                 for (int r = 0; r < CL; ++r) mbar_arrive_cluster(qr_remote[r]);
@@ -781,6 +786,7 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 CDL_TRACE(3);
                 WFrag<8> wo;                                       // out-projection weights: in flight during the exchange
                 wo.load(lw + AdaW::C_WO, 16, w, lane);
+                fence_cluster();
                 csync();
                 if (tid == 0)
                     for (int r = 0; r < CL; ++r) mbar_arrive_cluster(pr_remote[r]);
@@ -885,7 +891,8 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 }
                 WFrag<8> wso;
                 wso.load(lw + AdaW::S_WO, 16, w, lane);
-                csync();                                           // remote stores issued by every thread; Q planes complete
+                fence_cluster();
+                csync();                                           // remote stores ordered by every thread; Q planes complete
                 if (tid == 0)
                     for (int r = 0; r < CL; ++r) mbar_arrive_cluster(kvr_remote[r]);
                 CDL_TRACE(9);

@@ -172,32 +172,38 @@ def run_planner(rank, world, device, iters=3):
 
 
 def _ddp(model, local, world):
-    """Stock DistributedDataParallel as the reference wraps its models (engine.py:121-124: find_unused_parameters=True,
-    broadcast_buffers=False) plus static_graph / gradient_as_bucket_view: the set of unused parameters (6 FPN tensors,
-    SURVEY App. B.2) is the same every step, so DDP records it once instead of walking the autograd graph per step."""
+    """Stock DistributedDataParallel exactly as the reference wraps its models (engine.py:121-124:
+    find_unused_parameters=True because 6 FPN tensors get no gradient; broadcast_buffers=False), plus
+    gradient_as_bucket_view (gradients live in the all-reduce buckets: no copy in / out)."""
     if world == 1:
         return model
     return torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
-                                                     find_unused_parameters=True, static_graph=True,
-                                                     gradient_as_bucket_view=True)
+                                                     find_unused_parameters=True, gradient_as_bucket_view=True)
 
 
-def _ddp_gradient_check(model, net, step_loss, reseed, world, device):
-    """Once per run under N > 1: the gradients DDP leaves on every rank equal the mean over ranks of the gradients each
-    rank computes alone on its own shard (NCCL all-reduce of gradients only), and are identical on all ranks."""
+def _local_mean_gradients(model, step_loss, reseed, world):
+    """Gradients of this rank's own shard, computed on the bare module BEFORE it is wrapped in DDP, averaged over the
+    ranks with a plain all-reduce: what DDP's bucketed all-reduce must reproduce."""
     params = [p for p in model.parameters() if p.requires_grad]
     reseed()
     model.zero_grad(set_to_none=True)
-    step_loss(model).backward()                                  # local gradients, no DDP hooks
-    local = [torch.zeros_like(p) if p.grad is None else p.grad.detach().clone() for p in params]
-    for g in local:
+    step_loss(model).backward()
+    mean = [torch.zeros_like(p) if p.grad is None else p.grad.detach().clone() for p in params]
+    for g in mean:
         torch.distributed.all_reduce(g)
         g /= world
-    reseed()
     model.zero_grad(set_to_none=True)
+    return mean
+
+
+def _ddp_gradient_check(model, net, mean, step_loss, reseed):
+    """Once per run under N > 1: the gradients DDP leaves on every rank equal the all-reduced mean of the per-rank
+    gradients (NCCL all-reduce of gradients only) and are identical on all ranks."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    reseed()
     step_loss(net).backward()                                    # through DDP: bucketed all-reduce
     worst = 0.0
-    for p, want in zip(params, local):
+    for p, want in zip(params, mean):
         got = torch.zeros_like(p) if p.grad is None else p.grad.detach()
         lo, hi = got.clone(), got.clone()
         torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
@@ -206,7 +212,6 @@ def _ddp_gradient_check(model, net, step_loss, reseed, world, device):
         denom = want.abs().max().item() + 1e-12
         worst = max(worst, (got - want).abs().max().item() / denom)
     assert worst <= 1e-4, f"DDP gradients differ from the all-reduced mean of the per-rank gradients: {worst:.2e}"
-    model.zero_grad(set_to_none=True)
     return worst
 
 
@@ -238,8 +243,6 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
                   gripper_loc_bounds=synth.BOUNDS, num_ghost_points=w["ghost_total"], num_sampling_level=3,
                   use_instruction=True).to(device).train()
     model.seed_ghost_sampler(99 + rank)
-    net = _ddp(model, local, world)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     rgb, pcd, instr, grip = [t.to(device) for t in act3d_inputs(w["batch"], w["ncam"], seed=300 + rank)]
     gt = grip.clone()
     gt[:, :3] += 0.02
@@ -248,6 +251,11 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
         out = m(rgb, pcd, instr, grip, gt_action=gt)
         return sum(keypose_loss(out, gt).values())
 
+    reseed = lambda: model.seed_ghost_sampler(99 + rank)
+    mean = _local_mean_gradients(model, step_loss, reseed, world) if world > 1 else None
+    net = _ddp(model, local, world)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+
     def step():
         loss = step_loss(net)
         opt.zero_grad(set_to_none=True)
@@ -255,12 +263,10 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
         opt.step()
         return loss
 
-    check = None
-    if world > 1:
-        check = _ddp_gradient_check(model, net, step_loss, lambda: model.seed_ghost_sampler(99 + rank), world, device)
+    check = _ddp_gradient_check(model, net, mean, step_loss, reseed) if world > 1 else None
     ms, loss = _time_train(step, world, device, iters, warmup)
     out = {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
-           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only, static graph)",
+           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
            "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
                        "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
     if check is not None:
@@ -274,8 +280,6 @@ def run_train_planner(rank, world, device, local, iters=6, warmup=3):
     w = PLANNER_WORKLOAD
     torch.manual_seed(0)
     model = build_planner().to(device).train()
-    net = _ddp(model, local, world)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     mask, rgb, pcd, instr, cur, goal = [t.to(device) for t in planner_inputs(w["batch"], w["ncam"], w["length"], 500 + rank)]
     g = torch.Generator().manual_seed(700 + rank)
     alpha = torch.linspace(0, 1, w["length"]).view(1, -1, 1)
@@ -286,6 +290,11 @@ def run_train_planner(rank, world, device, local, iters=6, warmup=3):
     def step_loss(m):
         return m(gt_traj, mask, rgb, pcd, instr, cur, goal)
 
+    reseed = lambda: torch.manual_seed(1234 + rank)
+    mean = _local_mean_gradients(model, step_loss, reseed, world) if world > 1 else None
+    net = _ddp(model, local, world)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+
     def step():
         loss = step_loss(net)
         opt.zero_grad(set_to_none=True)
@@ -293,13 +302,11 @@ def run_train_planner(rank, world, device, local, iters=6, warmup=3):
         opt.step()
         return loss
 
-    check = None
-    if world > 1:
-        check = _ddp_gradient_check(model, net, step_loss, lambda: torch.manual_seed(1234 + rank), world, device)
+    check = _ddp_gradient_check(model, net, mean, step_loss, reseed) if world > 1 else None
     ms, loss = _time_train(step, world, device, iters, warmup)
     nbytes = sum(p.numel() * 4 for p in model.parameters() if p.requires_grad)
     out = {"metric": "train trajectories/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
-           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only, static graph)",
+           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
            "gradient_bytes": int(nbytes),
            "workload": f"ChainedDiffuser training step: {w['batch']} trajectories/GPU, {w['length']} waypoints, 4 views 256x256, "
                        "E=120 H=8, frozen ResNet-50, fp32, AdamW"}

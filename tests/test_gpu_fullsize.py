@@ -110,12 +110,12 @@ def test_planner_c3_properties():
     goal = synth.gripper_pose("c3.goal", bsz, 1, with_open=False).cuda()
     mask = torch.zeros(bsz, length, dtype=torch.bool, device="cuda")
     outs = []
-    for _ in range(2):
-        m._noise_fn = synth.NoiseStream("c3")
+    for _ in range(6):      # the persistent cluster kernel exchanges rows through distributed shared memory: any ordering
+        m._noise_fn = synth.NoiseStream("c3")                                   # hole shows up as a run-to-run difference
         outs.append(m.compute_trajectory(mask, rgb, pcd, instr, cur, goal))
     a = outs[0]
     assert a.shape == (bsz, length, 7) and torch.isfinite(a).all()
-    assert torch.equal(a, outs[1])                                              # deterministic (graph replay included)
+    assert all(torch.equal(a, o) for o in outs[1:])                             # deterministic
     assert (a[:, 0, :3] - cur[:, :3]).abs().max() <= 1e-5                        # inpainted start pose
     assert torch.allclose(a[..., 3:].norm(dim=-1), torch.ones(bsz, length, device="cuda"), atol=1e-4)
     # batch rows are independent: the first 8 samples alone give the same trajectories
