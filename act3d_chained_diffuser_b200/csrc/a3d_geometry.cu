@@ -585,7 +585,8 @@ struct Bounds6 {
 
 __global__ void __launch_bounds__(256) sample_ghost_kernel(const float* __restrict__ anchor, float radius, Bounds6 bd,
                                                            int batch, int ng, uint64_t seed, uint64_t stream_id,
-                                                           float* __restrict__ out) {
+                                                           const uint64_t* __restrict__ stream_base, float* __restrict__ out) {
+    if (stream_base) stream_id += *stream_base;      // device-resident call counter: fresh points on every CUDA-graph replay
     const long total = (long)batch * ng;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int b = (int)(i / ng);
@@ -619,6 +620,8 @@ __global__ void __launch_bounds__(256) sample_ghost_kernel(const float* __restri
         out[i * 3 + 2] = p[2];
     }
 }
+
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { *ctr += inc; }
 
 }  // namespace a3d
 
@@ -721,8 +724,27 @@ extern "C" int a3d_argmax_pick(const float* logits, const float* ghost, int batc
     return check_launch("a3d_argmax_pick");
 }
 
+extern "C" int a3d_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+    A3D_REQUIRE(counter, "a3d_counter_add: null pointer");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+    return check_launch("a3d_counter_add");
+}
+
+static int sample_ghost_impl(const float* anchor, float radius, const float* bounds_host, int batch, int ng, uint64_t seed,
+                             uint64_t stream_id, const uint64_t* stream_base, float* out, void* stream);
+
 extern "C" int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
                                 uint64_t seed, uint64_t stream_id, float* out, void* stream) {
+    return sample_ghost_impl(anchor, radius, bounds_host, batch, ng, seed, stream_id, nullptr, out, stream);
+}
+extern "C" int a3d_sample_ghost_ctr(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
+                                    uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, float* out, void* stream) {
+    A3D_REQUIRE(stream_base, "a3d_sample_ghost_ctr: null counter");
+    return sample_ghost_impl(anchor, radius, bounds_host, batch, ng, seed, stream_id, stream_base, out, stream);
+}
+
+static int sample_ghost_impl(const float* anchor, float radius, const float* bounds_host, int batch, int ng, uint64_t seed,
+                             uint64_t stream_id, const uint64_t* stream_base, float* out, void* stream) {
     A3D_REQUIRE(bounds_host && out && batch > 0 && ng > 0, "a3d_sample_ghost: bad arguments");
     A3D_REQUIRE(!anchor || radius > 0.f, "a3d_sample_ghost: radius must be positive with an anchor");
     Bounds6 bd;
@@ -732,6 +754,6 @@ extern "C" int a3d_sample_ghost(const float* anchor, float radius, const float* 
     }
     const long total = (long)batch * ng;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    sample_ghost_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(anchor, radius, bd, batch, ng, seed, stream_id, out);
+    sample_ghost_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(anchor, radius, bd, batch, ng, seed, stream_id, stream_base, out);
     return check_launch("a3d_sample_ghost");
 }

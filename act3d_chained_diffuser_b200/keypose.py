@@ -99,6 +99,13 @@ class Act3D(nn.Module):
         self._profile_events = None         # bench hook: list collecting (tag, start, end) CUDA events
         self.fold_trunk = True              # eval: BN-folded channels-last copy of the frozen backbone (trunk.EvalTrunk)
         self.overlap_query = True           # run the 1-token query stack on a side stream next to the ghost stack
+        self.use_cuda_graph = False         # inference on CUDA inputs: capture the whole forward once per input signature and
+                                            # replay it (no host launch cost: matters at small batches / online evaluation);
+                                            # the big feature / point pyramids of the returned dict then alias static buffers
+                                            # that the next call overwrites
+        self._graphs = {}
+        self._graph_counter = None          # device call counter of the ghost sampler while a graph is being captured
+        self._graph_counter_buf = None
         self._side_stream_obj = None
         self._eval_trunk = EvalTrunk()
 
@@ -125,18 +132,25 @@ class Act3D(nn.Module):
     def seed_ghost_sampler(self, seed):
         """Seed of the device-side Philox ghost sampler (the reference draws from numpy's global RNG)."""
         self._sampler_seed, self._sampler_calls = int(seed), 0
+        if self._graph_counter_buf is not None:
+            self._graph_counter_buf.zero_()
 
     def _sample_ghost_points(self, total_timesteps, device, level, anchor=None):
         """(B, Ng, 3) uniform ghost points; same contract as act3d.py:394-440 but sampled on the
         device (no anchor.cpu() round trip).  Ng switches on self.training like the reference."""
         n = self.num_ghost_points if self.training else self.num_ghost_points_val
-        self._sampler_calls += 1
+        ctr = self._graph_counter            # inside a CUDA-graph capture: the call counter lives on the device
+        if ctr is None:
+            self._sampler_calls += 1
+            sid = self._sampler_calls
+        else:
+            sid = level + 1                  # + the device counter, advanced by num_sampling_level per replay
         if level == 0:
             return lib.sample_ghost(None, 0.0, self.gripper_loc_bounds, total_timesteps, n,
-                                    self._sampler_seed, self._sampler_calls, device)
+                                    self._sampler_seed, sid, device, counter=ctr)
         anc = anchor[:, 0].detach().contiguous().float()
         return lib.sample_ghost(anc, self.sampling_ball_diameter_pyramid[level] / 2, self.gripper_loc_bounds,
-                                total_timesteps, n, self._sampler_seed, self._sampler_calls, device)
+                                total_timesteps, n, self._sampler_seed, sid, device, counter=ctr)
 
     # ------------------------------------------------------------------ visual trunk
     def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras, staged=None):
@@ -197,6 +211,61 @@ class Act3D(nn.Module):
                 torch.cuda.current_stream().wait_stream(self._side_stream)
                 visible_pcd, instruction, curr_gripper, gt_action = staged
             return self._forward_train(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
+        if (self.use_cuda_graph and staged is None and self._teacher_positions is None and self._profile_events is None
+                and "_sample_ghost_points" not in self.__dict__ and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_graphed(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
+        return self._forward_infer(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action, staged)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the inference forward
+    def _forward_graphed(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action):
+        """The forward has no host synchronisation (sampler, top-k, argmax all stay on the device), so the ~150 launches
+        of one call are captured once per (input shapes, parameter versions, sampler seed) and replayed.  Ghost points
+        stay fresh: the sampler's call counter lives on the device and is advanced inside the graph."""
+        inputs = [visible_rgb, visible_pcd, instruction, curr_gripper, gt_action]
+        key = (tuple(tuple(t.shape) + (str(t.dtype),) if t is not None else None for t in inputs), self.training,
+               str(visible_rgb.device), self._sampler_seed, self.overlap_query,
+               tuple(p._version for p in self.parameters()), tuple(bf._version for bf in self.buffers()))
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = visible_rgb.device
+            static_in = [t.detach().clone() if t is not None else None for t in inputs]
+            main = torch.cuda.current_stream()
+            warm = torch.cuda.Stream(device=dev)
+            warm.wait_stream(main)
+            with torch.cuda.stream(warm):              # cuDNN autotuning, weight packing, kernel attributes: outside the capture
+                for _ in range(2):
+                    self._forward_infer(*static_in, None)
+            main.wait_stream(warm)
+            torch.cuda.synchronize(dev)
+            if self._graph_counter_buf is None:
+                self._graph_counter_buf = torch.zeros(1, dtype=torch.int64, device=dev)
+            graph = torch.cuda.CUDAGraph()
+            self._graph_counter = self._graph_counter_buf
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._forward_infer(*static_in, None)
+                    lib.counter_add(self._graph_counter_buf, self.num_sampling_level)
+            finally:
+                self._graph_counter = None
+            if len(self._graphs) >= 4:                 # bounded: a graph pins its activations (hundreds of MB at batch 16)
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = (graph, static_in, out)
+        graph, static_in, out = entry
+        for dst, src in zip(static_in, inputs):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        keep = ("visible_rgb_features_pyramid", "visible_pcd_pyramid")      # large: returned as views of the static buffers
+
+        def own(v):
+            if torch.is_tensor(v):
+                return v.clone()
+            if isinstance(v, (list, tuple)):
+                return [own(x) for x in v]
+            return v
+        return {k: (v if k in keep else own(v)) for k, v in out.items()}
+
+    def _forward_infer(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action=None, staged=None):
         e, h = self.embedding_dim, self.num_attn_heads
         b, ncam, _, height, width = visible_rgb.shape
         dev = visible_rgb.device

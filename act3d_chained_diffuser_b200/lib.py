@@ -41,6 +41,9 @@ EXPORTS = {
     "a3d_argmax_pick": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "a3d_sample_ghost": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
                                  c_void_p, c_void_p]),
+    "a3d_sample_ghost_ctr": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_int, c_int, c_uint64, c_uint64,
+                                     c_void_p, c_void_p, c_void_p]),
+    "a3d_counter_add": (c_int, [c_void_p, c_uint64, c_void_p]),
     "a3d_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                              c_void_p, c_float, c_uint64, c_void_p]),
     "a3d_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -296,12 +299,21 @@ def argmax_pick(logits, ghost):
     return top, pos
 
 
-def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device):
+def sample_ghost(anchor, radius, bounds, batch, ng, seed, stream_id, device, counter=None):
+    """counter: optional int64 device tensor (1,) added to stream_id ON THE DEVICE (CUDA-graph replays draw fresh points)."""
     out = torch.empty(batch, ng, 3, device=device, dtype=torch.float32)
     bd = (c_float * 6)(*[float(x) for x in (list(bounds[0]) + list(bounds[1]))])
-    _check(load().a3d_sample_ghost(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
-                                   int(stream_id), _ptr(out), _stream()), "a3d_sample_ghost")
+    if counter is None:
+        _check(load().a3d_sample_ghost(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
+                                       int(stream_id), _ptr(out), _stream()), "a3d_sample_ghost")
+    else:
+        _check(load().a3d_sample_ghost_ctr(_ptr(anchor), float(radius), bd, batch, ng, int(seed) & (2**64 - 1),
+                                           int(stream_id), _ptr(counter), _ptr(out), _stream()), "a3d_sample_ghost_ctr")
     return out
+
+
+def counter_add(counter, inc):
+    _check(load().a3d_counter_add(_ptr(counter), int(inc), _stream()), "a3d_counter_add")
 
 
 # ------------------------------------------------------------------------------------------------ training path

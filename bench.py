@@ -362,9 +362,18 @@ def run_ours(args, rank, world, device, local=0):
 
     clocks = ClockSampler(torch.cuda.current_device() if device.index is None else device.index)
     clocks.start()
-    ms_res, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    # resident inputs: the forward is replayed from a CUDA graph (model.use_cuda_graph: no host launch cost)
+    model.use_cuda_graph = True
+    ms_res, _, _ = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop()
+    # the same forward launched eagerly for a few steps: counts our launches per step and times the ghost kernel with events
+    model.use_cuda_graph = False
+    k_prof = min(args.steps, 10)
+    _, launches_prof, prof = timed(step_resident, k_prof, 2, profile=True)
+    launches = launches_prof // k_prof * args.steps
+    # end to end: pinned host inputs, uploaded inside the timed region (eager launches: images first, the rest overlapped)
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    model.use_cuda_graph = True
 
     # ---- strong scaling: the SAME 16 keyframes split over the N ranks (16 / N per GPU), no data-path collective
     strong = None
@@ -400,7 +409,7 @@ def run_ours(args, rank, world, device, local=0):
                 "bound": "tensor", "achieved": round(ach, 2),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
                 "traffic": 57.5e6, "traffic_source": "profiles/r2_xattn6_ncu.txt (ncu --set full, one C2 launch)", "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
-                "share_of_step": round(sum(kern_ms) / ms_res, 4), "peak_source": peaks["source"] + " bf16 sustained",
+                "share_of_step": round(avg * w["levels"] / (ms_res / args.steps), 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
                 "binding_unit": {"unit": "MUFU ex2 (16 / clk / SM at 1.965 GHz, measured 15.9 with tools/micro/mufu_bench.cu)",
                                  "floor_ms": round(w["batch"] * w["ghost_per_level"] * nk * w["heads"] * 2 / (148 * 16 * 1.965e9) * 1e3, 3),
@@ -417,11 +426,13 @@ def run_ours(args, rank, world, device, local=0):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (fp16 tensor-core operands, fp32 accumulate)",
         "data": "synthetic", "impl": "ours",
         "config": {"workload": CONFIG_WORKLOAD, "batch_per_gpu": w["batch"], "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"replicas x{world} (no data-path collective)"},
+                   "parallelism": f"replicas x{world} (no data-path collective)",
+                   "launch": "resident: CUDA-graph replay of the whole forward; e2e: eager launches with staged uploads"},
         "e2e": {"value": round(kf / (ms_e2e * 1e-3), 3), "unit": "keyframes/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host)),
                 "d2h_bytes_per_step": int(w["batch"] * 8 * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "gpu_launches_note": "kernels of libact3d_b200.so per timed region (counted on eager launches of the "
+                                                             "same forward; the resident measurement replays them from a CUDA graph)",
         "clocks": clk,
         "roofline": roof,
     }

@@ -186,6 +186,11 @@ int a3d_argmax_pick(const float* logits, const float* ghost, int batch, int ng,
  */
 int a3d_sample_ghost(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
                      uint64_t seed, uint64_t stream_id, float* out, void* stream);
+/* Same sampler with the Philox stream id = stream_id + *stream_base, stream_base a DEVICE counter: a forward captured in a
+ * CUDA graph draws fresh ghost points on every replay (a3d_counter_add advances the counter inside the graph). */
+int a3d_sample_ghost_ctr(const float* anchor, float radius, const float* bounds_host, int batch, int ng,
+                         uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, float* out, void* stream);
+int a3d_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /* =================================================================================
  * Training path (fp32, gradients).  The reference trains both models through autograd over the eager

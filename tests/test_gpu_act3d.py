@@ -170,3 +170,39 @@ def test_host_inputs_are_uploaded_by_the_module():
     assert torch.equal(outs[0]["position"], outs[1]["position"])
     assert torch.equal(outs[0]["ghost_pcd_masks_pyramid"][2][1], outs[1]["ghost_pcd_masks_pyramid"][2][1])
     assert outs[1]["position"].is_cuda
+
+
+def test_cuda_graph_replay_matches_eager_and_draws_fresh_ghost_points():
+    """use_cuda_graph: the whole forward is captured once and replayed; the ghost sampler's call counter lives on the
+    device, so replay k draws the points eager call k draws after the same seed."""
+    m, kw = build(True, num_ghost_points_val=3 * 700)
+    m = m.cuda()
+    inp = {k: v.cuda() for k, v in cases.act3d_inputs(batch=2, ncam=2, seed=13).items()}
+    args = (inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"])
+    m.seed_ghost_sampler(5)
+    with torch.no_grad():
+        eager = [m(*args) for _ in range(3)]
+    m.use_cuda_graph = True
+    with torch.no_grad():
+        m(*args)                                                  # capture (its warm-up calls consume host-side sampler calls)
+        m.seed_ghost_sampler(5)                                   # also resets the device counter
+        graphed = [m(*args) for _ in range(3)]
+    torch.cuda.synchronize()
+    for a, g in zip(eager, graphed):
+        assert torch.equal(a["position"], g["position"])
+        assert torch.equal(a["rotation"], g["rotation"])
+        for lvl in range(3):
+            assert torch.equal(a["ghost_pcd_pyramid"][lvl], g["ghost_pcd_pyramid"][lvl])
+            assert torch.equal(a["ghost_pcd_masks_pyramid"][lvl][-1], g["ghost_pcd_masks_pyramid"][lvl][-1])
+    assert not torch.equal(graphed[0]["ghost_pcd_pyramid"][0], graphed[1]["ghost_pcd_pyramid"][0])     # fresh points per replay
+    # new inputs of the same shape reuse the graph
+    inp2 = {k: v.cuda() for k, v in cases.act3d_inputs(batch=2, ncam=2, seed=14).items()}
+    args2 = (inp2["visible_rgb"], inp2["visible_pcd"], inp2["instruction"], inp2["curr_gripper"])
+    m.seed_ghost_sampler(5)
+    with torch.no_grad():
+        g2 = m(*args2)
+    m.use_cuda_graph = False
+    m.seed_ghost_sampler(5)
+    with torch.no_grad():
+        e2 = m(*args2)
+    assert torch.equal(g2["position"], e2["position"]) and len(m._graphs) == 1
