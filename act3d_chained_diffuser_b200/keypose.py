@@ -47,10 +47,13 @@ class Act3D(nn.Module):
             raise AssertionError(rotation_parametrization)
         if num_sampling_level not in (1, 2, 3, 4):
             raise AssertionError(num_sampling_level)
-        if embedding_dim % 6 or embedding_dim // num_attn_heads != 15 or embedding_dim % num_attn_heads:
-            raise NotImplementedError("the sm_100a kernels are built for head_dim 15 (embedding_dim=60, 4 heads)")
+        if embedding_dim != 60 or num_attn_heads != 4:
+            raise NotImplementedError(f"Act3D (B200): embedding_dim={embedding_dim}, num_attn_heads={num_attn_heads} is not built: the sm_100a "
+                                      "kernels are specialised for embedding_dim=60 with 4 heads (head_dim 15), the configuration every "
+                                      "reference script trains and evaluates (see INTEGRATION.md, 'Supported configurations')")
         if ins_pos_emb:
-            raise NotImplementedError("ins_pos_emb is off in every shipped configuration and is not built")
+            raise NotImplementedError("Act3D (B200): ins_pos_emb=1 is not built (accepted: ins_pos_emb=0, the value of every reference "
+                                      "script; see INTEGRATION.md, 'Supported configurations')")
 
         self.image_size = image_size
         self.rotation_parametrization = rotation_parametrization

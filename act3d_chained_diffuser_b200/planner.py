@@ -64,10 +64,13 @@ class DiffusionHead(nn.Module):
             # (diffusion_head.py:253-259); only the local-refinement form (find_traj_nn) is built
             raise NotImplementedError("feat_scales_to_use > 1 needs use_goal=True (local refinement around the trajectory)")
         if use_sigma:
-            raise NotImplementedError("use_sigma is never enabled by the reference's entry points")
+            raise NotImplementedError("DiffusionPlanner (B200): use_sigma=True is not built (accepted: False, the value of every "
+                                      "reference entry point)")
         if embedding_dim != 120 or num_attn_heads != 8:
-            raise NotImplementedError("the sm_100a denoiser kernels are built for embedding_dim=120, 8 heads "
-                                      "(the shipped ChainedDiffuser configuration)")
+            raise NotImplementedError(f"DiffusionPlanner (B200): embedding_dim={embedding_dim}, num_attn_heads={num_attn_heads} is not "
+                                      "built: the sm_100a denoiser kernels are specialised for embedding_dim=120 with 8 heads "
+                                      "(head_dim 15), the configuration of scripts/train_trajectory.sh (see INTEGRATION.md, "
+                                      "'Supported configurations')")
         self.image_size = tuple(image_size)
         self.embedding_dim, self.num_attn_heads = embedding_dim, num_attn_heads
         self.use_instruction, self.use_goal = use_instruction, use_goal
@@ -476,7 +479,8 @@ class DiffusionPlanner(nn.Module):
         self.rng_compat = False        # True: draw Gaussian noise with the reference's torch.randn call sequence
         self.use_cuda_graph = True     # launch-per-layer path only: capture the 100-step loop once per shape and replay it
         self.persistent_loop = True    # single-offset sampling: the whole loop in ONE persistent cluster kernel (cd_loop.cu)
-        self._samplers = {}
+        self._samplers = {}            # per problem shape: noise / trajectory buffers, K/V cache, captured graph
+        self.max_sampler_shapes = 4    # LRU bound on the above (a C3-sized entry holds ~0.5 GB); clear_samplers() frees all
 
     # ------------------------------------------------------------------ frame conversions (torch, elementwise)
     def normalize_pos(self, pos):
@@ -510,11 +514,19 @@ class DiffusionPlanner(nn.Module):
         return torch.randn(shape, device=device)
 
     # ------------------------------------------------------------------ sampling
+    def clear_samplers(self):
+        """Drop every cached sampling state (persistent buffers and captured CUDA graphs)."""
+        self._samplers.clear()
+
     def _sampler_state(self, b, length, rows_key, dev):
         """Persistent buffers (+ the captured CUDA graph) of the sampling loop for one problem shape."""
         key = (b, length, rows_key, str(dev))
-        st = self._samplers.get(key)
-        if st is None:
+        st = self._samplers.pop(key, None)
+        if st is not None:
+            self._samplers[key] = st                  # most recently used last
+        else:
+            while len(self._samplers) >= self.max_sampler_shapes:     # least recently used shape goes (buffers + graph)
+                self._samplers.pop(next(iter(self._samplers)))
             n = self.n_steps
             st = dict(traj=torch.empty(b, length, 9, device=dev), cond=torch.empty(b, length, 9, device=dev),
                       cmask=torch.empty(b, length, 9, device=dev, dtype=torch.uint8),
@@ -610,7 +622,7 @@ class DiffusionPlanner(nn.Module):
         if not self.use_cuda_graph:
             self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
             return st["traj"].clone()
-        sig = (ctx["kv"].data_ptr(), id(ctx["w"]), ctx["nk"])
+        sig = (ctx["kv"].data_ptr(), id(ctx["w"]), ctx["nk"], bool(getattr(head, "parallel_heads", False)))
         if st["graph"] is None or st["graph_sig"] != sig:
             # one eager evaluation first: sets kernel attributes / warms caches outside the capture
             scratch = st["traj"].clone()
@@ -619,7 +631,9 @@ class DiffusionPlanner(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run_steps(ctx, st, work, trajectory_mask if has_mask else None, timesteps, st["t_all"])
-            st["graph"], st["graph_sig"], st["ctx_keepalive"] = g, sig, ctx
+            # the graph reads the K/V cache and the packed weights; the FPN maps / tokens behind them are not kept
+            st["graph"], st["graph_sig"] = g, sig
+            st["ctx_keepalive"] = {k: v for k, v in ctx.items() if k not in ("levels", "offs")}
         st["graph"].replay()
         return st["traj"].clone()
 
@@ -644,11 +658,11 @@ class DiffusionPlanner(nn.Module):
         cond[:, 0] = cur
         cmask[:, 0] = 1
         if self._use_goal_at_test:
-            n_pad = trajectory_mask.sum(1).long()
-            for i in range(b):
-                neg = -int(n_pad[i])
-                cond[i][neg - 1] = goal[i]
-                cmask[i][neg - 1:] = 1
+            # last un-padded waypoint of every sample <- goal pose, and it and the padding are inpainted
+            # (diffusion_model.py:163-167: cond[i][-n_pad-1] = goal, mask[i][-n_pad-1:] = 1), without a host sync
+            last = length - 1 - trajectory_mask.sum(1).long()
+            cond[torch.arange(b, device=dev), last] = goal
+            cmask[torch.arange(length, device=dev)[None, :] >= last[:, None]] = 1
         traj = self.conditional_sample(cond, cmask.bool(), (trajectory_mask, rgb_obs, pcd_n, instruction, cur, goal))
         traj = self.unconvert_rot(traj)
         traj[:, :, :3] = self.unnormalize_pos(traj[:, :, :3])

@@ -8,7 +8,8 @@ the published algorithm of ``diffusers.schedulers.scheduling_ddpm.DDPMScheduler`
 (Ho et al. 2020, eq. 7 posterior; diffusers defaults beta_start=1e-4, beta_end=0.02,
 variance_type="fixed_small", clip_sample=True with range 1.0, timestep_spacing
 "leading", steps_offset 0) for the two configurations the reference constructs.
-It is anchored by closed-form known answers in tests/test_ddpm.py.
+It is anchored by closed-form known answers in tests/test_ddpm.py, which also checks it against
+``diffusers`` itself whenever that package is importable (skipped in this image).
 
 It doubles as the import stub that lets the unmodified reference be imported in the
 build container (oracle/ref_import.py).
