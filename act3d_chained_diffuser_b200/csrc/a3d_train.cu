@@ -469,21 +469,40 @@ __global__ void __launch_bounds__(256) wgrad_partial_kernel(const float* __restr
     }
 }
 
-// out[e] = sum over slices of part[slice][e], e < n  (n = O*I for the weight, O for the bias), fixed summation order
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, long slices, long n,
-                                                           float* __restrict__ out) {
-    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
+// out[e] = sum over slices of part[slice][e]: CTAs [0, ceil(nw/32)) reduce the weight partials, the rest the bias
+// partials.  256 threads = 32 elements x 8 slice groups (group w takes slices w, w+8, ...: eight loads in flight per
+// thread instead of one thread walking all ~500 slices), groups combined through shared memory in a fixed order, so
+// the result is deterministic.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part_w, long nw, float* __restrict__ dw,
+                                                           const float* __restrict__ part_b, long nb, float* __restrict__ db,
+                                                           long slices) {
+    __shared__ float red[8][33];
+    const long wblocks = (nw + 31) / 32;
+    const bool bias = blockIdx.x >= wblocks;
+    const float* part = bias ? part_b : part_w;
+    const long n = bias ? nb : nw;
+    float* out = bias ? db : dw;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long e = (bias ? (long)blockIdx.x - wblocks : (long)blockIdx.x) * 32 + lane;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    long k = 0;
-    for (; k + 4 <= slices; k += 4) {
-        s0 += __ldg(part + (k + 0) * n + e);
-        s1 += __ldg(part + (k + 1) * n + e);
-        s2 += __ldg(part + (k + 2) * n + e);
-        s3 += __ldg(part + (k + 3) * n + e);
+    if (e < n) {
+        long k = grp;
+        for (; k + 24 < slices; k += 32) {
+            s0 += __ldg(part + (k + 0) * n + e);
+            s1 += __ldg(part + (k + 8) * n + e);
+            s2 += __ldg(part + (k + 16) * n + e);
+            s3 += __ldg(part + (k + 24) * n + e);
+        }
+        for (; k < slices; k += 8) s0 += __ldg(part + k * n + e);
     }
-    for (; k < slices; ++k) s0 += __ldg(part + k * n + e);
-    out[e] = (s0 + s1) + (s2 + s3);
+    red[grp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (grp == 0 && e < n) {
+        float s = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += red[w][lane];
+        out[e] = s;
+    }
 }
 
 int drop_args(float p, uint32_t* thresh, float* scale) {
@@ -499,6 +518,17 @@ int drop_args(float p, uint32_t* thresh, float* scale) {
 }
 
 }  // namespace
+
+// a3d_set_option("train_attn_core", 0 | 1): 0 = tensor-core kernels (a3d_train_mma.cu, default), 1 = the fp32 CUDA-core
+// kernels of this file (kept as the A/B reference)
+int g_train_attn_core = 0;
+int a3d_launch_attn_fwd_mma(const float* q, const float* k, const float* v, const unsigned char* key_mask, int batch,
+                            int heads, int nq, int nk, int embed, float* o, float* lse, int drop, uint32_t th, float sc,
+                            uint64_t seed, cudaStream_t st);
+int a3d_launch_attn_bwd_mma(const float* q, const float* k, const float* v, const unsigned char* key_mask,
+                            const float* o, const float* dout, const float* lse, int batch, int heads, int nq, int nk,
+                            int embed, float* dq, float* dk, float* dv, float* dsum, int drop, uint32_t th, float sc,
+                            uint64_t seed, cudaStream_t st);
 }  // namespace a3d
 
 using namespace a3d;
@@ -514,6 +544,8 @@ extern "C" int a3d_attn_fwd(const float* q, const float* k, const float* v, cons
     uint32_t th;
     float sc;
     const int drop = drop_args(dropout_p, &th, &sc);
+    if (g_train_attn_core == 0)
+        return a3d_launch_attn_fwd_mma(q, k, v, key_mask, batch, heads, nq, nk, embed, o, lse, drop, th, sc, seed, (cudaStream_t)stream);
     dim3 grid((nq + kRows - 1) / kRows, batch * heads);
     if (drop)
         attn_fwd_kernel<true><<<grid, kRows * kSplit, 0, (cudaStream_t)stream>>>(q, k, v, key_mask, heads, nq, nk, embed, o, lse, th, sc, seed);
@@ -535,6 +567,8 @@ extern "C" int a3d_attn_bwd(const float* q, const float* k, const float* v, cons
     float sc;
     const int drop = drop_args(dropout_p, &th, &sc);
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_train_attn_core == 0)
+        return a3d_launch_attn_bwd_mma(q, k, v, key_mask, o, dout, lse, batch, heads, nq, nk, embed, dq, dk, dv, dsum, drop, th, sc, seed, st);
     dim3 g1((nq + kRows - 1) / kRows, batch * heads);
     const int chunks = (nq + kQChunk - 1) / kQChunk;
     A3D_REQUIRE(chunks <= 65535, "a3d_attn_bwd: nq=%d too large", nq);
@@ -602,7 +636,7 @@ extern "C" int a3d_linear_wgrad(const float* dy, const float* x, long rows, int 
     cudaStream_t st = (cudaStream_t)stream;
     wgrad_partial_kernel<<<grid, 256, 0, st>>>(dy, x, rows, out_features, in_features, part_w, db ? part_b : nullptr);
     const long nw = (long)out_features * in_features;
-    wgrad_reduce_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(part_w, slices, nw, dw);
-    if (db) wgrad_reduce_kernel<<<(out_features + 255) / 256, 256, 0, st>>>(part_b, slices, out_features, db);
+    const long nb = db ? out_features : 0;
+    wgrad_reduce_kernel<<<(unsigned)((nw + 31) / 32 + (nb + 31) / 32), 256, 0, st>>>(part_w, nw, dw, part_b, nb, db, slices);
     return check_launch("a3d_linear_wgrad");
 }

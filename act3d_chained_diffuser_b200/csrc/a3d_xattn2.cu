@@ -356,6 +356,7 @@ int g_xattn_core = 0;
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int a3d_launch_xattn6(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int g_xattn6_np = 6;    // a3d_set_option("xattn6_np", n): score pairs (of 16 per thread and unit) on the FMA-pipe polynomial
+namespace a3d { extern int g_train_attn_core; }   // a3d_train.cu
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" int a3d_set_option(const char* name, int value) {
@@ -374,6 +375,11 @@ extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "xattn_poly") == 0) {
         A3D_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4, "a3d_set_option: xattn_poly must be 0, 2, 3 or 4");
         g_xattn_poly = value;
+        return A3D_OK;
+    }
+    if (name && strcmp(name, "train_attn_core") == 0) {
+        A3D_REQUIRE(value == 0 || value == 1, "a3d_set_option: train_attn_core must be 0 (tensor cores) or 1 (fp32 CUDA cores)");
+        g_train_attn_core = value;
         return A3D_OK;
     }
     A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");

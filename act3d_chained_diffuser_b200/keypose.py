@@ -7,6 +7,8 @@ coarse-to-fine loop itself -- point pyramid, local top-k, gather, K/V cache with
 fused ghost-point / query cross-attention stacks, mask logits, top-ghost pick and the ghost
 sampler -- runs in libact3d_b200.so with no host synchronisation between levels.
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -18,7 +20,7 @@ from .autograd_ops import gather_tokens
 from .packing import PackCache, pack_kv_set, pack_xattn_layer
 from .params import XAttnStackParams, mlp
 from .rotations import normalise_quat, ortho6d_to_matrix
-from .trunk import EvalTrunk, build_backbone
+from .trunk import EvalTrunk, build_backbone, normalize_images
 
 
 def _shared_or_separate(n, tie, factory):
@@ -107,6 +109,8 @@ class Act3D(nn.Module):
                                             # the big feature / point pyramids of the returned dict then alias static buffers
                                             # that the next call overwrites
         self._graphs = {}
+        self.train_channels_last = True     # training forward: backbone + FPN on channels-last activations
+        self._trunk_nhwc = False
         self._graph_counter = None          # device call counter of the ghost sampler while a graph is being captured
         self._graph_counter_buf = None
         self._side_stream_obj = None
@@ -138,6 +142,20 @@ class Act3D(nn.Module):
         if self._graph_counter_buf is not None:
             self._graph_counter_buf.zero_()
 
+    @contextlib.contextmanager
+    def device_sampler_counter(self, device):
+        """While a CUDA graph of a forward is being captured the sampler's call counter must live on the device:
+        inside this scope every draw is keyed on (seed, level + device counter), and leaving the scope appends the
+        kernel that advances the counter -- so each replay of the graph draws fresh ghost points."""
+        if self._graph_counter_buf is None:
+            self._graph_counter_buf = torch.zeros(1, dtype=torch.int64, device=device)
+        self._graph_counter = self._graph_counter_buf
+        try:
+            yield
+            lib.counter_add(self._graph_counter_buf, self.num_sampling_level)
+        finally:
+            self._graph_counter = None
+
     def _sample_ghost_points(self, total_timesteps, device, level, anchor=None):
         """(B, Ng, 3) uniform ghost points; same contract as act3d.py:394-440 but sampled on the
         device (no anchor.cpu() round trip).  Ng switches on self.training like the reference."""
@@ -164,7 +182,7 @@ class Act3D(nn.Module):
         rgb = visible_rgb.reshape(b * num_cameras, *visible_rgb.shape[2:])
         if self.training or not self.fold_trunk or not isinstance(self.backbone, torch.nn.Module) \
                 or isinstance(self.backbone, torch.nn.Identity):
-            feats, feat_bias = self.feature_pyramid(self.backbone(self.normalize(rgb))), {}
+            feats, feat_bias = self.feature_pyramid(self.backbone(normalize_images(self.normalize, rgb))), {}
         else:
             feats, feat_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
                                                 needed=self.feature_map_pyramid[:self.num_sampling_level],
@@ -240,16 +258,9 @@ class Act3D(nn.Module):
                     self._forward_infer(*static_in, None)
             main.wait_stream(warm)
             torch.cuda.synchronize(dev)
-            if self._graph_counter_buf is None:
-                self._graph_counter_buf = torch.zeros(1, dtype=torch.int64, device=dev)
             graph = torch.cuda.CUDAGraph()
-            self._graph_counter = self._graph_counter_buf
-            try:
-                with torch.cuda.graph(graph):
-                    out = self._forward_infer(*static_in, None)
-                    lib.counter_add(self._graph_counter_buf, self.num_sampling_level)
-            finally:
-                self._graph_counter = None
+            with torch.cuda.graph(graph), self.device_sampler_counter(dev):
+                out = self._forward_infer(*static_in, None)
             if len(self._graphs) >= 4:                 # bounded: a graph pins its activations (hundreds of MB at batch 16)
                 self._graphs.pop(next(iter(self._graphs)))
             entry = self._graphs[key] = (graph, static_in, out)
@@ -437,7 +448,17 @@ class Act3D(nn.Module):
         grip_xyz = curr_gripper[:, :3].float()
 
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:]).float()
-        feats = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        x = normalize_images(self.normalize, rgb)
+        if self.train_channels_last and isinstance(self.backbone, nn.Module) and not isinstance(self.backbone, nn.Identity):
+            # NHWC activations end to end: cuDNN's tensor-core convolutions and batch-norm kernels are NHWC-native, so
+            # this drops a layout conversion around every convolution (1.2 ms of a 30 ms step).  Parameters keep their
+            # shapes and state_dict; the gather kernel and its backward read either layout.
+            if not self._trunk_nhwc:
+                self.backbone.to(memory_format=torch.channels_last)
+                self.feature_pyramid.to(memory_format=torch.channels_last)
+                self._trunk_nhwc = True
+            x = x.contiguous(memory_format=torch.channels_last)
+        feats = self.feature_pyramid(self.backbone(x))
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         feats_pyr, pcd_pyr, cache = [], [], {}
         for i in range(self.num_sampling_level):

@@ -332,9 +332,9 @@ def attn_bwd(q, k, v, key_mask, o, dout, lse, heads, dropout_p=0.0, seed=0):
     """-> dq (B,Nq,E), dk (B,Nk,E), dv (B,Nk,E)"""
     b, nq, e = q.shape
     nk = k.shape[1]
-    dq = torch.empty_like(q)
+    dq = torch.zeros_like(q)
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
-    dsum = torch.empty_like(lse)
+    dsum = torch.zeros(b * heads * (nq + 1), device=q.device, dtype=torch.float32)   # D per row, then max |dO| per (b, h)
     _check(load().a3d_attn_bwd(_ptr(_f32(q)), _ptr(_f32(k)), _ptr(_f32(v)), _ptr(key_mask), _ptr(_f32(o)),
                                _ptr(_f32(dout)), _ptr(_f32(lse)), b, heads, nq, nk, e, _ptr(dq), _ptr(dk), _ptr(dv),
                                _ptr(dsum), float(dropout_p), int(seed) & (2**64 - 1), _stream()), "a3d_attn_bwd")

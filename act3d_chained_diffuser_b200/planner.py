@@ -25,7 +25,7 @@ from .ddpm import PosteriorTable
 from .packing import PackCache, pack_ada_layer, pack_kv_set, pack_lang_layer, pack_mlp, pack_traj_encoder
 from .params import ParallelStackParams, mlp
 from .rotations import matrix_to_ortho6d, matrix_to_quat, normalise_quat, ortho6d_to_matrix, quat_to_matrix
-from .trunk import EvalTrunk, build_backbone
+from .trunk import EvalTrunk, build_backbone, normalize_images
 
 
 def _repeat(n, tie, factory):
@@ -175,7 +175,7 @@ class DiffusionHead(nn.Module):
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:])
         needed = tuple(dict.fromkeys(self.feature_map_pyramid[s] for s in range(self.feat_scales)))
         if self.training or not self.fold_trunk or isinstance(self.backbone, torch.nn.Identity):
-            fpn, fpn_bias = self.feature_pyramid(self.backbone(self.normalize(rgb))), {}
+            fpn, fpn_bias = self.feature_pyramid(self.backbone(normalize_images(self.normalize, rgb))), {}
         else:
             fpn, fpn_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb, needed=needed,
                                              defer_bias=True)
@@ -403,7 +403,7 @@ class DiffusionHead(nn.Module):
         dev = trajectory.device
         training = self.training
         rgb = visible_rgb.reshape(b * ncam, *visible_rgb.shape[2:]).float()
-        fpn = self.feature_pyramid(self.backbone(self.normalize(rgb)))
+        fpn = self.feature_pyramid(self.backbone(normalize_images(self.normalize, rgb)))
         pcd = visible_pcd.reshape(b * ncam, *visible_pcd.shape[2:]).contiguous().float()
         pts_cache = {}
         for s_ in range(self.feat_scales):

@@ -59,6 +59,24 @@ def build_backbone(kind):
     raise ValueError(f"backbone must be 'resnet' or 'clip', got {kind!r}")
 
 
+_NORM_CONSTS = {}
+
+
+def normalize_images(normalize, rgb):
+    """torchvision ``Normalize`` (resnet.py:20 / clip.py:34-35 in the reference) with its mean / std kept on the
+    device: the stock module rebuilds both from Python lists on every call (two pageable host->device copies, which
+    also forbids CUDA-graph capture of a training step).  Same arithmetic: (x - mean) / std."""
+    if not hasattr(normalize, "mean"):          # a user-installed transform (e.g. nn.Identity in the test trunk)
+        return normalize(rgb)
+    key = (id(normalize), rgb.device, rgb.dtype)
+    c = _NORM_CONSTS.get(key)
+    if c is None:
+        mean = torch.as_tensor(normalize.mean, dtype=rgb.dtype).view(-1, 1, 1).to(rgb.device)
+        std = torch.as_tensor(normalize.std, dtype=rgb.dtype).view(-1, 1, 1).to(rgb.device)
+        c = _NORM_CONSTS[key] = (mean, std)
+    return (rgb - c[0]) / c[1]
+
+
 class EvalTrunk:
     """Inference-time evaluation of (normalize, frozen backbone, FPN) -- still PyTorch / cuDNN library
     calls (the trunk is dense convolution work that stays on cuDNN), but organised the

@@ -204,9 +204,12 @@ int a3d_counter_add(uint64_t* counter, uint64_t inc, void* stream);
  *   rotated), key_mask [B][Nk] bytes (non-zero = ignore key, :398-404) or NULL, lse [B*H][Nq] =
  *   log sum exp of each score row (saved for backward).  dropout_p in [0,1) on the attention weights
  *   (:413) from a counter-based generator keyed on (seed, b, h, row, key); 0 disables it.
- * a3d_attn_bwd: gradients of the above.  dq [B][Nq][E] is written; dk / dv [B][Nk][E] are ACCUMULATED
- *   into (fp32 atomics over query chunks: zero-fill them first); dsum [B*H][Nq] is scratch (dO . O).
+ * a3d_attn_bwd: gradients of the above.  dq [B][Nq][E] and dk / dv [B][Nk][E] are ACCUMULATED into (fp32 atomics
+ *   over query / key chunks: zero-fill all three first); dsum is scratch of B*H*(Nq+1) floats, ZERO-FILLED
+ *   by the caller ([B*H][Nq] dO . O, then [B*H] max |dO| used to rescale gradients into fp16 range).
  *   The same dropout_p / seed as the forward call regenerate the same mask.
+ *   Both run on the tensor cores (error-compensated fp16 pairs on mma.sync m16n8k16, fp32 accumulation:
+ *   csrc/a3d_train_mma.cu); a3d_set_option("train_attn_core", 1) selects the fp32 CUDA-core kernels instead.
  * a3d_rope_apply: out = rotary(x; pos) on channel pairs (2i, 2i+1) of the full E vector
  *   (position_encodings.py:31-34 with the 3-D table of :58-97 evaluated on the fly); x / out [rows][E],
  *   pos [rows][3].  transpose != 0 applies the inverse rotation = the backward of the forward call.
