@@ -10,8 +10,10 @@ batch into the static input buffers.
 DDP (torch.nn.parallel.DistributedDataParallel) is captured with its all-reduce inside the graph; this needs
   * ``find_unused_parameters=False`` -- use :func:`freeze_parameters_without_gradient` first: the reference relies
     on find_unused_parameters=True only because six FPN output blocks never reach the loss (SURVEY.md App. B.2);
-  * the DDP wrapper constructed and warmed up (>= 11 iterations) on a side stream, which :class:`GraphedTrainStep`
-    does itself when handed the bare module and ``ddp_kwargs``.
+  * the DDP wrapper constructed on a side stream (:func:`build_ddp`) and warmed up for >= 11 iterations before the
+    capture (:class:`GraphedTrainStep` does the warm-up);
+  * ``TORCH_NCCL_ASYNC_ERROR_HANDLING=0`` in the environment before ``init_process_group`` (the watchdog thread must
+    not poll the captured collectives).
 """
 import torch
 
@@ -31,24 +33,35 @@ def freeze_parameters_without_gradient(model, step_loss):
     return frozen
 
 
+def build_ddp(model, **kwargs):
+    """DistributedDataParallel constructed on a side stream, as whole-step capture requires (its buckets and hooks must
+    not belong to the stream the graph is later captured on)."""
+    dev = next(model.parameters()).device
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        net = torch.nn.parallel.DistributedDataParallel(model, **kwargs)
+    main.wait_stream(side)
+    return net
+
+
 class GraphedTrainStep:
     """step_loss(net, *inputs) -> scalar loss.  ``inputs``: example CUDA tensors (shapes / dtypes are fixed).
     Call the object with a new batch: copies it into the static buffers, replays the graph and returns the (static)
     loss tensor of that step.  ``make_optimizer(params)`` must build a capturable optimizer, e.g.
-    ``torch.optim.AdamW(params, lr=..., capturable=True)``."""
+    ``torch.optim.AdamW(params, lr=..., capturable=True)``.  ``net``: the module to call -- ``model`` itself, or a
+    DDP wrapper made by :func:`build_ddp` (then the bucketed all-reduce is part of the graph)."""
 
-    def __init__(self, model, step_loss, make_optimizer, inputs, ddp_kwargs=None, warmup=11):
+    def __init__(self, model, step_loss, make_optimizer, inputs, net=None, warmup=11):
         dev = inputs[0].device
         self.model = model
+        self.net = model if net is None else net
         self.static_in = [t.detach().clone() for t in inputs]
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            if ddp_kwargs is not None:
-                self.net = torch.nn.parallel.DistributedDataParallel(model, **ddp_kwargs)
-            else:
-                self.net = model
             self.optimizer = make_optimizer([p for p in model.parameters() if p.requires_grad])
             for _ in range(warmup):
                 self.optimizer.zero_grad(set_to_none=True)

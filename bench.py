@@ -247,13 +247,19 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
     gt = grip.clone()
     gt[:, :3] += 0.02
 
-    def step_loss(m):
+    def batch_loss(m, rgb, pcd, instr, grip, gt):
         out = m(rgb, pcd, instr, grip, gt_action=gt)
         return sum(keypose_loss(out, gt).values())
 
+    step_loss = lambda m: batch_loss(m, rgb, pcd, instr, grip, gt)
+    from act3d_chained_diffuser_b200.train_graph import GraphedTrainStep, build_ddp, freeze_parameters_without_gradient
     reseed = lambda: model.seed_ghost_sampler(99 + rank)
+    # the six FPN output blocks that never reach the loss stop requiring gradients, so DDP runs without
+    # find_unused_parameters (no per-step graph traversal / used-parameter all-reduce) and the step can be captured
+    frozen = freeze_parameters_without_gradient(model, step_loss)
     mean = _local_mean_gradients(model, step_loss, reseed, world) if world > 1 else None
-    net = _ddp(model, local, world)
+    net = model if world == 1 else build_ddp(model, device_ids=[local], broadcast_buffers=False,
+                                             gradient_as_bucket_view=True)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
 
     def step():
@@ -264,11 +270,17 @@ def run_train(rank, world, device, local, iters=6, warmup=3):
         return loss
 
     check = _ddp_gradient_check(model, net, mean, step_loss, reseed) if world > 1 else None
-    ms, loss = _time_train(step, world, device, iters, warmup)
+    ms_eager, _ = _time_train(step, world, device, iters, warmup)
+    # the whole step (forward, loss, backward, bucketed all-reduce, AdamW) as one CUDA graph
+    graphed = GraphedTrainStep(model, batch_loss, lambda ps: torch.optim.AdamW(ps, lr=1e-4, capturable=True),
+                               (rgb, pcd, instr, grip, gt), net=net)
+    ms, loss = _time_train(lambda: graphed(rgb, pcd, instr, grip, gt), world, device, max(iters, 20), warmup)
     out = {"metric": "train keyframes/s", "value": round(w["batch"] * world / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
-           "final_loss": round(loss, 4), "parallelism": f"DDP x{world} (NCCL gradient all-reduce only)",
+           "eager_launch_ms_per_step": round(ms_eager, 3), "final_loss": round(loss, 4),
+           "parallelism": f"DDP x{world} (NCCL gradient all-reduce only, inside the captured step)",
+           "frozen_unreachable_parameters": len(frozen),
            "workload": f"Act3D training step: {w['batch']} keyframes/GPU, 4 views 256x256, {w['ghost_total']} ghost points "
-                       "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW"}
+                       "(333/level), use_instruction=1, frozen ResNet-50, fp32, AdamW; whole step replayed from a CUDA graph"}
     if check is not None:
         out["ddp_gradient_check_max_rel"] = float(f"{check:.2e}")
     return out
@@ -571,6 +583,7 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")     # whole-step CUDA-graph capture of DDP (train_graph.py)
         torch.distributed.init_process_group("nccl", device_id=device)
     args.warmup = max(args.warmup, 3)
     line = run_ours(args, rank, world, device, local)
