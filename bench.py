@@ -420,7 +420,7 @@ def run_ours(args, rank, world, device, local=0):
                           "FMA-pipe polynomial for 6 of 16 exponentials)",
                 "bound": "tensor", "achieved": round(ach, 2),
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops_sustained"], 4),
-                "traffic": 57.5e6, "traffic_source": "profiles/r2_xattn6_ncu.txt (ncu --set full, one C2 launch)", "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
+                "traffic": 53.8e6, "traffic_source": "profiles/r2_xattn6_ncu.txt (ncu --set full, one C2 launch)", "avg_launch_ms": round(avg, 4), "launches_timed": len(kern_ms),
                 "share_of_step": round(avg * w["levels"] / (ms_res / args.steps), 4), "peak_source": peaks["source"] + " bf16 sustained",
                 "algorithmic_flops_per_launch": flops_launch,
                 "binding_unit": {"unit": "MUFU ex2 (16 / clk / SM at 1.965 GHz, measured 15.9 with tools/micro/mufu_bench.cu)",
