@@ -2,8 +2,9 @@
 
 Test infrastructure only.  /root/reference does not exist on the GPU box; nothing in
 ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this.  It is used by
-``tests/golden/make_golden.py`` (fixture generation) and by the container-only test
-``tests/test_oracle_vs_reference.py``.
+``tests/golden/make_golden.py`` (fixture generation) and by the container-only parts of
+``tests/test_dropin_contract.py`` (constructor / forward signatures and state_dict keys against the real
+reference; they skip where /root/reference is absent).
 
 Two packages the reference imports at module scope are not installed here
 (SURVEY.md App. B.1):
