@@ -356,7 +356,7 @@ int g_xattn_core = 0;
 int a3d_launch_xattn4(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int a3d_launch_xattn6(const Xa2Args& a, dim3 grid, cudaStream_t stream, int poly);
 int g_xattn6_np = 6;    // a3d_set_option("xattn6_np", n): score pairs (of 16 per thread and unit) on the FMA-pipe polynomial
-namespace a3d { extern int g_train_attn_core; }   // a3d_train.cu
+namespace a3d { extern int g_train_attn_core; extern int g_cd_prefetch_tiles; }   // a3d_train.cu, cd_loop.cu
 int g_xattn_poly = 0;   // set through a3d_set_option("xattn_poly", 0|2|3|4); measured: 0 is fastest (issue-bound)
 
 extern "C" int a3d_set_option(const char* name, int value) {
@@ -380,6 +380,11 @@ extern "C" int a3d_set_option(const char* name, int value) {
     if (name && strcmp(name, "train_attn_core") == 0) {
         A3D_REQUIRE(value == 0 || value == 1, "a3d_set_option: train_attn_core must be 0 (tensor cores) or 1 (fp32 CUDA cores)");
         g_train_attn_core = value;
+        return A3D_OK;
+    }
+    if (name && strcmp(name, "cd_prefetch_tiles") == 0) {
+        A3D_REQUIRE(value >= 0 && value <= 64, "a3d_set_option: cd_prefetch_tiles must be in [0, 64]");
+        g_cd_prefetch_tiles = value;
         return A3D_OK;
     }
     A3D_REQUIRE(false, "a3d_set_option: unknown option '%s'", name ? name : "(null)");

@@ -10,8 +10,11 @@
 //     n tile of the [16 x 128] output, takes its weight fragments STRAIGHT from L2 with all k steps in flight (no
 //     staging, no barrier inside a GEMM) and the stage costs one block barrier;
 //   * the cross-attention is split BY KEYS instead: every CTA streams its own quarter of the context K/V tile images
-//     (32 KiB per 64 keys, all 8 heads; cp.async.bulk on a 3-slot mbarrier ring fed by its own producer warp, with
-//     cp.async.bulk.prefetch.L2 running 12 tiles ahead) against the Q of ALL 64 rows, and the unnormalised partial results
+//     (32 KiB per 64 keys, all 8 heads; cp.async.bulk on a 3-slot mbarrier ring fed by its own producer warp; an optional
+//     cp.async.bulk.prefetch.L2 running n tiles ahead -- a3d_set_option("cd_prefetch_tiles", n) -- measured as a loss:
+//     62.5 ms per C3 batch without it, 63.2 / 64.0 / 64.4 ms at 3 / 8 / 12 tiles, and at 12 tiles ncu shows 95 GB of
+//     DRAM reads for a 54.5 GB stream: the 128 x 12 x 32 KiB of prefetched tiles evict each other before they are
+//     used) against the Q of ALL 64 rows, and the unnormalised partial results
 //     go to the CTA that owns the rows.  (A first version kept the rows split here too and multicast every tile to the
 //     4 CTAs: 96 KiB in flight per cluster against ~2 us of HBM + multicast latency made the ring latency-bound, 54 us per
 //     layer, ncu: 20 % of all stall samples on the tile barrier; the key split puts 4 x 96 KiB in flight per sample.)
@@ -36,7 +39,10 @@ constexpr int CT = CW * 32;               // compute threads
 constexpr int LT = CT + 32;               // + producer warp
 constexpr int LP = 136;                   // halfs per row of an fp16 plane (272 B: conflict-free ldmatrix)
 constexpr int FPT = 132;                  // floats per row of an fp32 tile
-constexpr int PF_TILES = 12;              // L2 prefetch distance of the K/V stream (tiles of this CTA's own sequence)
+constexpr int PF_TILES = 0;               // default L2 prefetch distance of the K/V stream (0 = off; measured best, see header)
+}  // namespace cd
+int g_cd_prefetch_tiles = cd::PF_TILES;   // a3d_set_option("cd_prefetch_tiles", n)
+namespace cd {
 constexpr int KV_TILE = 2 * H * 2048;     // K image + V image of 64 keys, all heads
 constexpr int ST = 3;                     // ring slots
 constexpr int MAXL = 12;
@@ -50,7 +56,7 @@ __device__ long long g_cdl_trace[64];
 #endif
 
 struct LoopArgs {
-    int batch, nrows, n_steps, nl, n_traj, nk, ntiles, n_instr;
+    int batch, nrows, n_steps, nl, n_traj, nk, ntiles, n_instr, pf_tiles;
     float* traj;                          // [B][L][9] in: x_T (+ conditioning), out: x_0
     const float* cond;                    // [B][L][9]
     const unsigned char* cmask;           // [B][L][9]
@@ -362,9 +368,10 @@ __global__ void __launch_bounds__(LT, 1) cd_loop_kernel(const LoopArgs a) {
                 const uint32_t l = (j / my_tiles) % a.nl, t = j % my_tiles;
                 return kv_b + (size_t)l * a.kv_set_bytes + (size_t)t * KV_TILE;
             };
-            for (uint32_t j = 0; j < (uint32_t)PF_TILES && j < total; ++j) bulk_prefetch_l2(src_of(j), KV_TILE);
+            const uint32_t pf = (uint32_t)a.pf_tiles;          // 0 = no L2 prefetch
+            for (uint32_t j = 0; j < pf && j < total; ++j) bulk_prefetch_l2(src_of(j), KV_TILE);
             for (uint32_t j = 0; j < total; ++j) {
-                if (j + PF_TILES < total) bulk_prefetch_l2(src_of(j + PF_TILES), KV_TILE);
+                if (pf && j + pf < total) bulk_prefetch_l2(src_of(j + pf), KV_TILE);
                 const uint32_t slot = j % ST, use = j / ST;
                 if (use >= 1) mbar_wait(s.empty + slot, (use - 1) & 1);
                 mbar_expect_tx(s.full + slot, KV_TILE);
@@ -1043,6 +1050,7 @@ extern "C" int cd_denoise_loop(float* traj, int batch, int length, int n_steps, 
     LoopArgs a{};
     a.batch = batch, a.nrows = length, a.n_steps = n_steps, a.nl = ada_layers, a.n_traj = n_traj_layers, a.nk = nk;
     a.ntiles = (nk + kTileKeys - 1) / kTileKeys;
+    a.pf_tiles = g_cd_prefetch_tiles;
     a.n_instr = n_instr;
     a.traj = traj, a.cond = cond, a.cmask = cond_mask, a.mask = mask, a.wp_pe = wp_pe, a.timesteps = timesteps, a.ada = ada, a.coef = coef;
     a.noise_pos = noise_pos, a.noise_rot = noise_rot;
