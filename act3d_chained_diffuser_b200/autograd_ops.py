@@ -97,32 +97,79 @@ def gather_tokens(feat, pcd, idx, batch, ncam):
 
 
 class _Linear(torch.autograd.Function):
-    """y = x W^T + b with the weight / bias gradient from a3d_linear_wgrad (row-split reduction at HBM speed)
-    instead of autograd's single-CTA SIMT GEMM + separate bias reduction; dx stays a library GEMM."""
+    """y = x W^T + b [ReLU] for the many-row token tensors of the training path.  Forward and the data gradient are the
+    tensor-core kernel a3d_linear_fwd (error-compensated fp16 pairs: fp32-class accuracy; autograd's GEMMs are fp32
+    SIMT because TF32 is off, as in the reference); the weight / bias gradient is a3d_linear_wgrad (row-split
+    reduction at HBM speed instead of a single-CTA SIMT GEMM + separate bias reduction)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+    def forward(ctx, x, weight, bias, relu):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w = weight.contiguous()
+        b = bias.contiguous() if bias is not None else None
+        if lib.linear_supported(w.shape[0], w.shape[1]):
+            y = lib.linear_rows(x2, w, b, relu=relu)
+        else:
+            y = torch.nn.functional.linear(x2, w, b)
+            if relu:
+                y = torch.relu_(y)
+        ctx.save_for_backward(x2, w, y if relu else torch.empty(0))
+        ctx.has_bias, ctx.relu, ctx.x_shape = bias is not None, relu, x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, grad):
-        x, weight = ctx.saved_tensors
-        g2 = grad.reshape(-1, grad.shape[-1]).contiguous()
-        dx = (g2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        x2, weight, y = ctx.saved_tensors
+        g2 = grad.reshape(-1, grad.shape[-1])
+        g2 = (g2 * (y > 0)) if ctx.relu else g2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if lib.linear_supported(weight.shape[0], weight.shape[1], transpose=True):
+                dx = lib.linear_rows(g2, weight, transpose=True).view(ctx.x_shape)
+            else:
+                dx = (g2 @ weight).view(ctx.x_shape)
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            x2 = x.reshape(-1, x.shape[-1]).contiguous()
             if weight.numel() <= 128 * 128:      # one to four 64 x 64 output tiles: the row-split kernel
                 dw, db = lib.linear_wgrad(g2, x2, want_bias=ctx.has_bias)
             else:                                # wide FFN matrices give a library GEMM enough output tiles
                 dw, db = g2.t() @ x2, (g2.sum(0) if ctx.has_bias else None)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x, weight, bias=None):
-    """torch.nn.functional.linear for the training path; rows = every leading dimension of x."""
+def linear(x, weight, bias=None, relu=False):
+    """torch.nn.functional.linear (+ optional fused ReLU) for the training path; rows = every leading dimension of x."""
     if x.numel() // x.shape[-1] < 2048:          # few rows: autograd's own GEMM is as good
-        return torch.nn.functional.linear(x, weight, bias)
-    return _Linear.apply(x, weight, bias)
+        y = torch.nn.functional.linear(x, weight, bias)
+        return torch.relu(y) if relu else y
+    return _Linear.apply(x, weight, bias, relu)
+
+
+class _ResidualLayerNorm(torch.autograd.Function):
+    """LayerNorm(x + res) * g + b in one pass (a3d_layernorm_fwd), backward in one pass + a fixed-order column sum
+    (a3d_layernorm_bwd); `res` may be None."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, eps):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        r2 = res.reshape(-1, x.shape[-1]).contiguous() if res is not None else None
+        y, z, mean, rstd = lib.layernorm_fwd(x2, r2, weight.contiguous(), bias.contiguous(), eps)
+        ctx.save_for_backward(z, mean, rstd, weight)
+        ctx.has_res = res is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        z, mean, rstd, weight = ctx.saved_tensors
+        g2 = grad.reshape(-1, grad.shape[-1]).contiguous()
+        dz, dg, db = lib.layernorm_bwd(g2, z, mean, rstd, weight.contiguous())
+        dz = dz.view(grad.shape)
+        return dz, (dz if ctx.has_res else None), dg, db, None
+
+
+def residual_layer_norm(norm, x, res=None):
+    """``norm(x + res)`` for an nn.LayerNorm over the last dimension (layers.py:309, 331, 147, 182, 209)."""
+    e = x.shape[-1]
+    if e not in (60, 120) or x.numel() // e < 2048 or norm.weight is None:
+        return norm(x if res is None else x + res)
+    return _ResidualLayerNorm.apply(x, res, norm.weight, norm.bias, norm.eps)

@@ -53,6 +53,14 @@ EXPORTS = {
                                       c_void_p]),
     "a3d_linear_wgrad_workspace": (c_size_t, [c_long, c_int, c_int]),
     "a3d_linear_wgrad": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "a3d_linear_supported": (c_int, [c_int, c_int, c_int]),
+    "a3d_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "a3d_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "a3d_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_float, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "a3d_layernorm_bwd_workspace": (c_size_t, [c_int]),
+    "a3d_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "a3d_soft_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "cd_pack_floats": (c_size_t, [c_int]),
     "cd_ctx_lang": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -372,6 +380,48 @@ def linear_wgrad(dy, x, want_bias=True):
     _check(load().a3d_linear_wgrad(_ptr(_f32(dy)), _ptr(_f32(x)), rows, o, i, _ptr(dw), _ptr(db), _ptr(ws), _stream()),
            "a3d_linear_wgrad")
     return dw, db
+
+
+def linear_supported(out_features, in_features, transpose=False):
+    return bool(load().a3d_linear_supported(int(out_features), int(in_features), int(transpose)))
+
+
+def linear_rows(x, weight, bias=None, relu=False, transpose=False):
+    """x (rows, K) fp32.  transpose=False: y = x W^T + b (W (O, I), K = I) -> (rows, O);
+    transpose=True: y = x W (K = O) -> (rows, I): the data gradient of the same layer."""
+    rows = x.shape[0]
+    o, i = weight.shape
+    n = i if transpose else o
+    y = torch.empty(rows, n, device=x.device, dtype=torch.float32)
+    ws = torch.empty(load().a3d_linear_workspace(o, i, int(transpose)), device=x.device, dtype=torch.uint8)
+    _check(load().a3d_linear_fwd(_ptr(_f32(x)), _ptr(_f32(weight)), _ptr(bias), rows, o, i, int(relu), int(transpose),
+                                 _ptr(y), _ptr(ws), _stream()), "a3d_linear_fwd")
+    return y
+
+
+def layernorm_fwd(x, res, gamma, beta, eps):
+    """x, res (rows, E) -> y, z (= x + res, or x itself when res is None), mean, rstd (rows,)."""
+    rows, e = x.shape
+    y = torch.empty_like(x)
+    z = torch.empty_like(x) if res is not None else x
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    _check(load().a3d_layernorm_fwd(_ptr(_f32(x)), _ptr(res), _ptr(_f32(gamma)), _ptr(_f32(beta)), rows, e, float(eps),
+                                    _ptr(z) if res is not None else None, _ptr(y), _ptr(mean), _ptr(rstd), _stream()),
+           "a3d_layernorm_fwd")
+    return y, z, mean, rstd
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma):
+    """-> dz (rows, E), dgamma (E,), dbeta (E,)"""
+    rows, e = dy.shape
+    dz = torch.empty_like(dy)
+    dg = torch.empty(e, device=dy.device, dtype=torch.float32)
+    db = torch.empty_like(dg)
+    ws = torch.empty(load().a3d_layernorm_bwd_workspace(e), device=dy.device, dtype=torch.uint8)
+    _check(load().a3d_layernorm_bwd(_ptr(_f32(dy)), _ptr(_f32(z)), _ptr(mean), _ptr(rstd), _ptr(_f32(gamma)), rows, e,
+                                    _ptr(dz), _ptr(dg), _ptr(db), _ptr(ws), _stream()), "a3d_layernorm_bwd")
+    return dz, dg, db
 
 
 def soft_ce(logits, ghost, gt, spread, label_smoothing=0.0, want_grad=True):

@@ -11,7 +11,7 @@ MultiheadCustomAttention (model/utils/multihead_custom_attention.py:157-462).
 """
 import torch.nn.functional as F
 
-from .autograd_ops import attention_core, linear, rope_apply
+from .autograd_ops import attention_core, linear, residual_layer_norm, rope_apply
 
 
 def mha(attn, heads, query, key, value, q_pos=None, k_pos=None, key_padding_mask=None, dropout_p=0.0):
@@ -42,8 +42,9 @@ def xattn_stack(stack, x, ctx, q_pos=None, k_pos=None):
         al, fl = stack.attn_layers[l], stack.ffw_layers[l]
         rot = q_pos is not None
         att = mha(al.multihead_attn, stack.num_heads, x, ctx, ctx, q_pos if rot else None, k_pos if rot else None)
-        x = al.norm(x + att)
-        x = fl.norm(x + linear(F.relu(linear(x, fl.linear1.weight, fl.linear1.bias)), fl.linear2.weight, fl.linear2.bias))
+        x = residual_layer_norm(al.norm, x, att)
+        x = residual_layer_norm(fl.norm, x, linear(linear(x, fl.linear1.weight, fl.linear1.bias, relu=True),
+                                                   fl.linear2.weight, fl.linear2.bias))
         outs.append(x)
     return outs
 
@@ -71,7 +72,7 @@ def parallel_stack(stack, x, x_mask, ctx, x_pos=None, ctx_pos=None, sem_pos=None
             q1 = ada_ln(layer.adaln_12, q1, t_emb)
         att = mha(layer.cross_12, heads, q1, ctx, ctx, x_pos if rot else None, ctx_pos if rot else None,
                   dropout_p=p_att)
-        x = layer.norm_12(x + F.dropout(att, dropout, training))
+        x = residual_layer_norm(layer.norm_12, x, F.dropout(att, dropout, training))
         # ---- self attention on seq1 (layers.py:165-182)
         if stack.self_attention:
             qk = x if sem_pos is None else x + sem_pos
@@ -81,11 +82,11 @@ def parallel_stack(stack, x, x_mask, ctx, x_pos=None, ctx_pos=None, sem_pos=None
                 vv = ada_ln(layer.adaln_1, vv, t_emb)
             att = mha(layer.sa1, heads, qk, qk, vv, x_pos if rot else None, x_pos if rot else None,
                       key_padding_mask=x_mask, dropout_p=p_att)
-            x = layer.norm_1(x + F.dropout(att, dropout, training))
+            x = residual_layer_norm(layer.norm_1, x, F.dropout(att, dropout, training))
         # ---- FFN-1 (layers.py:205-209); ffn_12 holds its own Dropout modules
         if stack.apply_ffn:
             y = ada_ln(layer.adaln_ff1, x, t_emb) if ada else x
             ffn = layer.ffn_12                      # Linear, ReLU, Dropout, Linear, Dropout (layers.py:76-82)
-            hid = F.dropout(F.relu(linear(y, ffn[0].weight, ffn[0].bias)), ffn[2].p, training)
-            x = layer.norm_122(y + F.dropout(linear(hid, ffn[3].weight, ffn[3].bias), ffn[4].p, training))
+            hid = F.dropout(linear(y, ffn[0].weight, ffn[0].bias, relu=True), ffn[2].p, training)
+            x = residual_layer_norm(layer.norm_122, y, F.dropout(linear(hid, ffn[3].weight, ffn[3].bias), ffn[4].p, training))
     return x

@@ -236,6 +236,28 @@ size_t a3d_linear_wgrad_workspace(long rows, int out_features, int in_features);
 int a3d_linear_wgrad(const float* dy, const float* x, long rows, int out_features, int in_features, float* dw,
                      float* db, void* workspace, void* stream);
 
+/* The per-token linear layers and LayerNorms of the attention stacks for training (csrc/a3d_train_rows.cu), replacing
+ * the fp32 SIMT GEMMs and ATen LayerNorm kernels autograd issues for them (multihead_custom_attention.py:260-303,452;
+ * layers.py:300-310, 328-332, 146-147, 181-182, 205-209) when rows = batch * tokens is in the tens of thousands.
+ * a3d_linear_fwd: transpose_w = 0: y [rows][O] = x [rows][I] W^T + bias [ReLU if relu], W [O][I] row-major fp32 as
+ *   nn.Linear stores it (bias may be NULL); transpose_w = 1: y [rows][I] = x [rows][O] W, the data gradient of the same
+ *   layer.  Tensor cores with error-compensated fp16 pairs (fp32-class accuracy).  `workspace`: a3d_linear_workspace
+ *   bytes, 16-byte aligned (the weight is re-packed into MMA fragment order on every call: training weights change).
+ *   a3d_linear_supported tells whether a shape is built (even feature counts, contraction length <= 480).
+ * a3d_layernorm_fwd: z = x + res (res and z may be NULL: z = x), y = LayerNorm(z; eps) * gamma + beta over the last
+ *   dimension (embed 60 or 120), mean / rstd [rows] saved for the backward.  a3d_layernorm_bwd: dz [rows][E] (the
+ *   gradient of both x and res), dgamma, dbeta [E] via per-CTA partial sums in `workspace`
+ *   (a3d_layernorm_bwd_workspace bytes) added in a fixed order: deterministic. */
+int a3d_linear_supported(int out_features, int in_features, int transpose_w);
+size_t a3d_linear_workspace(int out_features, int in_features, int transpose_w);
+int a3d_linear_fwd(const float* x, const float* w, const float* bias, long rows, int out_features, int in_features,
+                   int relu, int transpose_w, float* y, void* workspace, void* stream);
+int a3d_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, long rows, int embed,
+                      float eps, float* z, float* y, float* mean, float* rstd, void* stream);
+size_t a3d_layernorm_bwd_workspace(int embed);
+int a3d_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                      long rows, int embed, float* dz, float* dgamma, float* dbeta, void* workspace, void* stream);
+
 /* Position loss of the keypose trainer in one pass.  Replaces the label construction + F.cross_entropy with
  * probability targets of LossAndMetrics._compute_position_loss (main_keypose.py:387-403) for one pyramid level:
  *   label_n = softmax_n(-||ghost_n - gt|| / spread) * (1 - label_smoothing) + label_smoothing / Ng

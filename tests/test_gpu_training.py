@@ -190,7 +190,7 @@ def test_linear_weight_gradient_kernel(rows, o, i):
     w = synth.normal("wg.w", (o, i), 0.1).cuda().requires_grad_(True)
     b = synth.normal("wg.b", (o,), 0.1).cuda().requires_grad_(True)
     xin = x.cuda().view(1, rows, i).requires_grad_(True)
-    y = _Linear.apply(xin, w, b)
+    y = _Linear.apply(xin, w, b, False)
     y.backward(dy.cuda().view(1, rows, o))
     assert rel(w.grad.cpu().double(), want_w) <= 1e-5 and rel(b.grad.cpu().double(), want_b) <= 1e-5
     assert rel(xin.grad.cpu().double()[0], dy.double() @ w.detach().cpu().double()) <= 1e-4
@@ -516,3 +516,53 @@ def test_planner_training_matches_reference_golden():
     loss.backward()
     grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
     assert check_grad_fingerprints(grads, g["grads"], tol=1e-3) >= 200
+
+
+# ------------------------------------------------------------------------------------------------ row-wise kernels
+@pytest.mark.parametrize("rows,o,i", [(5000, 60, 60), (66000, 120, 60), (3001, 480, 120), (3001, 120, 480), (4099, 240, 120)])
+def test_linear_rows_kernel_forward_and_data_gradient(rows, o, i):
+    """a3d_linear_fwd against fp64: y = x W^T + b [ReLU] and the transposed product dx = dy W."""
+    from act3d_chained_diffuser_b200 import lib
+    x = synth.normal("lr.x", (rows, i), 1.0)
+    w = synth.normal("lr.w", (o, i), 0.3)
+    b = synth.normal("lr.b", (o,), 0.5)
+    dy = synth.normal("lr.g", (rows, o), 1.0)
+    want = x.double() @ w.double().t() + b.double()
+    assert lib.linear_supported(o, i) and lib.linear_supported(o, i, transpose=True)
+    got = lib.linear_rows(x.cuda(), w.cuda(), b.cuda())
+    assert rel(got.cpu().double(), want) <= 2e-6
+    got = lib.linear_rows(x.cuda(), w.cuda(), b.cuda(), relu=True)
+    assert rel(got.cpu().double(), want.clamp_min(0)) <= 2e-6
+    got = lib.linear_rows(x.cuda(), w.cuda(), None)
+    assert rel(got.cpu().double(), x.double() @ w.double().t()) <= 2e-6
+    dx = lib.linear_rows(dy.cuda(), w.cuda(), transpose=True)
+    assert rel(dx.cpu().double(), dy.double() @ w.double()) <= 2e-6
+
+
+@pytest.mark.parametrize("rows,e,with_res", [(4099, 60, True), (66000, 60, False), (3001, 120, True), (2049, 120, False)])
+def test_layernorm_kernels(rows, e, with_res):
+    from act3d_chained_diffuser_b200.autograd_ops import residual_layer_norm
+    norm = torch.nn.LayerNorm(e)
+    with torch.no_grad():
+        norm.weight.copy_(1 + synth.normal("ln.w", (e,), 0.2))
+        norm.bias.copy_(synth.normal("ln.b", (e,), 0.2))
+    x = synth.normal("ln.x", (2, rows // 2 + 1, e), 1.5)[:, : rows // 2]
+    res = synth.normal("ln.r", tuple(x.shape), 0.7) if with_res else None
+    g = synth.normal("ln.g", tuple(x.shape), 1.0)
+    ref = torch.nn.LayerNorm(e).double()
+    ref.load_state_dict(norm.state_dict())
+    xr = x.double().clone().requires_grad_(True)
+    rr = res.double().clone().requires_grad_(True) if with_res else None
+    want = ref(xr if rr is None else xr + rr)
+    want.backward(g.double())
+    norm = norm.cuda()
+    xc = x.cuda().requires_grad_(True)
+    rc = res.cuda().requires_grad_(True) if with_res else None
+    got = residual_layer_norm(norm, xc, rc)
+    got.backward(g.cuda())
+    assert rel(got.detach().cpu().double(), want.detach()) <= 2e-6
+    assert rel(xc.grad.cpu().double(), xr.grad) <= 1e-5
+    if with_res:
+        assert torch.equal(rc.grad, xc.grad)
+    assert rel(norm.weight.grad.cpu().double(), ref.weight.grad) <= 1e-5
+    assert rel(norm.bias.grad.cpu().double(), ref.bias.grad) <= 1e-5
