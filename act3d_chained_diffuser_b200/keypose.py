@@ -142,13 +142,20 @@ class Act3D(nn.Module):
         if self._graph_counter_buf is not None:
             self._graph_counter_buf.zero_()
 
+    def ensure_sampler_counter(self, device):
+        """Allocate the device-side call counter.  Must happen BEFORE a capture starts: allocated inside one, its
+        zero-fill would be part of the graph and every replay would draw the same ghost points."""
+        if self._graph_counter_buf is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("Act3D.ensure_sampler_counter(device) must be called before the CUDA-graph capture starts")
+            self._graph_counter_buf = torch.zeros(1, dtype=torch.int64, device=device)
+
     @contextlib.contextmanager
     def device_sampler_counter(self, device):
         """While a CUDA graph of a forward is being captured the sampler's call counter must live on the device:
         inside this scope every draw is keyed on (seed, level + device counter), and leaving the scope appends the
         kernel that advances the counter -- so each replay of the graph draws fresh ghost points."""
-        if self._graph_counter_buf is None:
-            self._graph_counter_buf = torch.zeros(1, dtype=torch.int64, device=device)
+        self.ensure_sampler_counter(device)
         self._graph_counter = self._graph_counter_buf
         try:
             yield
@@ -174,19 +181,21 @@ class Act3D(nn.Module):
                                 total_timesteps, n, self._sampler_seed, sid, device, counter=ctr)
 
     # ------------------------------------------------------------------ visual trunk
-    def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras, staged=None):
-        """backbone + FPN (PyTorch) and the point pyramid (kernel).  Unlike act3d.py:359-392 no
-        rotary table is built here: angles are evaluated inside the K/V kernel for the tokens that
-        are actually attended to."""
-        b = visible_rgb.shape[0]
-        rgb = visible_rgb.reshape(b * num_cameras, *visible_rgb.shape[2:])
+    def _trunk(self, visible_rgb):
+        """backbone + FPN (PyTorch / cuDNN): (B, ncam, 3, H, W) -> ({level name: feature map}, {level name: deferred bias})."""
+        rgb = visible_rgb.reshape(-1, *visible_rgb.shape[2:])
         if self.training or not self.fold_trunk or not isinstance(self.backbone, torch.nn.Module) \
                 or isinstance(self.backbone, torch.nn.Identity):
-            feats, feat_bias = self.feature_pyramid(self.backbone(normalize_images(self.normalize, rgb))), {}
-        else:
-            feats, feat_bias = self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
-                                                needed=self.feature_map_pyramid[:self.num_sampling_level],
-                                                defer_bias=True)
+            return self.feature_pyramid(self.backbone(normalize_images(self.normalize, rgb))), {}
+        return self._eval_trunk(self.normalize, self.backbone, self.feature_pyramid, rgb,
+                                needed=self.feature_map_pyramid[:self.num_sampling_level], defer_bias=True)
+
+    def _compute_visual_features(self, visible_rgb, visible_pcd, num_cameras, staged=None, trunk_out=None):
+        """backbone + FPN (PyTorch) and the point pyramid (kernel).  Unlike act3d.py:359-392 no
+        rotary table is built here: angles are evaluated inside the K/V kernel for the tokens that
+        are actually attended to.  ``trunk_out``: result of an earlier ``_trunk`` call on the same images."""
+        b = visible_rgb.shape[0]
+        feats, feat_bias = trunk_out if trunk_out is not None else self._trunk(visible_rgb)
         if staged is not None:      # point clouds were uploaded on the copy stream while the backbone ran
             torch.cuda.current_stream().wait_stream(self._side_stream)
             visible_pcd = staged[0]
@@ -211,6 +220,9 @@ class Act3D(nn.Module):
         Returns the reference's output dict (act3d.py:340-357).
         """
         staged = None
+        if (not visible_rgb.is_cuda and self.use_cuda_graph and not torch.is_grad_enabled() and self._graph_ok()
+                and next(self.parameters()).is_cuda):
+            return self._forward_graphed(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
         if not visible_rgb.is_cuda:
             # Host inputs (e.g. straight from a DataLoader with pin_memory): upload here, images first so that the
             # backbone starts while the point clouds / instruction are still crossing PCIe on the copy stream.
@@ -232,25 +244,31 @@ class Act3D(nn.Module):
                 torch.cuda.current_stream().wait_stream(self._side_stream)
                 visible_pcd, instruction, curr_gripper, gt_action = staged
             return self._forward_train(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
-        if (self.use_cuda_graph and staged is None and self._teacher_positions is None and self._profile_events is None
-                and "_sample_ghost_points" not in self.__dict__ and not torch.cuda.is_current_stream_capturing()):
+        if self.use_cuda_graph and staged is None and self._graph_ok():
             return self._forward_graphed(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action)
         return self._forward_infer(visible_rgb, visible_pcd, instruction, curr_gripper, gt_action, staged)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the inference forward
+    def _graph_ok(self):
+        return (self._teacher_positions is None and self._profile_events is None
+                and "_sample_ghost_points" not in self.__dict__ and not torch.cuda.is_current_stream_capturing())
+
     def _forward_graphed(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action):
-        """The forward has no host synchronisation (sampler, top-k, argmax all stay on the device), so the ~150 launches
+        """The forward has no host synchronisation (sampler, top-k, argmax all stay on the device), so the ~140 launches
         of one call are captured once per (input shapes, parameter versions, sampler seed) and replayed.  Ghost points
-        stay fresh: the sampler's call counter lives on the device and is advanced inside the graph."""
+        stay fresh: the sampler's call counter lives on the device and is advanced inside the graph.
+        Two graphs share one memory pool: the trunk (needs the images only) and everything after it -- with HOST inputs
+        the images are uploaded first, the trunk graph starts, and the point clouds / instruction / gripper cross PCIe
+        on the copy stream underneath it, exactly like the eager staged path."""
         inputs = [visible_rgb, visible_pcd, instruction, curr_gripper, gt_action]
+        dev = next(self.parameters()).device
         key = (tuple(tuple(t.shape) + (str(t.dtype),) if t is not None else None for t in inputs), self.training,
-               str(visible_rgb.device), self._sampler_seed, self.overlap_query,
+               str(dev), self._sampler_seed, self.overlap_query,
                tuple(p._version for p in self.parameters()), tuple(bf._version for bf in self.buffers()))
         entry = self._graphs.get(key)
         if entry is None:
-            dev = visible_rgb.device
-            static_in = [t.detach().clone() if t is not None else None for t in inputs]
-            main = torch.cuda.current_stream()
+            static_in = [t.detach().to(dev, copy=True) if t is not None else None for t in inputs]
+            main = torch.cuda.current_stream(dev)
             warm = torch.cuda.Stream(device=dev)
             warm.wait_stream(main)
             with torch.cuda.stream(warm):              # cuDNN autotuning, weight packing, kernel attributes: outside the capture
@@ -258,17 +276,33 @@ class Act3D(nn.Module):
                     self._forward_infer(*static_in, None)
             main.wait_stream(warm)
             torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), self.device_sampler_counter(dev):
-                out = self._forward_infer(*static_in, None)
+            self.ensure_sampler_counter(dev)
+            g_trunk, g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_trunk):
+                trunk_out = self._trunk(static_in[0])
+            with torch.cuda.graph(g_rest, pool=g_trunk.pool()), self.device_sampler_counter(dev):
+                out = self._forward_infer(*static_in, None, trunk_out)
             if len(self._graphs) >= 4:                 # bounded: a graph pins its activations (hundreds of MB at batch 16)
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[key] = (graph, static_in, out)
-        graph, static_in, out = entry
-        for dst, src in zip(static_in, inputs):
-            if src is not None:
-                dst.copy_(src, non_blocking=True)
-        graph.replay()
+            entry = self._graphs[key] = (g_trunk, g_rest, static_in, out, trunk_out)
+        g_trunk, g_rest, static_in, out, _ = entry
+        main = torch.cuda.current_stream(dev)
+        static_in[0].copy_(visible_rgb, non_blocking=True)
+        if visible_rgb.is_cuda:
+            for dst, src in zip(static_in[1:], inputs[1:]):
+                if src is not None:
+                    dst.copy_(src, non_blocking=True)
+            g_trunk.replay()
+        else:
+            copy = self._side_stream
+            copy.wait_stream(main)                     # after the images (PCIe is not shared) and after the previous replay
+            with torch.cuda.stream(copy):
+                for dst, src in zip(static_in[1:], inputs[1:]):
+                    if src is not None:
+                        dst.copy_(src, non_blocking=True)
+            g_trunk.replay()
+            main.wait_stream(copy)
+        g_rest.replay()
         keep = ("visible_rgb_features_pyramid", "visible_pcd_pyramid")      # large: returned as views of the static buffers
 
         def own(v):
@@ -279,14 +313,15 @@ class Act3D(nn.Module):
             return v
         return {k: (v if k in keep else own(v)) for k, v in out.items()}
 
-    def _forward_infer(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action=None, staged=None):
+    def _forward_infer(self, visible_rgb, visible_pcd, instruction, curr_gripper, gt_action=None, staged=None,
+                       trunk_out=None):
         e, h = self.embedding_dim, self.num_attn_heads
         b, ncam, _, height, width = visible_rgb.shape
         dev = visible_rgb.device
         gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None
         grip_xyz = curr_gripper[:, :3].float()
 
-        feats_pyr, pcd_pyr = self._compute_visual_features(visible_rgb, visible_pcd, ncam, staged)
+        feats_pyr, pcd_pyr = self._compute_visual_features(visible_rgb, visible_pcd, ncam, staged, trunk_out)
         if staged is not None:
             visible_pcd, instruction, curr_gripper, gt_action = staged
             gt_position = gt_action[:, :3].unsqueeze(1).detach().float() if gt_action is not None else None

@@ -71,6 +71,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
+        if hasattr(model, "ensure_sampler_counter"):
+            model.ensure_sampler_counter(dev)          # allocated outside the capture (its zero-fill must not be replayed)
         scope = model.device_sampler_counter(dev) if hasattr(model, "device_sampler_counter") else _null()
         with torch.cuda.graph(self.graph):
             with scope:

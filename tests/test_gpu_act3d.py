@@ -206,3 +206,15 @@ def test_cuda_graph_replay_matches_eager_and_draws_fresh_ghost_points():
     with torch.no_grad():
         e2 = m(*args2)
     assert torch.equal(g2["position"], e2["position"]) and len(m._graphs) == 1
+    # HOST inputs (pinned) through the graphs: images first, the rest on the copy stream under the trunk graph
+    host = [t.cpu().pin_memory() for t in args2]
+    m.use_cuda_graph = True
+    m.seed_ghost_sampler(5)
+    with torch.no_grad():
+        m(*host)                                                  # captures a second entry? no: same shapes, same key
+        m.seed_ghost_sampler(5)
+        h2 = m(*host)
+    torch.cuda.synchronize()
+    assert len(m._graphs) == 1
+    assert torch.equal(h2["position"], e2["position"]) and torch.equal(h2["rotation"], e2["rotation"])
+    assert torch.equal(h2["ghost_pcd_masks_pyramid"][2][-1], e2["ghost_pcd_masks_pyramid"][2][-1])

@@ -307,6 +307,36 @@ def test_act3d_training_step_reduces_loss():
     assert losses[-1] < losses[0], losses
 
 
+def test_graphed_train_step_replays_a_whole_step():
+    """train_graph.GraphedTrainStep: forward + keypose loss + backward + capturable AdamW captured in one CUDA graph.
+    Every replay advances the device-side sampler counter (fresh ghost points), updates the parameters and lowers the
+    loss on a fixed batch; parameters unreachable from the loss are frozen first."""
+    from act3d_chained_diffuser_b200.losses import keypose_loss
+    from act3d_chained_diffuser_b200.train_graph import GraphedTrainStep, freeze_parameters_without_gradient
+    m, kw = _act3d(True, num_ghost_points=3 * 128)
+    m = m.cuda().train()
+    m.seed_ghost_sampler(3)
+    inp = {k: v.cuda() for k, v in cases.act3d_inputs(batch=2, ncam=1, seed=8).items()}
+    gt = torch.cat([synth.points_in_bounds("tr.gt3", (2,), 8), torch.nn.functional.normalize(torch.ones(2, 4), dim=-1),
+                    torch.ones(2, 1)], -1).cuda()
+    batch = (inp["visible_rgb"], inp["visible_pcd"], inp["instruction"], inp["curr_gripper"], gt)
+
+    def step_loss(net, rgb, pcd, instr, grip, action):
+        return sum(keypose_loss(net(rgb, pcd, instr, grip, gt_action=action), action).values())
+
+    frozen = freeze_parameters_without_gradient(m, lambda net: step_loss(net, *batch))
+    assert all(not dict(m.named_parameters())[n].requires_grad for n in frozen)
+    step = GraphedTrainStep(m, step_loss, lambda ps: torch.optim.AdamW(ps, lr=1e-3, capturable=True), batch, warmup=3)
+    m.seed_ghost_sampler(3)
+    before = [p.detach().clone() for p in m.parameters() if p.requires_grad]
+    losses = [step(*batch).item() for _ in range(8)]
+    assert int(m._graph_counter_buf.item()) == 8 * m.num_sampling_level          # the counter is advanced by the graph itself
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0], losses
+    assert len(set(losses)) == len(losses)                                        # no two replays saw the same ghost points
+    changed = sum(int(not torch.equal(a, b)) for a, b in zip(before, (p for p in m.parameters() if p.requires_grad)))
+    assert changed >= 0.9 * len(before)
+
+
 # ------------------------------------------------------------------------------------------------ planner
 def _planner(**over):
     from model import DiffusionPlanner
