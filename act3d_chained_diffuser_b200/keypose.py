@@ -109,6 +109,9 @@ class Act3D(nn.Module):
                                             # the big feature / point pyramids of the returned dict then alias static buffers
                                             # that the next call overwrites
         self._graphs = {}
+        self.upload_chunks = 1              # use_cuda_graph with HOST inputs: pieces the image upload / trunk are pipelined in
+                                            # (measured at C2: 1 piece 12.73 ms, 2: 12.96, 4: 14.10, 8: 15.25 -- the trunk loses more
+                                            # on small batches than the overlap wins; profiles/r2_e2e_chunks.jsonl)
         self.train_channels_last = True     # training forward: backbone + FPN on channels-last activations
         self._trunk_nhwc = False
         self._graph_counter = None          # device call counter of the ghost sampler while a graph is being captured
@@ -262,45 +265,69 @@ class Act3D(nn.Module):
         on the copy stream underneath it, exactly like the eager staged path."""
         inputs = [visible_rgb, visible_pcd, instruction, curr_gripper, gt_action]
         dev = next(self.parameters()).device
+        host = not visible_rgb.is_cuda
+        bsz = visible_rgb.shape[0]
+        # host inputs: the images cross PCIe in `chunks` pieces and the trunk runs piece by piece behind them
+        chunks = max(1, min(int(self.upload_chunks), bsz)) if host else 1
         key = (tuple(tuple(t.shape) + (str(t.dtype),) if t is not None else None for t in inputs), self.training,
-               str(dev), self._sampler_seed, self.overlap_query,
+               str(dev), self._sampler_seed, self.overlap_query, chunks,
                tuple(p._version for p in self.parameters()), tuple(bf._version for bf in self.buffers()))
         entry = self._graphs.get(key)
         if entry is None:
             static_in = [t.detach().to(dev, copy=True) if t is not None else None for t in inputs]
+            bounds = [(bsz * c) // chunks for c in range(chunks + 1)]
+            pieces = [static_in[0][lo:hi] for lo, hi in zip(bounds[:-1], bounds[1:])]
             main = torch.cuda.current_stream(dev)
             warm = torch.cuda.Stream(device=dev)
             warm.wait_stream(main)
             with torch.cuda.stream(warm):              # cuDNN autotuning, weight packing, kernel attributes: outside the capture
                 for _ in range(2):
                     self._forward_infer(*static_in, None)
+                    if chunks > 1:
+                        for piece in pieces:
+                            self._trunk(piece)
             main.wait_stream(warm)
             torch.cuda.synchronize(dev)
             self.ensure_sampler_counter(dev)
-            g_trunk, g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_trunk):
-                trunk_out = self._trunk(static_in[0])
-            with torch.cuda.graph(g_rest, pool=g_trunk.pool()), self.device_sampler_counter(dev):
+            g_trunks, trunk_outs, pool = [], [], None
+            for piece in pieces:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    trunk_outs.append(self._trunk(piece))
+                pool = g.pool()
+                g_trunks.append(g)
+            g_rest = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_rest, pool=pool), self.device_sampler_counter(dev):
+                if chunks > 1:                         # per-piece feature maps -> one batch (a 0.1 ms copy at C2)
+                    feats = {k: torch.cat([t[0][k] for t in trunk_outs]) for k in trunk_outs[0][0]}
+                    trunk_out = (feats, trunk_outs[0][1])
+                else:
+                    trunk_out = trunk_outs[0]
                 out = self._forward_infer(*static_in, None, trunk_out)
             if len(self._graphs) >= 4:                 # bounded: a graph pins its activations (hundreds of MB at batch 16)
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[key] = (g_trunk, g_rest, static_in, out, trunk_out)
-        g_trunk, g_rest, static_in, out, _ = entry
+            entry = self._graphs[key] = (g_trunks, g_rest, static_in, out, trunk_outs, pieces, bounds)
+        g_trunks, g_rest, static_in, out, _, pieces, bounds = entry
         main = torch.cuda.current_stream(dev)
-        static_in[0].copy_(visible_rgb, non_blocking=True)
-        if visible_rgb.is_cuda:
-            for dst, src in zip(static_in[1:], inputs[1:]):
+        if not host:
+            for dst, src in zip(static_in, inputs):
                 if src is not None:
                     dst.copy_(src, non_blocking=True)
-            g_trunk.replay()
+            g_trunks[0].replay()
         else:
             copy = self._side_stream
-            copy.wait_stream(main)                     # after the images (PCIe is not shared) and after the previous replay
-            with torch.cuda.stream(copy):
+            copy.wait_stream(main)                     # the previous replay may still read the static buffers
+            landed = []
+            with torch.cuda.stream(copy):              # one stream = one PCIe order: image pieces first, then the rest
+                for piece, lo, hi in zip(pieces, bounds[:-1], bounds[1:]):
+                    piece.copy_(visible_rgb[lo:hi], non_blocking=True)
+                    landed.append(copy.record_event())
                 for dst, src in zip(static_in[1:], inputs[1:]):
                     if src is not None:
                         dst.copy_(src, non_blocking=True)
-            g_trunk.replay()
+            for g, ev in zip(g_trunks, landed):
+                main.wait_event(ev)
+                g.replay()
             main.wait_stream(copy)
         g_rest.replay()
         keep = ("visible_rgb_features_pyramid", "visible_pcd_pyramid")      # large: returned as views of the static buffers
