@@ -28,13 +28,14 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
 }
-// two consecutive elements -> packed half2 words for the hi and lo planes
+// two consecutive elements -> packed half2 words for the hi and lo planes (packed conversions: cvt.rn.f16x2.f32 is one
+// F2FP on the ALU pipe, the scalar cvt.rn.f16.f32 a quarter-rate F2F; same round-to-nearest results)
 __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __half h0, l0, h1, l1;
-    split_h(x0, h0, l0);
-    split_h(x1, h1, l1);
-    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 h2 = __floats2half2_rn(x0, x1);
+    const float2 f = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((x0 - f.x) * kLoScale, (x1 - f.y) * kLoScale);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
 // acc[nt][4] (+)= A[m0 .. m0+16, 0 .. 16*KSTEPS) * W^T[:, n tiles nt0 .. nt0+NT)

@@ -50,10 +50,11 @@ __device__ __forceinline__ uint32_t drop_bits(uint64_t seed, uint64_t idx) {    
     return (uint32_t)(z >> 32);
 }
 
+// packed conversions (cvt.rn.f16x2.f32 = one F2FP on the ALU pipe); the scalar cvt.rn.f16.f32 is a quarter-rate F2F
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-    const __half al = __float2half_rn((a - __half2float(ah)) * 2048.f), bl = __float2half_rn((b - __half2float(bh)) * 2048.f);
-    const __half2 h2 = __halves2half2(ah, bh), l2 = __halves2half2(al, bl);
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);
     hi = *reinterpret_cast<const uint32_t*>(&h2);
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
