@@ -433,14 +433,37 @@ __global__ void __launch_bounds__(256) gather_tokens_nhwc_kernel(const float* __
     const int b = blockIdx.y;
     const int r0 = blockIdx.x * 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int rr = wid; rr < 32; rr += 8) {
-        const int r = r0 + rr;
-        if (r >= k) break;
-        const int s = idx ? __ldg(idx + (long)b * k + r) : r;
-        const float* src = feat + ((long)b * ncam * hw + s) * E;
+    // a warp owns rows r0 + wid + {0, 8, 16, 24}: all four index loads first, then all feature / point loads in flight
+    // at once, then the stores (one dependent round trip per CTA instead of two per row)
+    constexpr int NC = (E + 31) / 32;
+    int s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + wid + 8 * j;
+        s[j] = (r < k) ? (idx ? __ldg(idx + (long)b * k + r) : r) : -1;
+    }
+    float v[4][NC], p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long row = (long)b * ncam * hw + (s[j] >= 0 ? s[j] : 0);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            v[j][i] = __ldg(feat + row * E + (c < E ? c : 0));
+        }
+        p[j] = __ldg(pcd + row * 3 + (lane < 3 ? lane : 0));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (s[j] < 0) continue;
+        const int r = r0 + wid + 8 * j;
         float* dst = tok + ((long)b * tok_rows + r) * E;
-        for (int c = lane; c < E; c += 32) dst[c] = bias ? __fadd_rn(__ldg(src + c), __ldg(bias + c)) : __ldg(src + c);
-        if (lane < 3) pos[((long)b * tok_rows + r) * 3 + lane] = __ldg(pcd + ((long)b * ncam * hw + s) * 3 + lane);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < E) dst[c] = bias ? __fadd_rn(v[j][i], __ldg(bias + c)) : v[j][i];
+        }
+        if (lane < 3) pos[((long)b * tok_rows + r) * 3 + lane] = p[j];
     }
 }
 
