@@ -44,7 +44,9 @@ int a3d_abi_version(void);
  *                 tcgen05 kernel (attention only on tcgen05; kept as A/B reference), 6 = a3d_xattn6.cu.
  *   "xattn6_np":  how many of the 16 score pairs a thread of a3d_xattn6.cu exponentiates per unit go through the FMA-pipe
  *                 polynomial instead of the MUFU unit: 0, 4, 6 (default, fastest measured), 7, 8, 9, 10.
- *   "xattn_poly": the same knob of the round-1 kernels (of every 8 scores): 0 (default), 2, 3 or 4. */
+ *   "xattn_poly": the same knob of the round-1 kernels (of every 8 scores): 0 (default), 2, 3 or 4.
+ *   "train_attn_core": a3d_attn_fwd / a3d_attn_bwd: 0 (default) = tensor cores (csrc/a3d_train_mma.cu), 1 = fp32 CUDA cores.
+ *   "cd_prefetch_tiles": cd_denoise_loop: K/V tiles prefetched into L2 ahead of the ring, 0 (default, fastest measured) .. 64. */
 int a3d_set_option(const char* name, int value);
 /* Test / diagnostics counters kept on the current device; the call SYNCHRONISES the device (it is not part of the
  * hot path).  "xattn_replays": attention layers that a CTA of a3d_xattn_stack's tcgen05 kernels replayed in safe mode
@@ -196,8 +198,9 @@ int a3d_counter_add(uint64_t* counter, uint64_t inc, void* stream);
  * Training path (fp32, gradients).  The reference trains both models through autograd over the eager
  * attention (multihead_custom_attention.py:157-462), which materialises the (B*H, Nq, Nk) scores, the
  * softmax and their gradients.  These entry points are the attention core and its backward without that
- * tensor; projections / LayerNorm / FFN around them stay torch.nn ops in the training path
- * (act3d_chained_diffuser_b200/autograd_ops.py, train_layers.py).  head_dim 15 (embed == 15 * heads).
+ * tensor; the many-row projections / LayerNorms around them are a3d_linear_fwd / a3d_linear_wgrad / a3d_layernorm_*
+ * below, the rest stays torch.nn ops (act3d_chained_diffuser_b200/autograd_ops.py, train_layers.py).
+ * head_dim 15 (embed == 15 * heads).
  *
  * a3d_attn_fwd: o = dropout(softmax(q k^T + key_mask)) v per head.  q / o [B][Nq][E], k / v [B][Nk][E]
  *   (head h = columns 15h .. 15h+14, the reference's head split :355-359; q already scaled by 15^-1/2 and
